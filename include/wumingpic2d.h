@@ -1,0 +1,151 @@
+/*
+ * wumingpic2d.h -- C ABI of the B200-native per-timestep PIC hot path.
+ *
+ * This is the drop-in boundary for WumingPIC2D's hot-path module procedures
+ * (Fortran 90, no existing C/FFI layer).  Each entry point names the reference
+ * procedure it replaces (file:line relative to the reference tree); the Fortran
+ * ISO_C_BINDING shim that binds them under the reference's own module/procedure
+ * names is in fortran/ and INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns 0 on success, non-zero
+ *    on error, with the message available from wm_last_error() (the reference
+ *    does `write + stop`, e.g. common/particle.f90:63-66; the shim does the same).
+ *  - host arrays use the reference's Fortran (column-major) layout, per rank:
+ *      up,gp  real(8) (6, np, nys:nye, nsp)           proj/weibel/app.f90:281-282
+ *      uf     real(8) (6, nxgs-2:nxge+2, nys-2:nye+2) proj/weibel/app.f90:280
+ *      uj     real(8) (3, nxgs-2:nxge+2, nys-2:nye+2) common/field.f90:108
+ *      np2    integer (nys:nye, nsp)                  proj/weibel/app.f90:278
+ *      cumcnt integer (nxgs:nxge+1, nys:nye, nsp)     proj/weibel/app.f90:279
+ *      mom    real(8) (7, nxgs-1:nxge+1, nys-1:nye+1, nsp) proj/weibel/app.f90:283
+ *  - device state is authoritative between calls ("resident" mode).  The library
+ *    owns all device memory including the CG warm-start `df` that the reference
+ *    keeps as a SAVE variable (common/field.f90:98).
+ *  - one context = one GPU = one y-slab (common/mpi_set.f90:36-47).  Not re-entrant
+ *    per context; contexts are independent.
+ *  - there is no CPU fallback: every entry point fails if no CUDA device is usable.
+ */
+#ifndef WUMINGPIC2D_H
+#define WUMINGPIC2D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WM_NSP_MAX 2
+#define WM_UNIQUE_ID_BYTES 128
+
+/* boundary plugin (the module chosen by `use ... => bc__*` in proj/<problem>/app.f90:6-13) */
+enum { WM_BC_PERIODIC = 0 };
+
+/* flags */
+enum {
+  WM_FLAG_EXACT_PUSH = 1, /* push arithmetic without FMA contraction, IEEE sqrt/div in the
+                             reference's operation order: bit-identical to the CPU path   */
+  WM_FLAG_DETERMINISTIC = 2 /* reserved */
+};
+
+/* All scalars the reference passes to particle__init (common/particle.f90:18),
+ * field__init (common/field.f90:22), sort__init (common/sort.f90:16),
+ * boundary_periodic__init (common/boundary_periodic.f90:26), mom_calc__init
+ * (common/mom_calc.f90:18) and mpi_set__init (common/mpi_set.f90:19). */
+typedef struct wm_config {
+  int32_t ndim;             /* 6 */
+  int32_t np;               /* host row capacity of up/gp (second dimension) */
+  int32_t nsp;              /* 2 */
+  int32_t nxgs, nxge, nygs, nyge; /* global cell index range */
+  int32_t nys, nye;         /* this rank's rows */
+  int32_t nrank, nsize;     /* rank / number of ranks (ring: nup=nrank+1, ndown=nrank-1, periodic) */
+  int32_t bc;               /* WM_BC_* */
+  int32_t device;           /* CUDA device ordinal, -1 = current */
+  int32_t flags;            /* WM_FLAG_* */
+  double delx, delt, c, gfac;
+  double q[WM_NSP_MAX], r[WM_NSP_MAX];
+  int64_t capacity;         /* device particle capacity per species; 0 = 1.25 x (np2 total at upload) */
+} wm_config;
+
+typedef struct wm_ctx wm_ctx;
+
+const char *wm_last_error(void);
+int wm_version(void);
+
+/* ---- life cycle ------------------------------------------------------------------ */
+/* the six *__init calls of proj/weibel/app.f90:331-347 */
+int wm_create(const wm_config *cfg, wm_ctx **out);
+int wm_destroy(wm_ctx *ctx);
+
+/* Communicator for nsize > 1 (replaces MPI_COMM_WORLD of common/mpi_set.f90:25-28):
+ * rank 0 calls wm_comm_unique_id, the host broadcasts the 128 bytes by any means,
+ * every rank calls wm_comm_init.  NCCL send/recv + all-reduce over NVLink. */
+int wm_comm_unique_id(void *id128);
+int wm_comm_init(wm_ctx *ctx, const void *id128);
+
+/* ---- residency: the only points where host arrays are read / written -------------- */
+/* `up` need not be sorted: rows are taken as lists of np2(j,isp) records and bucket-
+ * sorted on the device exactly like sort__bucket (common/sort.f90:36). */
+int wm_upload_particles(wm_ctx *ctx, const double *up, const int32_t *np2);
+/* `up` is already cell-sorted with a consistent cumcnt (the reference's loop invariant
+ * at the top of a step): plain transposition, no sort. */
+int wm_upload_particles_sorted(wm_ctx *ctx, const double *up, const int32_t *np2, const int32_t *cumcnt);
+int wm_upload_field(wm_ctx *ctx, const double *uf);
+/* sorted state -> up (rows, cell-sorted), np2, cumcnt; any may be NULL */
+int wm_download_particles(wm_ctx *ctx, double *up, int32_t *np2, int32_t *cumcnt);
+/* the post-push / post-boundary buffer (`gp` in the reference) in the slot order of the
+ * sorted state; valid after wm_particle__solv and until wm_sort__bucket */
+int wm_download_gp(wm_ctx *ctx, double *gp);
+int wm_download_field(wm_ctx *ctx, double *uf);
+int wm_download_current(wm_ctx *ctx, double *uj);  /* uj after the last deposit / bc */
+int wm_download_dfield(wm_ctx *ctx, double *df);   /* df (CG warm start + last dE) */
+/* per-species active particle counts on this rank */
+int wm_particle_counts(wm_ctx *ctx, int64_t *n);
+
+/* ---- the hot path, device resident, one call per reference procedure --------------- */
+int wm_particle__solv(wm_ctx *ctx);        /* particle__solv  common/particle.f90:48        */
+int wm_field__ele_cur(wm_ctx *ctx);        /* ele_cur only    common/field.f90:189 (testing) */
+int wm_boundary__curre(wm_ctx *ctx);       /* bc__curre       common/boundary_periodic.f90:357 (testing) */
+int wm_field__fdtd_i(wm_ctx *ctx);         /* field__fdtd_i   common/field.f90:66 (incl. ele_cur, bc__curre, cgm, bc__dfield) */
+int wm_boundary__particle_x(wm_ctx *ctx);  /* bc__particle_x  common/boundary_periodic.f90:61 */
+int wm_boundary__particle_y(wm_ctx *ctx);  /* bc__particle_y  common/boundary_periodic.f90:99 */
+int wm_sort__bucket(wm_ctx *ctx);          /* sort__bucket    common/sort.f90:36             */
+/* the five calls above fused: push + deposit + particle boundaries in one kernel,
+ * then the field solve, then the scatter pass (proj/weibel/app.f90:100-107) */
+int wm_step(wm_ctx *ctx, int32_t nsteps);
+
+/* ---- the same, with HOST arrays (drop-in signatures; copies inside the call) -------- */
+/* One full time step on host arrays: on entry `up` is cell-sorted with `cumcnt`
+ * consistent (as after sort__bucket); on exit the same holds for the new state. */
+int wm_host_step(wm_ctx *ctx, double *up, double *uf, int32_t *np2, int32_t *cumcnt);
+/* particle__solv(gp,up,uf,cumcnt,nxs,nxe)   common/particle.f90:48 */
+int wm_host_particle__solv(wm_ctx *ctx, double *gp, const double *up, const double *uf,
+                           const int32_t *cumcnt, const int32_t *np2);
+/* sort__bucket(gp_out,up_in,cumcnt,np2,nxs,nxe)  common/sort.f90:36 (first argument is the output) */
+int wm_host_sort__bucket(wm_ctx *ctx, double *gp_out, const double *up_in, int32_t *cumcnt,
+                         const int32_t *np2);
+
+/* ---- diagnostics ------------------------------------------------------------------- */
+int wm_cg_iters(wm_ctx *ctx, int32_t out[3]);  /* CG iterations of the last solve, l=1..3 */
+/* energy_history (proj/weibel/app.f90:479-545), this rank's share:
+ * out[0..nsp-1] kinetic, out[nsp] = sum E^2/8pi, out[nsp+1] = sum B^2/8pi */
+int wm_energy(wm_ctx *ctx, double *out);
+/* mom_calc__accl + mom_calc__nvt + bc__mom (common/mom_calc.f90:48,167;
+ * common/boundary_periodic.f90:571) -> host mom */
+int wm_moments(wm_ctx *ctx, double *mom);
+
+/* Synthetic uniform Maxwellian of proj/weibel/app.f90:380-474 generated on the device
+ * with the counter-based RNG documented in DESIGN.md (same stream definition as the
+ * test oracle; Box-Muller in device libm, so velocities agree to a few ulp only). */
+int wm_ic_weibel(wm_ctx *ctx, uint64_t seed, int32_t n0, double vti, double vte, double t_ani, double b0);
+
+/* ---- measurement hooks ----------------------------------------------------------- */
+/* device milliseconds (CUDA events on the context's stream) accumulated per stage by
+ * wm_step since the last reset: [0] push+deposit+boundary kernel, [1] field solve,
+ * [2] exchange+scan, [3] scatter pass, [4] whole step; launches = kernels launched */
+int wm_timing(wm_ctx *ctx, double ms[5], int64_t *launches, int32_t reset);
+int wm_synchronize(wm_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

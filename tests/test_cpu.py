@@ -1,0 +1,100 @@
+"""CPU tests (-m "not gpu"): the oracle against invariants, and that the C-ABI library loads and
+exports every symbol include/wumingpic2d.h declares (no compute calls without a GPU)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from helpers import flatten_by_id, make_world
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(wmlib):
+    hdr = open(os.path.join(ROOT, "include", "wumingpic2d.h")).read()
+    names = set(re.findall(r"\b(wm_[a-z_0-9]+)\s*\(", hdr))
+    assert len(names) >= 30
+    for n in sorted(names):
+        assert hasattr(wmlib, n), "libwumingpic2d.so does not export " + n
+    from wumingpic2d_b200.api import EXPORTS
+    assert names == set(EXPORTS)
+
+
+def test_no_cpu_fallback(wmlib):
+    """Without a device the product path must fail loudly, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import wumingpic2d_b200 as wm
+    prm = O.weibel_params(16, 16, 2)
+    with pytest.raises(wm.WmError, match="no CUDA device"):
+        wm.Context.from_params(prm)
+
+
+def test_product_does_not_reference_oracle():
+    for d, _, files in os.walk(os.path.join(ROOT, "wumingpic2d_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                src = open(os.path.join(d, f)).read()
+                for needle in ("oracle_lib", "wm_oracle", "orc_", "oracle/", "import oracle", "from oracle"):
+                    assert needle not in src, "%s references the test oracle (%s)" % (f, needle)
+
+
+def test_oracle_gauss_law_and_energy():
+    """Discrete Gauss law holds to roundoff through deposit + field solve + boundaries + sort;
+    total energy stays within 1e-3 over 40 steps (implicit scheme, gfac=0.501)."""
+    prm, w = make_world(32, 32, 10)
+    e0 = w.energy().sum()
+    r0, s0 = w.gauss_residual()
+    assert r0 <= 1e-13 * s0
+    for _ in range(4):
+        w.step(10)
+        r, s = w.gauss_residual()
+        assert r <= 1e-12 * s
+        assert all(1 <= k < 100 for k in w.cg_iters())
+    assert abs(w.energy().sum() - e0) <= 1e-3 * e0
+    cnt = w.cell_counts()
+    assert cnt.sum() == 2 * 32 * 32 * 10
+    w.close()
+
+
+def test_oracle_sort_invariants():
+    prm, w = make_world(24, 12, 6, steps=5)
+    up, np2, cum = w.array(0, O.UP), w.array(0, O.NP2), w.array(0, O.CUMCNT)
+    for isp in range(2):
+        for jl in range(12):
+            n = np2[isp, jl]
+            xs = up[isp, jl, :n, 0].astype(np.int64) - 2
+            ys = up[isp, jl, :n, 1].astype(np.int64) - 2
+            assert np.all(ys == jl)
+            assert np.all(np.diff(xs) >= 0)
+            assert np.array_equal(np.bincount(xs, minlength=24), np.diff(cum[isp, jl]))
+            assert cum[isp, jl, 0] == 0 and cum[isp, jl, -1] == n
+    w.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 4])
+def test_oracle_nrank_equals_one_rank(nranks):
+    """The y-slab decomposition (common/mpi_set.f90:36-47) does not change the answer."""
+    _, w1 = make_world(32, 30, 8, steps=12)
+    _, wn = make_world(32, 30, 8, nranks=nranks, steps=12)
+    i1, s1, r1 = w1.particles_by_id()
+    i2, s2, r2 = wn.particles_by_id()
+    assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
+    assert np.abs(r1 - r2).max() <= 1e-12
+    assert np.abs(w1.global_field() - wn.global_field()).max() <= 1e-13
+    assert np.array_equal(w1.cell_counts(), wn.cell_counts())
+    assert w1.cg_iters() == wn.cg_iters()
+    w1.close(); wn.close()
+
+
+def test_oracle_rng_is_decomposition_independent():
+    _, w1 = make_world(16, 16, 4)
+    _, w4 = make_world(16, 16, 4, nranks=4)
+    a, b = w1.particles_by_id(), w4.particles_by_id()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    u = a[2][:, 2:]
+    assert abs(u[:, 0].std() - 0.1) < 5e-3 and abs(u[:, 2].std() - 0.5) < 2.5e-2
+    w1.close(); w4.close()

@@ -1,0 +1,269 @@
+"""Parity of the CUDA hot path (through the C ABI) against the CPU oracle.  -m gpu.
+
+Tolerances (BASELINE.json north_star): per-cell counts bit-exact; x, y, u matched by
+particle ID, J and E/B <= 1e-12 relative after one step (J/E/B relative to each component's
+max-abs, conditional on equal CG iteration counts); with WM_FLAG_EXACT_PUSH the push is
+bit-identical to the oracle.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from helpers import flatten_by_id, make_world, oracle_state, particle_err, rel_to_max
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def ctx_for(prm, **kw):
+    import wumingpic2d_b200 as wm
+    return wm.Context.from_params(prm, **kw)
+
+
+@pytest.fixture(scope="module")
+def warm():
+    """A 48x24 Weibel world advanced 6 steps: non-trivial fields, particles off their IC lattice.
+    nx is not a multiple of the 16-cell tile and ny not of 8: partial tiles are exercised."""
+    prm, w = make_world(48 + 8, 24 + 4, 12, steps=6)
+    return prm, w
+
+
+def test_upload_sort_roundtrip(warm):
+    """wm_upload_particles == sort__bucket (common/sort.f90:36): cumcnt bit-exact, rows hold the
+    same records bit for bit."""
+    prm, w = warm
+    s = oracle_state(w)
+    c = ctx_for(prm)
+    rng = np.random.default_rng(1)
+    up = s["up"].copy()
+    for isp in range(up.shape[0]):  # shuffle every row: arbitrary order in, sorted out
+        for jl in range(up.shape[1]):
+            n = s["np2"][isp, jl]
+            up[isp, jl, :n] = up[isp, jl, rng.permutation(n)]
+    c.upload_particles(up, s["np2"])
+    out, np2, cum = c.download_particles()
+    assert np.array_equal(np2, s["np2"])
+    assert np.array_equal(cum, s["cumcnt"])
+    a, b = flatten_by_id(out, np2), flatten_by_id(s["up"], s["np2"])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    # cell invariant: int(x) is the cell the slot belongs to
+    for isp in range(out.shape[0]):
+        for jl in range(out.shape[1]):
+            xs = out[isp, jl, :np2[isp, jl], 0].astype(np.int64) - prm["nxgs"]
+            assert np.array_equal(np.bincount(xs, minlength=prm["nx"]), np.diff(cum[isp, jl]))
+            assert np.all(np.diff(xs) >= 0)
+    c.close()
+
+
+def test_host_sort_bucket_matches_oracle(warm):
+    prm, _ = warm
+    _, w = make_world(prm["nx"], prm["ny"], prm["n0"], steps=3)
+    w.particle_solv(); w.field_fdtd_i(); w.bc_particle_x(); assert w.bc_particle_y() == 0
+    s = oracle_state(w)           # gp is now an unsorted set of row lists
+    w.sort_bucket()
+    ref = oracle_state(w)
+    c = ctx_for(prm)
+    out = np.zeros_like(s["gp"]); cum = np.zeros_like(s["cumcnt"])
+    c.host_sort__bucket(out, s["gp"], cum, s["np2"])
+    assert np.array_equal(cum, ref["cumcnt"])
+    a, b = flatten_by_id(out, s["np2"]), flatten_by_id(ref["up"], ref["np2"])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    c.close()
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_push(warm, exact):
+    """particle__solv (common/particle.f90:48): same slot order, so compare slot by slot."""
+    import wumingpic2d_b200 as wm
+    prm, w0 = warm
+    s = oracle_state(w0)
+    _, w = make_world(prm["nx"], prm["ny"], prm["n0"], steps=6)
+    w.particle_solv()
+    ref = w.array(0, O.GP)
+    c = ctx_for(prm, flags=wm.WM_FLAG_EXACT_PUSH if exact else 0)
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    c.upload_field(s["uf"])
+    c.particle__solv()
+    gp = c.download_gp()
+    for isp in range(gp.shape[0]):
+        for jl in range(gp.shape[1]):
+            n = s["np2"][isp, jl]
+            a, b = gp[isp, jl, :n], ref[isp, jl, :n]
+            assert np.array_equal(a[:, 5].view(np.int64), b[:, 5].view(np.int64))
+            if exact:
+                assert np.array_equal(a, b), "EXACT push must be bit-identical to the CPU path"
+            else:
+                ex, eu = particle_err(a[:, :5], b[:, :5], prm["nx"], prm["vte"])
+                assert ex <= TOL and eu <= TOL
+    c.close()
+
+
+def test_deposit_and_field_solve(warm):
+    """ele_cur (field.f90:189), bc__curre, then the whole field__fdtd_i (field.f90:66)."""
+    import wumingpic2d_b200 as wm
+    prm, w0 = warm
+    s = oracle_state(w0)
+    _, w = make_world(prm["nx"], prm["ny"], prm["n0"], steps=6)
+    w.particle_solv()
+    w.ele_cur()
+    uj_raw = w.array(0, O.UJ).copy()
+    w.bc_curre()
+    uj_bc = w.array(0, O.UJ).copy()
+    c = ctx_for(prm, flags=wm.WM_FLAG_EXACT_PUSH)
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    c.upload_field(s["uf"])
+    # bring the CG warm start (the reference's SAVEd df) to the same state: run the same history
+    c2 = None
+    c.particle__solv()
+    c.field__ele_cur()
+    assert rel_to_max(c.download_current(), uj_raw).max() <= TOL
+    c.bc__curre()
+    assert rel_to_max(c.download_current(), uj_bc).max() <= TOL
+    c.close()
+
+
+def test_stage_calls_one_step(warm):
+    """The five calls of proj/weibel/app.f90:102-107 one by one, from the same history (so the CG
+    warm start df matches), against the oracle."""
+    import wumingpic2d_b200 as wm
+    prm, _ = warm
+    _, w = make_world(prm["nx"], prm["ny"], prm["n0"])
+    s = oracle_state(w)
+    c = ctx_for(prm, flags=wm.WM_FLAG_EXACT_PUSH)
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    c.upload_field(s["uf"])
+    for it in range(4):
+        w.step(1)
+        c.particle__solv(); c.field__fdtd_i(); c.bc__particle_x(); c.bc__particle_y(); c.sort__bucket()
+        assert c.cg_iters() == w.cg_iters()
+        uf = c.download_field()
+        assert rel_to_max(uf, w.array(0, O.UF)).max() <= TOL
+        up, np2, cum = c.download_particles()
+        assert np.array_equal(cum, w.array(0, O.CUMCNT)), "per-cell counts must be bit-exact"
+        a, b = flatten_by_id(up, np2), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+        ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+        assert ex <= TOL and eu <= TOL
+    c.close()
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_fused_step_matches_oracle(exact):
+    """wm_step (push+deposit+boundary fused, field solve, scatter) against the oracle, config-1-like
+    physics (proj/weibel/config_sample.json scaled down)."""
+    import wumingpic2d_b200 as wm
+    prm, w = make_world(64, 32, 20)
+    s = oracle_state(w)
+    c = ctx_for(prm, flags=wm.WM_FLAG_EXACT_PUSH if exact else 0)
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    c.upload_field(s["uf"])
+    w.step(1)
+    c.step(1)
+    assert c.cg_iters() == w.cg_iters()
+    assert rel_to_max(c.download_field(), w.array(0, O.UF)).max() <= TOL
+    assert rel_to_max(c.download_current(), w.array(0, O.UJ)).max() <= TOL
+    up, np2, cum = c.download_particles()
+    assert np.array_equal(cum, w.array(0, O.CUMCNT)), "per-cell counts must be bit-exact"
+    a, b = flatten_by_id(up, np2), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
+    assert np.array_equal(a[0], b[0])
+    if exact:
+        assert np.array_equal(a[2], b[2]), "first step from identical fields: bit-identical particles"
+    ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+    assert ex <= TOL and eu <= TOL
+    # a few more steps: still within tolerance (errors grow slowly before chaos sets in)
+    w.step(4)
+    c.step(4)
+    up, np2, cum = c.download_particles()
+    a, b = flatten_by_id(up, np2), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
+    ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+    assert ex <= 1e-10 and eu <= 1e-10
+    assert rel_to_max(c.download_field(), w.array(0, O.UF)).max() <= 1e-10
+    c.close()
+
+
+def test_gauss_law_and_energy_history():
+    """Discrete charge conservation (div E - 4 pi rho constant to roundoff) and the energy history
+    of proj/weibel/app.f90:479-545 over 100 steps against the oracle."""
+    prm, w = make_world(64, 64, 10)
+    s = oracle_state(w)
+    c = ctx_for(prm)
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    c.upload_field(s["uf"])
+    e0 = c.energy()
+    assert np.allclose(e0, w.energy(), rtol=1e-13, atol=0)
+    for _ in range(4):
+        w.step(25)
+        c.step(25)
+        eg, eo = c.energy(), w.energy()
+        assert abs(eg.sum() - eo.sum()) <= 1e-9 * eo.sum()
+        # load the device state into a scratch oracle world to evaluate the Gauss residual
+        up, np2, cum = c.download_particles()
+        g = O.World(prm)
+        g.array(0, O.UP)[...] = up
+        g.array(0, O.NP2)[...] = np2
+        g.array(0, O.UF)[...] = c.download_field()
+        res, scale = g.gauss_residual()
+        assert res <= 1e-12 * scale
+        g.close()
+    c.close()
+
+
+def test_host_step_dropin():
+    """wm_host_step: one step on host arrays in the reference's layout (the e2e path)."""
+    prm, w = make_world(32, 16, 8)
+    s = oracle_state(w)
+    c = ctx_for(prm)
+    up, uf, np2, cum = s["up"].copy(), s["uf"].copy(), s["np2"].copy(), s["cumcnt"].copy()
+    for _ in range(3):
+        w.step(1)
+        c.host_step(up, uf, np2, cum)
+    assert np.array_equal(cum, w.array(0, O.CUMCNT))
+    assert rel_to_max(uf, w.array(0, O.UF)).max() <= 1e-11
+    a, b = flatten_by_id(up, np2), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
+    assert np.array_equal(a[0], b[0])
+    ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+    assert ex <= 1e-11 and eu <= 1e-11
+    c.close()
+
+
+def test_moments_match_oracle(warm):
+    prm, w0 = warm
+    s = oracle_state(w0)
+    _, w = make_world(prm["nx"], prm["ny"], prm["n0"], steps=6)
+    w.mom_accl(); w.mom_nvt(); w.bc_mom()
+    c = ctx_for(prm)
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    c.upload_field(s["uf"])
+    mom = c.moments()
+    ref = w.array(0, O.MOM)
+    # interior nodes only: ghosts hold pre-fold partial sums in both implementations
+    assert rel_to_max(mom[:, 1:-1, 1:-1], ref[:, 1:-1, 1:-1]).max() <= 1e-12
+    c.close()
+
+
+def test_device_ic_matches_oracle_ic():
+    """wm_ic_weibel uses the oracle's stream definition: positions bit-identical, velocities to a few
+    ulp (device libm), analytic cumcnt identical."""
+    prm, w = make_world(32, 16, 8)
+    c = ctx_for(prm)
+    c.ic_weibel(20260117, prm["n0"], prm["vti"], prm["vte"], prm["t_ani"], prm["b0"])
+    up, np2, cum = c.download_particles()
+    assert np.array_equal(cum, w.array(0, O.CUMCNT)) and np.array_equal(np2, w.array(0, O.NP2))
+    a, b = flatten_by_id(up, np2), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
+    assert np.array_equal(a[0], b[0])
+    assert np.array_equal(a[2][:, :2], b[2][:, :2])
+    assert np.abs(a[2][:, 2:] - b[2][:, 2:]).max() <= 1e-14
+    c.close()
+
+
+def test_call_order_is_enforced(warm):
+    import wumingpic2d_b200 as wm
+    prm, w = warm
+    c = ctx_for(prm)
+    with pytest.raises(wm.WmError):
+        c.particle__solv()          # nothing uploaded
+    s = oracle_state(w)
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    with pytest.raises(wm.WmError):
+        c.sort__bucket()            # boundary not applied yet
+    c.close()

@@ -1,0 +1,275 @@
+"""ctypes binding of include/wumingpic2d.h.
+
+Method names follow the reference's Fortran module procedures (module__procedure), so a
+driver loop reads like proj/weibel/app.f90:100-107:
+
+    ctx.particle__solv(); ctx.field__fdtd_i(); ctx.bc__particle_x(); ctx.bc__particle_y();
+    ctx.sort__bucket()
+
+Host arrays are numpy float64/int32 buffers in the reference's Fortran layout (see the header).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+WM_NSP_MAX = 2
+WM_BC_PERIODIC = 0
+WM_FLAG_EXACT_PUSH = 1
+
+
+class WmError(RuntimeError):
+    pass
+
+
+class WmConfig(C.Structure):
+    _fields_ = [
+        ("ndim", C.c_int32), ("np", C.c_int32), ("nsp", C.c_int32),
+        ("nxgs", C.c_int32), ("nxge", C.c_int32), ("nygs", C.c_int32), ("nyge", C.c_int32),
+        ("nys", C.c_int32), ("nye", C.c_int32), ("nrank", C.c_int32), ("nsize", C.c_int32),
+        ("bc", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32),
+        ("delx", C.c_double), ("delt", C.c_double), ("c", C.c_double), ("gfac", C.c_double),
+        ("q", C.c_double * WM_NSP_MAX), ("r", C.c_double * WM_NSP_MAX),
+        ("capacity", C.c_int64),
+    ]
+
+
+def library_path():
+    return os.path.join(HERE, "libwumingpic2d.so")
+
+
+_lib = None
+
+EXPORTS = [
+    "wm_last_error", "wm_version", "wm_create", "wm_destroy", "wm_comm_unique_id", "wm_comm_init",
+    "wm_upload_particles", "wm_upload_particles_sorted", "wm_upload_field", "wm_download_particles",
+    "wm_download_gp", "wm_download_field", "wm_download_current", "wm_download_dfield",
+    "wm_particle_counts", "wm_particle__solv", "wm_field__ele_cur", "wm_boundary__curre",
+    "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_sort__bucket",
+    "wm_step", "wm_host_step", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
+    "wm_energy", "wm_moments", "wm_ic_weibel", "wm_timing", "wm_synchronize",
+]
+
+
+def _preload_nccl():
+    """libwumingpic2d.so needs libnccl.so.2.  PyTorch bundles a newer NCCL under the same soname; if
+    the system copy were loaded first, a later `import torch` in the same process would bind to it
+    and miss symbols.  So load the torch-bundled copy first when there is one (the ABI we use --
+    comm init, send/recv, all-reduce, groups -- is stable across 2.x)."""
+    import sys
+    for d in sys.path:
+        cand = os.path.join(d, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return cand
+            except OSError:
+                pass
+    return None
+
+
+def load_library():
+    """Load libwumingpic2d.so; raises if it has not been built (python -m wumingpic2d_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise WmError("%s not found: build it with `python -m wumingpic2d_b200.build` "
+                      "(there is no CPU fallback)" % path)
+    _preload_nccl()
+    lib = C.CDLL(path)
+    P, D, I32 = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    lib.wm_last_error.restype = C.c_char_p
+    lib.wm_create.argtypes = [C.POINTER(WmConfig), C.POINTER(P)]
+    lib.wm_destroy.argtypes = [P]
+    lib.wm_comm_unique_id.argtypes = [C.c_void_p]
+    lib.wm_comm_init.argtypes = [P, C.c_void_p]
+    lib.wm_upload_particles.argtypes = [P, D, I32]
+    lib.wm_upload_particles_sorted.argtypes = [P, D, I32, I32]
+    lib.wm_upload_field.argtypes = [P, D]
+    lib.wm_download_particles.argtypes = [P, D, I32, I32]
+    lib.wm_download_gp.argtypes = [P, D]
+    lib.wm_download_field.argtypes = [P, D]
+    lib.wm_download_current.argtypes = [P, D]
+    lib.wm_download_dfield.argtypes = [P, D]
+    lib.wm_particle_counts.argtypes = [P, C.POINTER(C.c_int64)]
+    for n in ("wm_particle__solv", "wm_field__ele_cur", "wm_boundary__curre", "wm_field__fdtd_i",
+              "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_sort__bucket", "wm_synchronize"):
+        getattr(lib, n).argtypes = [P]
+    lib.wm_step.argtypes = [P, C.c_int32]
+    lib.wm_host_step.argtypes = [P, D, D, I32, I32]
+    lib.wm_host_particle__solv.argtypes = [P, D, D, D, I32, I32]
+    lib.wm_host_sort__bucket.argtypes = [P, D, D, I32, I32]
+    lib.wm_cg_iters.argtypes = [P, I32]
+    lib.wm_energy.argtypes = [P, D]
+    lib.wm_moments.argtypes = [P, D]
+    lib.wm_ic_weibel.argtypes = [P, C.c_uint64, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]
+    lib.wm_timing.argtypes = [P, D, C.POINTER(C.c_int64), C.c_int32]
+    _lib = lib
+    return lib
+
+
+def _d(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(a):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class Context:
+    """One GPU = one y-slab.  Constructor arguments are those of the reference's *__init calls
+    (proj/weibel/app.f90:331-347) plus the ring position of common/mpi_set.f90."""
+
+    def __init__(self, *, np_cap, nxgs, nxge, nygs, nyge, nys, nye, delx, delt, c, q, r, gfac,
+                 ndim=6, nsp=2, nrank=0, nsize=1, bc=WM_BC_PERIODIC, device=-1, flags=0, capacity=0):
+        self.lib = load_library()
+        g = WmConfig()
+        g.ndim, g.np, g.nsp = ndim, np_cap, nsp
+        g.nxgs, g.nxge, g.nygs, g.nyge, g.nys, g.nye = nxgs, nxge, nygs, nyge, nys, nye
+        g.nrank, g.nsize, g.bc, g.device, g.flags = nrank, nsize, bc, device, flags
+        g.delx, g.delt, g.c, g.gfac = delx, delt, c, gfac
+        for s in range(nsp):
+            g.q[s] = q[s]
+            g.r[s] = r[s]
+        g.capacity = capacity
+        self.cfg = g
+        self.h = C.c_void_p()
+        self._ck(self.lib.wm_create(C.byref(g), C.byref(self.h)))
+        self.nx, self.nyl, self.nsp, self.np_cap = nxge - nxgs + 1, nye - nys + 1, nsp, np_cap
+
+    @classmethod
+    def from_params(cls, prm, nys=None, nye=None, nrank=0, **kw):
+        """prm: dict with nx, ny, np, nsp, delx, delt, c, gfac, q, r (and optionally nxgs, nygs)."""
+        nxgs, nygs = prm.get("nxgs", 2), prm.get("nygs", 2)
+        nyge = nygs + prm["ny"] - 1
+        return cls(np_cap=prm["np"], nxgs=nxgs, nxge=nxgs + prm["nx"] - 1, nygs=nygs, nyge=nyge,
+                   nys=nygs if nys is None else nys, nye=nyge if nye is None else nye,
+                   delx=prm["delx"], delt=prm["delt"], c=prm["c"], q=prm["q"], r=prm["r"],
+                   gfac=prm["gfac"], nsp=prm["nsp"], nrank=nrank, **kw)
+
+    def _ck(self, rc):
+        if rc:
+            raise WmError(self.lib.wm_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None) and self.h:
+            self.lib.wm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- shapes of the host arrays (C order = reversed Fortran order)
+    def shape_up(self): return (self.nsp, self.nyl, self.np_cap, 6)
+    def shape_uf(self): return (self.nyl + 4, self.nx + 4, 6)
+    def shape_uj(self): return (self.nyl + 4, self.nx + 4, 3)
+    def shape_np2(self): return (self.nsp, self.nyl)
+    def shape_cumcnt(self): return (self.nsp, self.nyl, self.nx + 1)
+    def shape_mom(self): return (self.nsp, self.nyl + 2, self.nx + 3, 7)
+
+    # ---- communicator
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self._ck(self.lib.wm_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, id128):
+        self._ck(self.lib.wm_comm_init(self.h, C.c_char_p(id128)))
+
+    # ---- residency
+    def upload_particles(self, up, np2): self._ck(self.lib.wm_upload_particles(self.h, _d(up), _i(np2)))
+    def upload_particles_sorted(self, up, np2, cumcnt):
+        self._ck(self.lib.wm_upload_particles_sorted(self.h, _d(up), _i(np2), _i(cumcnt)))
+    def upload_field(self, uf): self._ck(self.lib.wm_upload_field(self.h, _d(uf)))
+
+    def download_particles(self, up=None, want_up=True):
+        if up is None and want_up:
+            up = np.zeros(self.shape_up())
+        np2 = np.zeros(self.shape_np2(), np.int32)
+        cum = np.zeros(self.shape_cumcnt(), np.int32)
+        self._ck(self.lib.wm_download_particles(self.h, _d(up), _i(np2), _i(cum)))
+        return up, np2, cum
+
+    def download_gp(self):
+        gp = np.zeros(self.shape_up())
+        self._ck(self.lib.wm_download_gp(self.h, _d(gp)))
+        return gp
+
+    def download_field(self):
+        uf = np.zeros(self.shape_uf())
+        self._ck(self.lib.wm_download_field(self.h, _d(uf)))
+        return uf
+
+    def download_current(self):
+        uj = np.zeros(self.shape_uj())
+        self._ck(self.lib.wm_download_current(self.h, _d(uj)))
+        return uj
+
+    def download_dfield(self):
+        df = np.zeros(self.shape_uf())
+        self._ck(self.lib.wm_download_dfield(self.h, _d(df)))
+        return df
+
+    def particle_counts(self):
+        n = (C.c_int64 * WM_NSP_MAX)()
+        self._ck(self.lib.wm_particle_counts(self.h, n))
+        return [n[s] for s in range(self.nsp)]
+
+    # ---- the reference's module procedures, device resident
+    def particle__solv(self): self._ck(self.lib.wm_particle__solv(self.h))
+    def field__ele_cur(self): self._ck(self.lib.wm_field__ele_cur(self.h))
+    def bc__curre(self): self._ck(self.lib.wm_boundary__curre(self.h))
+    def field__fdtd_i(self): self._ck(self.lib.wm_field__fdtd_i(self.h))
+    def bc__particle_x(self): self._ck(self.lib.wm_boundary__particle_x(self.h))
+    def bc__particle_y(self): self._ck(self.lib.wm_boundary__particle_y(self.h))
+    def sort__bucket(self): self._ck(self.lib.wm_sort__bucket(self.h))
+    def step(self, n=1): self._ck(self.lib.wm_step(self.h, n))
+
+    # ---- host-array (drop-in) calls
+    def host_step(self, up, uf, np2, cumcnt):
+        self._ck(self.lib.wm_host_step(self.h, _d(up), _d(uf), _i(np2), _i(cumcnt)))
+
+    def host_particle__solv(self, gp, up, uf, cumcnt, np2):
+        self._ck(self.lib.wm_host_particle__solv(self.h, _d(gp), _d(up), _d(uf), _i(cumcnt), _i(np2)))
+
+    def host_sort__bucket(self, gp_out, up_in, cumcnt, np2):
+        self._ck(self.lib.wm_host_sort__bucket(self.h, _d(gp_out), _d(up_in), _i(cumcnt), _i(np2)))
+
+    # ---- diagnostics
+    def cg_iters(self):
+        out = (C.c_int32 * 3)()
+        self._ck(self.lib.wm_cg_iters(self.h, out))
+        return list(out)
+
+    def energy(self):
+        out = (C.c_double * (self.nsp + 2))()
+        self._ck(self.lib.wm_energy(self.h, out))
+        return np.array(list(out))
+
+    def moments(self):
+        mom = np.zeros(self.shape_mom())
+        self._ck(self.lib.wm_moments(self.h, _d(mom)))
+        return mom
+
+    def ic_weibel(self, seed, n0, vti, vte, t_ani, b0):
+        self._ck(self.lib.wm_ic_weibel(self.h, seed, n0, vti, vte, t_ani, b0))
+
+    def timing(self, reset=True):
+        ms = (C.c_double * 5)()
+        n = C.c_int64()
+        self._ck(self.lib.wm_timing(self.h, ms, C.byref(n), int(reset)))
+        return list(ms), n.value
+
+    def synchronize(self): self._ck(self.lib.wm_synchronize(self.h))

@@ -1,0 +1,52 @@
+"""Builds libwumingpic2d.so (CUDA kernels + C ABI) in-tree with nvcc for sm_100a.
+
+    python -m wumingpic2d_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The .so is git-ignored but travels with the tree.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libwumingpic2d.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# field kernels keep the reference's unfused operation order; particle kernels use FMA
+UNITS = [("particle_kernels.cu", []), ("field_kernels.cu", ["-fmad=false"]), ("wm_api.cu", [])]
+
+
+def _newer(a, b):
+    return not os.path.exists(b) or os.path.getmtime(a) > os.path.getmtime(b)
+
+
+def build(force=False, verbose=False):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    hdrs = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".h")]
+    hdrs.append(os.path.join(os.path.dirname(HERE), "include", "wumingpic2d.h"))
+    objs, rebuilt = [], False
+    os.makedirs(os.path.join(HERE, "_obj"), exist_ok=True)
+    for src, extra in UNITS:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(HERE, "_obj", src.replace(".cu", ".o"))
+        if force or _newer(s, o) or any(_newer(h, o) for h in hdrs):
+            cmd = [nvcc] + ARCH + COMMON + extra + ["-c", s, "-o", o]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            with open(o + ".log", "w") as f:
+                f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed on " + src)
+            if verbose:
+                sys.stderr.write(r.stderr)
+            rebuilt = True
+        objs.append(o)
+    if rebuilt or not os.path.exists(OUT):
+        cmd = [nvcc] + ARCH + ["-shared", "-o", OUT] + objs + ["-lnccl", "-lcudart"]
+        subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

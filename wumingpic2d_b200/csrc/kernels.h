@@ -1,0 +1,59 @@
+// kernels.h -- launch wrappers of the device kernels (particle_kernels.cu, field_kernels.cu)
+#pragma once
+#include "wm_internal.h"
+
+namespace wm {
+
+enum { M_PUSH = 1, M_DEPOSIT = 2, M_BOUND = 4, M_EXACT = 8, M_NOMOVE = 16 };
+
+// ---- particles
+void launch_pass1(int mode, const DevParams &P, const Pass1Args &a, cudaStream_t st);
+void launch_pass2(const DevParams &P, const PartSoA &src, const PartSoA &dst, const int *cstart_old,
+                  const int *cstart_new, const int *tilebase, const uint32_t *tag, unsigned *err, cudaStream_t st);
+int scan_scratch_ints(int n);
+int launch_scan(const int *in, int *out, int *scratch, int n, cudaStream_t st);
+void launch_incoming_tag(const DevParams &P, const double *rec, int n, int isp, int *gcnt, int *rank, unsigned *err,
+                         cudaStream_t st);
+void launch_incoming_scatter(const DevParams &P, const double *rec, int n, int isp, const int *cstart_new,
+                             const int *rank, const PartSoA &dst, unsigned *err, cudaStream_t st);
+void launch_aos2soa(const double *rec, long long n, size_t so, const PartSoA &dst, cudaStream_t st);
+void launch_soa2aos(const PartSoA &src, size_t so, long long n, double *rec, cudaStream_t st);
+void launch_bcx(const DevParams &P, double *x, const int *cstart, cudaStream_t st);
+void launch_ic_weibel(const DevParams &P, const PartSoA &dst, int *cstart, uint64_t seed, int n0, double vti,
+                      double vte, double t_ani, cudaStream_t st);
+void launch_kinetic(const DevParams &P, const PartSoA &src, const int *cstart, int isp, double *partial, int nblocks,
+                    cudaStream_t st);
+void launch_moments(const DevParams &P, const PartSoA &src, const int *cstart, double *mom, cudaStream_t st);
+
+// ---- fields
+struct FieldBufs {
+  double *uf, *df, *tmpf;     // AoS6 padded
+  double *uj, *gkl;           // AoS3 padded
+  double *phi, *p, *r, *ap;   // CG vectors, AoS3 padded (b lives in gkl, scaled by f5)
+  double *red;                // reduction scratch: see field_kernels.cu
+  int *cgstate;               // device CG control block
+};
+constexpr int RED_BLOCKS = 592;  // 148 SMs x 4
+
+void launch_tmpf(const DevParams &P, const double *uf, double *tmpf, cudaStream_t st);
+void launch_fill_x(const DevParams &P, double *a, int ncomp, int ng, cudaStream_t st);           // periodic x ghosts (copy)
+void launch_fill_y_local(const DevParams &P, double *a, int ncomp, int ng, cudaStream_t st);     // periodic y ghosts, nsize==1
+void launch_fold_x(const DevParams &P, double *uj, cudaStream_t st);                              // uj x fold + copy back
+void launch_fold_y_local(const DevParams &P, double *uj, cudaStream_t st);                        // uj y fold + refresh, nsize==1
+void launch_add_rows(double *dst, const double *src, long long n, cudaStream_t st);
+void launch_rhs(const DevParams &P, const FieldBufs &f, cudaStream_t st);
+void launch_cg_init(const DevParams &P, const FieldBufs &f, cudaStream_t st);      // phi<-df, b, sum b^2
+void launch_cg_resid0(const DevParams &P, const FieldBufs &f, cudaStream_t st);    // r, p, sum r^2
+void launch_cg_begin(const DevParams &P, const FieldBufs &f, int nranks_reduced, cudaStream_t st);
+void launch_cg_ap(const DevParams &P, const FieldBufs &f, cudaStream_t st);        // ap, sums
+void launch_cg_update(const DevParams &P, const FieldBufs &f, cudaStream_t st);    // phi, r, sum r^2
+void launch_cg_pupdate(const DevParams &P, const FieldBufs &f, cudaStream_t st);   // p
+void launch_cg_finish(const DevParams &P, const FieldBufs &f, cudaStream_t st);    // df(1:3) <- phi
+void launch_efield(const DevParams &P, const FieldBufs &f, cudaStream_t st);       // df(4:6)
+void launch_update_uf(const DevParams &P, const FieldBufs &f, cudaStream_t st);    // uf += df
+void launch_field_energy(const DevParams &P, const double *uf, double *partial, int nblocks, cudaStream_t st);
+size_t cgctl_bytes();
+size_t cgctl_active_offset();       // int active[3]; int ite[3]; int stop  (contiguous)
+size_t cgctl_sums_offset(int which); // 0 sumb, 1 sumr(+sum2 adjacent), 2 sum2, 3 sum1
+
+}  // namespace wm

@@ -1,0 +1,1008 @@
+// wm_api.cu -- host side of the C ABI (include/wumingpic2d.h): context, residency,
+// per-procedure entry points, the fused step, NCCL exchanges on the y ring.
+//
+// The call order of one step follows proj/weibel/app.f90:100-107; what each entry point
+// replaces is cited in the header.  No CPU fallback: everything fails without a device.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace wm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CU(x)                                                                                  \
+  do {                                                                                         \
+    cudaError_t e_ = (x);                                                                      \
+    if (e_ != cudaSuccess) return fail("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #x); \
+  } while (0)
+#define NC(x)                                                                                  \
+  do {                                                                                         \
+    ncclResult_t e_ = (x);                                                                     \
+    if (e_ != ncclSuccess) return fail("NCCL error %s at %s:%d (%s)", ncclGetErrorString(e_), __FILE__, __LINE__, #x); \
+  } while (0)
+#define WM(x)               \
+  do {                      \
+    int e_ = (x);           \
+    if (e_) return e_;      \
+  } while (0)
+
+enum State { ST_EMPTY = 0, ST_SORTED, ST_PUSHED, ST_BOUNDED };
+
+}  // namespace
+
+struct wm_ctx {
+  wm_config cfg;
+  DevParams P;
+  int dev = 0;
+  cudaStream_t st = nullptr, st2 = nullptr;
+  // particles: two SoA stores; `cur` holds the sorted state (the reference's `up`),
+  // the other one is `gp` in stage mode and the scatter target in the fused step
+  double *pbuf[2] = {nullptr, nullptr};
+  PartSoA soa[2];
+  int *cstart[2] = {nullptr, nullptr};
+  int cur = 0;
+  int *gcnt = nullptr, *tilebase = nullptr, *scan_scratch = nullptr;
+  uint32_t *tag = nullptr;
+  State state = ST_EMPTY;
+  // migration on the y ring
+  int sendcap = 0;
+  double *send[2] = {nullptr, nullptr}, *recv[2] = {nullptr, nullptr};
+  int *sendcnt = nullptr, *recvcnt = nullptr;  // device [2][nsp]
+  int *in_rank = nullptr;                      // [2*nsp*sendcap]
+  int *h_cnt = nullptr;                        // pinned [4*nsp]
+  int n_in[2][WM_NSP_MAX] = {{0}};
+  // fields
+  FieldBufs f{};
+  double *rowtmp = nullptr;  // 2 ghost rows x 6 comps (multi-rank fold)
+  double *mom = nullptr;
+  double *partial = nullptr, *h_partial = nullptr;
+  unsigned *d_err = nullptr, *h_err = nullptr;
+  int *h_cg = nullptr;       // pinned copies of CgCtl {active[3], ite[3], stop} x 2
+  cudaEvent_t ev_cg[2] = {nullptr, nullptr};
+  int cg_ite[3] = {0, 0, 0};
+  // comm
+  ncclComm_t comm = nullptr;
+  int nup = 0, ndown = 0;
+  // timing
+  cudaEvent_t ev[6] = {nullptr};
+  double ms[5] = {0, 0, 0, 0, 0};
+  long long launches = 0;
+  bool timing = true;
+};
+
+namespace {
+
+void carve(PartSoA &s, double *base, long long cap, int nsp) {
+  const size_t n = (size_t)cap * nsp;
+  s.x = base;
+  s.y = base + n;
+  s.ux = base + 2 * n;
+  s.uy = base + 3 * n;
+  s.uz = base + 4 * n;
+  s.id = reinterpret_cast<long long *>(base + 5 * n);
+}
+
+int alloc_particles(wm_ctx *c, long long need) {
+  if (c->pbuf[0]) {
+    if (need <= c->P.cap) return 0;
+    return fail("particle capacity %lld exceeded (need %lld); recreate the context with a larger wm_config.capacity", c->P.cap, need);
+  }
+  long long cap = c->cfg.capacity > 0 ? c->cfg.capacity : (long long)std::ceil(1.25 * (double)need) + 1024;
+  if (cap < need) return fail("wm_config.capacity %lld < particles per species %lld", cap, need);
+  cap = (cap + 1) & ~1LL;
+  if (cap >= (1LL << 31) - 1) return fail("more than 2^31 particles per species per GPU are not supported");
+  c->P.cap = cap;
+  const int nsp = c->P.nsp;
+  for (int b = 0; b < 2; b++) {
+    CU(cudaMalloc(&c->pbuf[b], (size_t)cap * nsp * 6 * sizeof(double)));
+    carve(c->soa[b], c->pbuf[b], cap, nsp);
+    CU(cudaMalloc(&c->cstart[b], (size_t)nsp * (c->P.ncell + 1) * sizeof(int)));
+  }
+  CU(cudaMalloc(&c->tag, (size_t)cap * nsp * sizeof(uint32_t)));
+  return 0;
+}
+
+inline size_t host_up_index(const wm_config &g, int isp, int jl) {
+  const int nyl = g.nye - g.nys + 1;
+  return (size_t)6 * ((size_t)g.np * ((size_t)jl + (size_t)nyl * isp));
+}
+
+int check_errors(wm_ctx *c, const char *where) {
+  CU(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  const unsigned e = *c->h_err;
+  if (!e) return 0;
+  CU(cudaMemsetAsync(c->d_err, 0, sizeof(unsigned), c->st));
+  std::string m = std::string(where) + ":";
+  if (e & ERR_MOVED_TOO_FAR) m += " particle moved more than one cell (CFL violated or NaN);";
+  if (e & ERR_CAPACITY) m += " memory over (particle slots exhausted, cf. boundary_periodic.f90:231-234);";
+  if (e & ERR_SENDBUF) m += " migration buffer exhausted;";
+  if (e & ERR_BAD_CELL) m += " particle outside the slab;";
+  if (e & ERR_TAG_RANK) m += " more than 2^24 particles from one tile into one cell;";
+  return fail("%s", m.c_str());
+}
+
+// ---- y-ring exchange of `rows` contiguous grid rows (ncomp doubles per cell) -------------
+// send rows starting at local row lj_send to `to`, receive into rows starting at lj_recv from `from`
+int ring_rows(wm_ctx *c, double *a, int ncomp, int lj_send, int to, int lj_recv, int from, int rows, double *recv_override = nullptr) {
+  const size_t w = (size_t)c->P.pitch * ncomp;
+  double *src = a + (size_t)(lj_send + 2) * w;
+  double *dst = recv_override ? recv_override : a + (size_t)(lj_recv + 2) * w;
+  NC(ncclGroupStart());
+  NC(ncclSend(src, rows * w, ncclDouble, to, c->comm, c->st));
+  NC(ncclRecv(dst, rows * w, ncclDouble, from, c->comm, c->st));
+  NC(ncclGroupEnd());
+  return 0;
+}
+
+// bc__dfield / bc__phi: ghost rows then periodic x ghosts   boundary_periodic.f90:251-354,511-568
+int halo_copy(wm_ctx *c, double *a, int ncomp, int ng, bool do_x) {
+  const int nyl = c->P.nyl;
+  if (c->P.nsize == 1) {
+    launch_fill_y_local(c->P, a, ncomp, ng, c->st);
+    c->launches++;
+  } else {
+    // my first ng rows -> ndown ; nup's first rows land in my upper ghosts
+    WM(ring_rows(c, a, ncomp, 0, c->ndown, nyl, c->nup, ng));
+    // my last ng rows -> nup ; ndown's last rows land in my lower ghosts
+    WM(ring_rows(c, a, ncomp, nyl - ng, c->nup, -ng, c->ndown, ng));
+  }
+  if (do_x) {
+    launch_fill_x(c->P, a, ncomp, ng, c->st);
+    c->launches++;
+  }
+  return 0;
+}
+
+// bc__curre: fold ghost rows into the neighbour, refresh ghosts, x fold   boundary_periodic.f90:357-508
+int bc_curre(wm_ctx *c) {
+  const int nyl = c->P.nyl;
+  double *uj = c->f.uj;
+  if (c->P.nsize == 1) {
+    launch_fold_y_local(c->P, uj, c->st);
+    c->launches++;
+  } else {
+    const size_t w = (size_t)c->P.pitch * 3;
+    // my lower ghosts (nys-2,nys-1) -> ndown ; nup's are added into my nye-1,nye
+    WM(ring_rows(c, uj, 3, -2, c->ndown, 0, c->nup, 2, c->rowtmp));
+    launch_add_rows(uj + (size_t)(nyl - 2 + 2) * w, c->rowtmp, 2 * w, c->st);
+    // my upper ghosts (nye+1,nye+2) -> nup ; ndown's are added into my nys,nys+1
+    WM(ring_rows(c, uj, 3, nyl, c->nup, 0, c->ndown, 2, c->rowtmp));
+    launch_add_rows(uj + (size_t)(0 + 2) * w, c->rowtmp, 2 * w, c->st);
+    c->launches += 2;
+    // refresh: my nys,nys+1 -> ndown (their upper ghosts) ; my nye-1,nye -> nup (their lower ghosts)
+    WM(ring_rows(c, uj, 3, 0, c->ndown, nyl, c->nup, 2));
+    WM(ring_rows(c, uj, 3, nyl - 2, c->nup, -2, c->ndown, 2));
+  }
+  launch_fold_x(c->P, uj, c->st);
+  c->launches++;
+  return 0;
+}
+
+int allreduce_ctl(wm_ctx *c, int which, int n) {
+  if (c->P.nsize == 1) return 0;
+  double *p = reinterpret_cast<double *>(reinterpret_cast<char *>(c->f.cgstate) + cgctl_sums_offset(which));
+  NC(ncclAllReduce(p, p, n, ncclDouble, ncclSum, c->comm, c->st));
+  return 0;
+}
+
+// cgm for l = 1..3 together                                                field.f90:319-461
+int cg_solve(wm_ctx *c) {
+  const DevParams &P = c->P;
+  launch_cg_init(P, c->f, c->st);
+  WM(allreduce_ctl(c, 0, 3));
+  if (P.nsize > 1) WM(halo_copy(c, c->f.phi, 3, 1, false));  // set_boundary_phi(phi)  field.f90:367
+  launch_cg_resid0(P, c->f, c->st);
+  WM(allreduce_ctl(c, 1, 3));
+  launch_cg_begin(P, c->f, P.nsize, c->st);
+  c->launches += 3;
+  char *ctl = reinterpret_cast<char *>(c->f.cgstate) + cgctl_active_offset();
+  const size_t ctl_n = 7 * sizeof(int);
+  int it = 0;
+  bool done = false;
+  for (; it < 101 && !done; it++) {
+    if (P.nsize > 1) WM(halo_copy(c, c->f.p, 3, 1, false));  // set_boundary_phi(p)  field.f90:392
+    launch_cg_ap(P, c->f, c->st);
+    WM(allreduce_ctl(c, 1, 6));
+    launch_cg_update(P, c->f, c->st);
+    WM(allreduce_ctl(c, 3, 3));
+    launch_cg_pupdate(P, c->f, c->st);
+    c->launches += 3;
+    int *h = c->h_cg + (it & 1) * 8;
+    CU(cudaMemcpyAsync(h, ctl, ctl_n, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaEventRecord(c->ev_cg[it & 1], c->st));
+    if (it >= 1) {
+      // look at the previous iteration's flags while this one is in flight
+      CU(cudaEventSynchronize(c->ev_cg[(it - 1) & 1]));
+      const int *hp = c->h_cg + ((it - 1) & 1) * 8;
+      if (!(hp[0] | hp[1] | hp[2])) done = true;
+    }
+  }
+  CU(cudaEventSynchronize(c->ev_cg[(it - 1) & 1]));
+  const int *hl = c->h_cg + ((it - 1) & 1) * 8;
+  for (int l = 0; l < 3; l++) c->cg_ite[l] = hl[3 + l];
+  if (hl[6]) return fail("********** stop at cgm after ite_max ********** (field.f90:427-430)");
+  if (hl[0] | hl[1] | hl[2]) return fail("cgm: internal error, loop ended while a component is still active");
+  launch_cg_finish(P, c->f, c->st);
+  c->launches++;
+  return 0;
+}
+
+// everything of field__fdtd_i after ele_cur                                 field.f90:122-184
+int field_solve(wm_ctx *c) {
+  const DevParams &P = c->P;
+  WM(bc_curre(c));
+  launch_rhs(P, c->f, c->st);
+  c->launches++;
+  WM(cg_solve(c));
+  WM(halo_copy(c, c->f.df, 6, 2, true));
+  launch_efield(P, c->f, c->st);
+  WM(halo_copy(c, c->f.df, 6, 2, true));
+  launch_update_uf(P, c->f, c->st);
+  c->launches += 2;
+  return 0;
+}
+
+Pass1Args p1args(wm_ctx *c, const PartSoA &src, const PartSoA &dst, double delt_push) {
+  Pass1Args a{};
+  a.src = src;
+  a.dst = dst;
+  a.cstart = c->cstart[c->cur];
+  a.tmpf = c->f.tmpf;
+  a.uj = c->f.uj;
+  a.gcnt = c->gcnt;
+  a.tilebase = c->tilebase;
+  a.tag = c->tag;
+  a.send[0] = c->send[0];
+  a.send[1] = c->send[1];
+  a.sendcnt = c->sendcnt;
+  a.sendcap = c->sendcap;
+  a.err = c->d_err;
+  a.delt_push = delt_push;
+  return a;
+}
+
+int zero_sort_state(wm_ctx *c) {
+  CU(cudaMemsetAsync(c->gcnt, 0, (size_t)c->P.nsp * c->P.ncell * sizeof(int), c->st));
+  if (c->P.nsize > 1) CU(cudaMemsetAsync(c->sendcnt, 0, 2 * WM_NSP_MAX * sizeof(int), c->st));
+  return 0;
+}
+
+// ring exchange of the leavers packed by the BOUND pass, then rank the arrivals
+// boundary_periodic.f90:173-189
+int migrate(wm_ctx *c) {
+  const DevParams &P = c->P;
+  if (P.nsize == 1) return 0;
+  if (!c->comm) return fail("nsize > 1 but wm_comm_init has not been called");
+  const int nsp = P.nsp;
+  // counts first (MPI_SENDRECV of cnt, :174,:183)
+  NC(ncclGroupStart());
+  NC(ncclSend(c->sendcnt, nsp, ncclInt, c->ndown, c->comm, c->st));
+  NC(ncclSend(c->sendcnt + nsp, nsp, ncclInt, c->nup, c->comm, c->st));
+  NC(ncclRecv(c->recvcnt, nsp, ncclInt, c->nup, c->comm, c->st));          // nup's down-going
+  NC(ncclRecv(c->recvcnt + nsp, nsp, ncclInt, c->ndown, c->comm, c->st));  // ndown's up-going
+  NC(ncclGroupEnd());
+  CU(cudaMemcpyAsync(c->h_cnt, c->sendcnt, 2 * nsp * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaMemcpyAsync(c->h_cnt + 2 * nsp, c->recvcnt, 2 * nsp * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  for (int k = 0; k < 4 * nsp; k++)
+    if (c->h_cnt[k] > c->sendcap) return fail("migration buffer exhausted (%d > %d records)", c->h_cnt[k], c->sendcap);
+  // payload (MPI_SENDRECV of bff_ptcl, :177,:186)
+  NC(ncclGroupStart());
+  for (int isp = 0; isp < nsp; isp++) {
+    const size_t off = (size_t)isp * c->sendcap * 6;
+    const int sd = c->h_cnt[isp], su = c->h_cnt[nsp + isp];
+    const int ru = c->h_cnt[2 * nsp + isp], rd = c->h_cnt[3 * nsp + isp];
+    if (sd) NC(ncclSend(c->send[0] + off, (size_t)sd * 6, ncclDouble, c->ndown, c->comm, c->st));
+    if (su) NC(ncclSend(c->send[1] + off, (size_t)su * 6, ncclDouble, c->nup, c->comm, c->st));
+    if (ru) NC(ncclRecv(c->recv[0] + off, (size_t)ru * 6, ncclDouble, c->nup, c->comm, c->st));
+    if (rd) NC(ncclRecv(c->recv[1] + off, (size_t)rd * 6, ncclDouble, c->ndown, c->comm, c->st));
+    c->n_in[0][isp] = ru;
+    c->n_in[1][isp] = rd;
+  }
+  NC(ncclGroupEnd());
+  for (int d = 0; d < 2; d++)
+    for (int isp = 0; isp < nsp; isp++) {
+      const size_t off = (size_t)isp * c->sendcap;
+      launch_incoming_tag(P, c->recv[d] + off * 6, c->n_in[d][isp], isp, c->gcnt,
+                          c->in_rank + (size_t)d * nsp * c->sendcap + off, c->d_err, c->st);
+      c->launches++;
+    }
+  return 0;
+}
+
+int scatter_arrivals(wm_ctx *c, int dstbuf) {
+  const DevParams &P = c->P;
+  if (P.nsize == 1) return 0;
+  for (int d = 0; d < 2; d++)
+    for (int isp = 0; isp < P.nsp; isp++) {
+      const size_t off = (size_t)isp * c->sendcap;
+      launch_incoming_scatter(P, c->recv[d] + off * 6, c->n_in[d][isp], isp, c->cstart[dstbuf],
+                              c->in_rank + (size_t)d * P.nsp * c->sendcap + off, c->soa[dstbuf], c->d_err, c->st);
+      c->launches++;
+    }
+  return 0;
+}
+
+int scan_counts(wm_ctx *c, int dstbuf) {
+  for (int isp = 0; isp < c->P.nsp; isp++) {
+    if (launch_scan(c->gcnt + (size_t)isp * c->P.ncell, c->cstart[dstbuf] + (size_t)isp * (c->P.ncell + 1), c->scan_scratch,
+                    c->P.ncell, c->st))
+      return fail("grid too large for the prefix scan");
+    c->launches += 3;
+  }
+  return 0;
+}
+
+int need_state(wm_ctx *c, State s, const char *who) {
+  if (!c) return fail("%s: null context", who);
+  if (c->state != s) {
+    static const char *nm[] = {"EMPTY", "SORTED", "PUSHED", "BOUNDED"};
+    return fail("%s: particle state is %s, expected %s (call order of proj/weibel/app.f90:100-107)", who, nm[c->state], nm[s]);
+  }
+  return 0;
+}
+
+int set_device(wm_ctx *c) {
+  CU(cudaSetDevice(c->dev));
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================ C ABI
+extern "C" {
+
+const char *wm_last_error(void) { return g_err.c_str(); }
+int wm_version(void) { return 100; }
+
+int wm_create(const wm_config *g, wm_ctx **out) {
+  if (!g || !out) return fail("wm_create: null argument");
+  *out = nullptr;
+  if (g->ndim != 6) return fail("wm_create: ndim must be 6 (x,y,ux,uy,uz,id)");
+  if (g->nsp < 1 || g->nsp > WM_NSP_MAX) return fail("wm_create: nsp must be 1..%d", WM_NSP_MAX);
+  if (g->bc != WM_BC_PERIODIC) return fail("wm_create: only the periodic boundary module is implemented");
+  if (g->delx != 1.0) return fail("wm_create: delx must be 1 (common/sort.f90:60 keys on int(x) without /delx; all apps use delx=1)");
+  const int nx = g->nxge - g->nxgs + 1, ny = g->nyge - g->nygs + 1, nyl = g->nye - g->nys + 1;
+  if (nx < 4 || nyl < 2 || ny < nyl) return fail("wm_create: grid too small (nx>=4, rows per rank>=2)");
+  if (g->nsize < 1 || g->nrank < 0 || g->nrank >= g->nsize) return fail("wm_create: bad rank/size");
+  if (g->nxgs < 1 || g->nygs < 1) return fail("wm_create: nxgs, nygs must be >= 1 (int() truncation is used as floor)");
+  if ((long long)nx * nyl >= (1LL << 31) / 4) return fail("wm_create: slab too large");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("wm_create: no CUDA device available (this library has no CPU fallback)");
+  wm_ctx *c = new wm_ctx();
+  c->cfg = *g;
+  if (g->device >= 0) {
+    c->dev = g->device;
+  } else {
+    CU(cudaGetDevice(&c->dev));
+  }
+  CU(cudaSetDevice(c->dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, c->dev));
+  if (prop.major < 10) {
+    const int d = c->dev;
+    delete c;
+    return fail("wm_create: device %d is sm_%d%d; this library is built for sm_100a only", d, prop.major, prop.minor);
+  }
+  DevParams &P = c->P;
+  P.nx = nx;
+  P.nyl = nyl;
+  P.nxgs = g->nxgs;
+  P.nys = g->nys;
+  P.nygs = g->nygs;
+  P.ny = ny;
+  P.nsize = g->nsize;
+  P.pitch = nx + 4;
+  P.ntx = (nx + TX - 1) / TX;
+  P.nty = (nyl + TY - 1) / TY;
+  P.nsp = g->nsp;
+  P.ncell = nx * nyl;
+  P.cap = 0;
+  P.delx = g->delx;
+  P.delt = g->delt;
+  P.c = g->c;
+  P.cc = g->c * g->c;
+  P.inv_cc = 1.0 / P.cc;
+  P.xlen = nx * g->delx;
+  P.ylen = ny * g->delx;
+  for (int s = 0; s < g->nsp; s++) {
+    P.q[s] = g->q[s];
+    P.r[s] = g->r[s];
+  }
+  const double pi = 4.0 * std::atan(1.0);
+  // field.f90:53-57
+  P.f1 = g->c * g->delt / g->delx;
+  P.f2 = g->gfac * P.f1 * P.f1;
+  P.f3 = 4.0 * pi * g->delx / g->c;
+  const double t = g->delx / (g->c * g->delt * g->gfac);
+  P.f4 = 4.0 + t * t;
+  P.f5 = t * t;
+  P.gfac = g->gfac;
+  P.pi4dt = 4. * pi * g->delt;
+  c->nup = (g->nrank == g->nsize - 1) ? 0 : g->nrank + 1;   // mpi_set.f90:44-47
+  c->ndown = (g->nrank == 0) ? g->nsize - 1 : g->nrank - 1;
+
+  CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+  const size_t ng = (size_t)P.pitch * (nyl + 4);
+  CU(cudaMalloc(&c->f.uf, ng * 6 * sizeof(double)));
+  CU(cudaMalloc(&c->f.df, ng * 6 * sizeof(double)));
+  CU(cudaMalloc(&c->f.tmpf, ng * 6 * sizeof(double)));
+  CU(cudaMalloc(&c->f.uj, ng * 3 * sizeof(double)));
+  CU(cudaMalloc(&c->f.gkl, ng * 3 * sizeof(double)));
+  CU(cudaMalloc(&c->f.phi, ng * 3 * sizeof(double)));
+  CU(cudaMalloc(&c->f.p, ng * 3 * sizeof(double)));
+  CU(cudaMalloc(&c->f.r, ng * 3 * sizeof(double)));
+  CU(cudaMalloc(&c->f.ap, ng * 3 * sizeof(double)));
+  CU(cudaMalloc(&c->f.red, (size_t)RED_BLOCKS * 8 * sizeof(double)));
+  CU(cudaMalloc(&c->f.cgstate, cgctl_bytes()));
+  CU(cudaMemset(c->f.cgstate, 0, cgctl_bytes()));
+  for (double *a : {c->f.uf, c->f.df, c->f.tmpf}) CU(cudaMemset(a, 0, ng * 6 * sizeof(double)));  // df=0: field.f90:109-111
+  for (double *a : {c->f.uj, c->f.gkl, c->f.phi, c->f.p, c->f.r, c->f.ap}) CU(cudaMemset(a, 0, ng * 3 * sizeof(double)));
+  CU(cudaMalloc(&c->rowtmp, (size_t)P.pitch * 2 * 6 * sizeof(double)));
+  CU(cudaMalloc(&c->mom, (size_t)7 * (nx + 3) * (nyl + 2) * P.nsp * sizeof(double)));
+  CU(cudaMalloc(&c->gcnt, (size_t)P.nsp * P.ncell * sizeof(int)));
+  CU(cudaMalloc(&c->tilebase, (size_t)P.ntx * P.nty * P.nsp * WIN * sizeof(int)));
+  CU(cudaMalloc(&c->scan_scratch, (size_t)scan_scratch_ints(P.ncell) * sizeof(int)));
+  CU(cudaMalloc(&c->partial, 4096 * 2 * sizeof(double)));
+  CU(cudaMallocHost(&c->h_partial, 4096 * 2 * sizeof(double)));
+  CU(cudaMalloc(&c->d_err, sizeof(unsigned)));
+  CU(cudaMemset(c->d_err, 0, sizeof(unsigned)));
+  CU(cudaMallocHost(&c->h_err, sizeof(unsigned)));
+  CU(cudaMallocHost(&c->h_cg, 16 * sizeof(int)));
+  CU(cudaMallocHost(&c->h_cnt, 4 * WM_NSP_MAX * sizeof(int)));
+  CU(cudaMalloc(&c->sendcnt, 2 * WM_NSP_MAX * sizeof(int)));
+  CU(cudaMalloc(&c->recvcnt, 2 * WM_NSP_MAX * sizeof(int)));
+  CU(cudaMemset(c->sendcnt, 0, 2 * WM_NSP_MAX * sizeof(int)));
+  for (auto &e : c->ev_cg) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : c->ev) CU(cudaEventCreate(&e));
+  *out = c;
+  return 0;
+}
+
+int wm_destroy(wm_ctx *c) {
+  if (!c) return 0;
+  cudaSetDevice(c->dev);
+  cudaDeviceSynchronize();
+  if (c->comm) ncclCommDestroy(c->comm);
+  for (int b = 0; b < 2; b++) {
+    cudaFree(c->pbuf[b]);
+    cudaFree(c->cstart[b]);
+    cudaFree(c->send[b]);
+    cudaFree(c->recv[b]);
+  }
+  for (void *p : {(void *)c->tag, (void *)c->gcnt, (void *)c->tilebase, (void *)c->scan_scratch, (void *)c->sendcnt,
+                  (void *)c->recvcnt, (void *)c->in_rank, (void *)c->f.uf, (void *)c->f.df, (void *)c->f.tmpf,
+                  (void *)c->f.uj, (void *)c->f.gkl, (void *)c->f.phi, (void *)c->f.p, (void *)c->f.r, (void *)c->f.ap,
+                  (void *)c->f.red, (void *)c->f.cgstate, (void *)c->rowtmp, (void *)c->mom, (void *)c->partial,
+                  (void *)c->d_err})
+    cudaFree(p);
+  cudaFreeHost(c->h_partial);
+  cudaFreeHost(c->h_err);
+  cudaFreeHost(c->h_cg);
+  cudaFreeHost(c->h_cnt);
+  for (auto &e : c->ev_cg) cudaEventDestroy(e);
+  for (auto &e : c->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(c->st);
+  cudaStreamDestroy(c->st2);
+  delete c;
+  return 0;
+}
+
+int wm_comm_unique_id(void *id128) {
+  static_assert(sizeof(ncclUniqueId) == WM_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  NC(ncclGetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+
+int wm_comm_init(wm_ctx *c, const void *id128) {
+  if (!c) return fail("wm_comm_init: null context");
+  WM(set_device(c));
+  if (c->P.nsize == 1) return 0;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  NC(ncclCommInitRank(&c->comm, c->P.nsize, id, c->cfg.nrank));
+  // migration buffers: a generous multiple of one row's worth of particles per direction and species
+  return 0;
+}
+
+static int ensure_migration_buffers(wm_ctx *c, long long n_per_species) {
+  if (c->P.nsize == 1 || c->send[0]) return 0;
+  long long per_row = n_per_species / c->P.nyl + 1;
+  c->sendcap = (int)std::min<long long>(per_row + 4096, (1LL << 30));
+  const size_t bytes = (size_t)c->P.nsp * c->sendcap * 6 * sizeof(double);
+  for (int d = 0; d < 2; d++) {
+    CU(cudaMalloc(&c->send[d], bytes));
+    CU(cudaMalloc(&c->recv[d], bytes));
+  }
+  CU(cudaMalloc(&c->in_rank, (size_t)2 * c->P.nsp * c->sendcap * sizeof(int)));
+  return 0;
+}
+
+// ---------------------------------------------------------------- residency
+static int count_host(const wm_ctx *c, const int32_t *np2, long long n[WM_NSP_MAX]) {
+  const int nyl = c->P.nyl;
+  for (int isp = 0; isp < c->P.nsp; isp++) {
+    n[isp] = 0;
+    for (int jl = 0; jl < nyl; jl++) {
+      const int v = np2[jl + nyl * isp];
+      if (v < 0 || v > c->cfg.np) return fail("np2(%d,%d)=%d outside 0..np=%d", jl, isp, v, c->cfg.np);
+      n[isp] += v;
+    }
+  }
+  return 0;
+}
+
+// rows of the host array -> tight AoS records on the device (in the idle particle store)
+static int stage_rows_h2d(wm_ctx *c, const double *up, const int32_t *np2, double *stage, const long long n[WM_NSP_MAX]) {
+  const int nyl = c->P.nyl;
+  long long off = 0;
+  for (int isp = 0; isp < c->P.nsp; isp++)
+    for (int jl = 0; jl < nyl; jl++) {
+      const int v = np2[jl + nyl * isp];
+      if (v) CU(cudaMemcpyAsync(stage + off * 6, up + host_up_index(c->cfg, isp, jl), (size_t)v * 6 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+      off += v;
+    }
+  (void)n;
+  return 0;
+}
+
+int wm_upload_particles(wm_ctx *c, const double *up, const int32_t *np2) {
+  if (!c || !up || !np2) return fail("wm_upload_particles: null argument");
+  WM(set_device(c));
+  long long n[WM_NSP_MAX];
+  WM(count_host(c, np2, n));
+  long long nmax = 0;
+  for (int isp = 0; isp < c->P.nsp; isp++) nmax = std::max(nmax, n[isp]);
+  WM(alloc_particles(c, nmax));
+  WM(ensure_migration_buffers(c, nmax));
+  const DevParams &P = c->P;
+  double *stage = c->pbuf[c->cur ^ 1];
+  WM(stage_rows_h2d(c, up, np2, stage, n));
+  WM(zero_sort_state(c));
+  int *rank = reinterpret_cast<int *>(c->tag);
+  long long off = 0;
+  for (int isp = 0; isp < P.nsp; isp++) {
+    launch_incoming_tag(P, stage + off * 6, (int)n[isp], isp, c->gcnt, rank + off, c->d_err, c->st);
+    off += n[isp];
+  }
+  WM(scan_counts(c, c->cur));
+  off = 0;
+  for (int isp = 0; isp < P.nsp; isp++) {
+    launch_incoming_scatter(P, stage + off * 6, (int)n[isp], isp, c->cstart[c->cur], rank + off, c->soa[c->cur], c->d_err, c->st);
+    off += n[isp];
+  }
+  WM(check_errors(c, "wm_upload_particles"));
+  c->state = ST_SORTED;
+  return 0;
+}
+
+int wm_upload_particles_sorted(wm_ctx *c, const double *up, const int32_t *np2, const int32_t *cumcnt) {
+  if (!c || !up || !np2 || !cumcnt) return fail("wm_upload_particles_sorted: null argument");
+  WM(set_device(c));
+  long long n[WM_NSP_MAX];
+  WM(count_host(c, np2, n));
+  long long nmax = 0;
+  for (int isp = 0; isp < c->P.nsp; isp++) nmax = std::max(nmax, n[isp]);
+  WM(alloc_particles(c, nmax));
+  WM(ensure_migration_buffers(c, nmax));
+  const DevParams &P = c->P;
+  double *stage = c->pbuf[c->cur ^ 1];
+  WM(stage_rows_h2d(c, up, np2, stage, n));
+  // cstart from cumcnt + row bases
+  std::vector<int> cs((size_t)P.nsp * (P.ncell + 1));
+  for (int isp = 0; isp < P.nsp; isp++) {
+    long long base = 0;
+    int *o = cs.data() + (size_t)isp * (P.ncell + 1);
+    for (int jl = 0; jl < P.nyl; jl++) {
+      const int32_t *cc = cumcnt + (size_t)(P.nx + 1) * ((size_t)jl + (size_t)P.nyl * isp);
+      if (cc[0] != 0 || cc[P.nx] != np2[jl + P.nyl * isp]) return fail("wm_upload_particles_sorted: cumcnt inconsistent with np2 in row %d", jl);
+      for (int li = 0; li < P.nx; li++) o[(size_t)jl * P.nx + li] = (int)(base + cc[li]);
+      base += cc[P.nx];
+    }
+    o[P.ncell] = (int)base;
+  }
+  CU(cudaMemcpyAsync(c->cstart[c->cur], cs.data(), cs.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
+  long long off = 0;
+  for (int isp = 0; isp < P.nsp; isp++) {
+    launch_aos2soa(stage + off * 6, n[isp], (size_t)isp * P.cap, c->soa[c->cur], c->st);
+    off += n[isp];
+  }
+  CU(cudaStreamSynchronize(c->st));  // cs goes out of scope
+  c->state = ST_SORTED;
+  return 0;
+}
+
+int wm_upload_field(wm_ctx *c, const double *uf) {
+  if (!c || !uf) return fail("wm_upload_field: null argument");
+  WM(set_device(c));
+  const size_t ng = (size_t)c->P.pitch * (c->P.nyl + 4);
+  CU(cudaMemcpyAsync(c->f.uf, uf, ng * 6 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+static int download_store(wm_ctx *c, int buf, double *up, int32_t *np2, int32_t *cumcnt, double *stage_override) {
+  const DevParams &P = c->P;
+  std::vector<int> cs((size_t)P.nsp * (P.ncell + 1));
+  CU(cudaMemcpyAsync(cs.data(), c->cstart[c->cur], cs.size() * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  double *stage = stage_override ? stage_override : c->pbuf[buf ^ 1];
+  long long off = 0;
+  for (int isp = 0; isp < P.nsp; isp++) {
+    const int *o = cs.data() + (size_t)isp * (P.ncell + 1);
+    const long long n = o[P.ncell];
+    if (up) launch_soa2aos(c->soa[buf], (size_t)isp * P.cap, n, stage + off * 6, c->st);
+    for (int jl = 0; jl < P.nyl; jl++) {
+      const int rb = o[(size_t)jl * P.nx], re = o[(size_t)(jl + 1) * P.nx];
+      if (re - rb > c->cfg.np) return fail("memory over (np2 > np): row %d species %d holds %d > np=%d (boundary_periodic.f90:231-234)", jl, isp, re - rb, c->cfg.np);
+      if (np2) np2[jl + P.nyl * isp] = re - rb;
+      if (cumcnt) {
+        int32_t *cc = cumcnt + (size_t)(P.nx + 1) * ((size_t)jl + (size_t)P.nyl * isp);
+        for (int li = 0; li <= P.nx; li++) cc[li] = o[(size_t)jl * P.nx + li] - rb;
+      }
+      if (up && re > rb)
+        CU(cudaMemcpyAsync(up + host_up_index(c->cfg, isp, jl), stage + (off + rb) * 6, (size_t)(re - rb) * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    }
+    off += n;
+  }
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int wm_download_particles(wm_ctx *c, double *up, int32_t *np2, int32_t *cumcnt) {
+  WM(need_state(c, ST_SORTED, "wm_download_particles"));
+  WM(set_device(c));
+  return download_store(c, c->cur, up, np2, cumcnt, nullptr);
+}
+
+int wm_download_gp(wm_ctx *c, double *gp) {
+  if (!c || !gp) return fail("wm_download_gp: null argument");
+  if (c->state != ST_PUSHED && c->state != ST_BOUNDED) return fail("wm_download_gp: no pushed state (call wm_particle__solv first)");
+  WM(set_device(c));
+  int64_t n[WM_NSP_MAX];
+  WM(wm_particle_counts(c, n));
+  long long tot = 0;
+  for (int isp = 0; isp < c->P.nsp; isp++) tot += n[isp];
+  double *tmp = nullptr;
+  CU(cudaMalloc(&tmp, (size_t)std::max<long long>(tot, 1) * 6 * sizeof(double)));
+  const int e = download_store(c, c->cur ^ 1, gp, nullptr, nullptr, tmp);
+  cudaFree(tmp);
+  return e;
+}
+
+int wm_download_field(wm_ctx *c, double *uf) {
+  if (!c || !uf) return fail("wm_download_field: null argument");
+  WM(set_device(c));
+  const size_t ng = (size_t)c->P.pitch * (c->P.nyl + 4);
+  CU(cudaMemcpyAsync(uf, c->f.uf, ng * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int wm_download_current(wm_ctx *c, double *uj) {
+  if (!c || !uj) return fail("wm_download_current: null argument");
+  WM(set_device(c));
+  const size_t ng = (size_t)c->P.pitch * (c->P.nyl + 4);
+  CU(cudaMemcpyAsync(uj, c->f.uj, ng * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int wm_download_dfield(wm_ctx *c, double *df) {
+  if (!c || !df) return fail("wm_download_dfield: null argument");
+  WM(set_device(c));
+  const size_t ng = (size_t)c->P.pitch * (c->P.nyl + 4);
+  CU(cudaMemcpyAsync(df, c->f.df, ng * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int wm_particle_counts(wm_ctx *c, int64_t *n) {
+  if (!c || !n) return fail("wm_particle_counts: null argument");
+  WM(set_device(c));
+  if (c->state == ST_EMPTY) {
+    for (int isp = 0; isp < c->P.nsp; isp++) n[isp] = 0;
+    return 0;
+  }
+  for (int isp = 0; isp < c->P.nsp; isp++) {
+    int v = 0;
+    CU(cudaMemcpyAsync(&v, c->cstart[c->cur] + (size_t)isp * (c->P.ncell + 1) + c->P.ncell, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    n[isp] = v;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- stage calls
+int wm_particle__solv(wm_ctx *c) {
+  WM(need_state(c, ST_SORTED, "wm_particle__solv"));
+  WM(set_device(c));
+  launch_tmpf(c->P, c->f.uf, c->f.tmpf, c->st);
+  const int mode = M_PUSH | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
+  launch_pass1(mode, c->P, p1args(c, c->soa[c->cur], c->soa[c->cur ^ 1], c->P.delt), c->st);
+  c->launches += 2;
+  CU(cudaGetLastError());
+  c->state = ST_PUSHED;
+  return 0;
+}
+
+int wm_field__ele_cur(wm_ctx *c) {
+  WM(need_state(c, ST_PUSHED, "wm_field__ele_cur"));
+  WM(set_device(c));
+  const size_t ng = (size_t)c->P.pitch * (c->P.nyl + 4);
+  CU(cudaMemsetAsync(c->f.uj, 0, ng * 3 * sizeof(double), c->st));  // field.f90:203-205
+  launch_pass1(M_DEPOSIT, c->P, p1args(c, c->soa[c->cur], c->soa[c->cur ^ 1], c->P.delt), c->st);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int wm_boundary__curre(wm_ctx *c) {
+  if (!c) return fail("wm_boundary__curre: null context");
+  WM(set_device(c));
+  WM(bc_curre(c));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int wm_field__fdtd_i(wm_ctx *c) {
+  WM(wm_field__ele_cur(c));
+  WM(field_solve(c));
+  WM(check_errors(c, "wm_field__fdtd_i"));
+  return 0;
+}
+
+int wm_boundary__particle_x(wm_ctx *c) {
+  WM(need_state(c, ST_PUSHED, "wm_boundary__particle_x"));
+  WM(set_device(c));
+  launch_bcx(c->P, c->soa[c->cur ^ 1].x, c->cstart[c->cur], c->st);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int wm_boundary__particle_y(wm_ctx *c) {
+  WM(need_state(c, ST_PUSHED, "wm_boundary__particle_y"));
+  WM(set_device(c));
+  WM(zero_sort_state(c));
+  const PartSoA &gp = c->soa[c->cur ^ 1];
+  launch_pass1(M_BOUND, c->P, p1args(c, gp, gp, c->P.delt), c->st);
+  c->launches++;
+  WM(migrate(c));
+  WM(check_errors(c, "wm_boundary__particle_y"));
+  c->state = ST_BOUNDED;
+  return 0;
+}
+
+int wm_sort__bucket(wm_ctx *c) {
+  WM(need_state(c, ST_BOUNDED, "wm_sort__bucket"));
+  WM(set_device(c));
+  // (out) up <- (in) gp: the scatter goes back into the store that held the old sorted state
+  const int src = c->cur ^ 1, dst = c->cur;
+  // the new offsets must not overwrite the old ones while pass 2 still reads them
+  WM(scan_counts(c, src));
+  launch_pass2(c->P, c->soa[src], c->soa[dst], c->cstart[dst], c->cstart[src], c->tilebase, c->tag, c->d_err, c->st);
+  c->launches++;
+  // arrivals use cstart[src] (new offsets) and go to soa[dst]
+  {
+    const DevParams &P = c->P;
+    if (P.nsize > 1)
+      for (int d = 0; d < 2; d++)
+        for (int isp = 0; isp < P.nsp; isp++) {
+          const size_t off = (size_t)isp * c->sendcap;
+          launch_incoming_scatter(P, c->recv[d] + off * 6, c->n_in[d][isp], isp, c->cstart[src],
+                                  c->in_rank + (size_t)d * P.nsp * c->sendcap + off, c->soa[dst], c->d_err, c->st);
+          c->launches++;
+        }
+  }
+  WM(check_errors(c, "wm_sort__bucket"));
+  std::swap(c->cstart[0], c->cstart[1]);  // new offsets now belong to store `cur`
+  c->state = ST_SORTED;
+  return 0;
+}
+
+int wm_step(wm_ctx *c, int32_t nsteps) {
+  WM(need_state(c, ST_SORTED, "wm_step"));
+  WM(set_device(c));
+  const DevParams &P = c->P;
+  const size_t ng = (size_t)P.pitch * (P.nyl + 4);
+  const int mode = M_PUSH | M_DEPOSIT | M_BOUND | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
+  for (int it = 0; it < nsteps; it++) {
+    if (c->timing) CU(cudaEventRecord(c->ev[0], c->st));
+    // particle__solv + ele_cur + bc__particle_x/y + histogram in one pass, in place
+    launch_tmpf(P, c->f.uf, c->f.tmpf, c->st);
+    CU(cudaMemsetAsync(c->f.uj, 0, ng * 3 * sizeof(double), c->st));
+    WM(zero_sort_state(c));
+    const PartSoA &a = c->soa[c->cur];
+    launch_pass1(mode, P, p1args(c, a, a, P.delt), c->st);
+    c->launches += 2;
+    if (c->timing) CU(cudaEventRecord(c->ev[1], c->st));
+    // rest of field__fdtd_i
+    WM(field_solve(c));
+    if (c->timing) CU(cudaEventRecord(c->ev[2], c->st));
+    // migration, prefix scan
+    WM(migrate(c));
+    const int dst = c->cur ^ 1;
+    WM(scan_counts(c, dst));
+    if (c->timing) CU(cudaEventRecord(c->ev[3], c->st));
+    // sort__bucket scatter
+    launch_pass2(P, c->soa[c->cur], c->soa[dst], c->cstart[c->cur], c->cstart[dst], c->tilebase, c->tag, c->d_err, c->st);
+    c->launches++;
+    WM(scatter_arrivals(c, dst));
+    c->cur = dst;
+    if (c->timing) {
+      CU(cudaEventRecord(c->ev[4], c->st));
+      CU(cudaEventSynchronize(c->ev[4]));
+      float t;
+      for (int k = 0; k < 4; k++) {
+        CU(cudaEventElapsedTime(&t, c->ev[k], c->ev[k + 1]));
+        c->ms[k] += t;
+      }
+      CU(cudaEventElapsedTime(&t, c->ev[0], c->ev[4]));
+      c->ms[4] += t;
+    }
+  }
+  WM(check_errors(c, "wm_step"));
+  return 0;
+}
+
+// ---------------------------------------------------------------- host-array (drop-in) calls
+int wm_host_step(wm_ctx *c, double *up, double *uf, int32_t *np2, int32_t *cumcnt) {
+  WM(wm_upload_particles_sorted(c, up, np2, cumcnt));
+  WM(wm_upload_field(c, uf));
+  WM(wm_step(c, 1));
+  WM(wm_download_particles(c, up, np2, cumcnt));
+  WM(wm_download_field(c, uf));
+  return 0;
+}
+
+int wm_host_particle__solv(wm_ctx *c, double *gp, const double *up, const double *uf, const int32_t *cumcnt, const int32_t *np2) {
+  WM(wm_upload_particles_sorted(c, up, np2, cumcnt));
+  WM(wm_upload_field(c, uf));
+  WM(wm_particle__solv(c));
+  WM(wm_download_gp(c, gp));
+  return 0;
+}
+
+int wm_host_sort__bucket(wm_ctx *c, double *gp_out, const double *up_in, int32_t *cumcnt, const int32_t *np2) {
+  WM(wm_upload_particles(c, up_in, np2));
+  WM(wm_download_particles(c, gp_out, nullptr, cumcnt));
+  return 0;
+}
+
+// ---------------------------------------------------------------- diagnostics
+int wm_cg_iters(wm_ctx *c, int32_t out[3]) {
+  if (!c) return fail("wm_cg_iters: null context");
+  for (int l = 0; l < 3; l++) out[l] = c->cg_ite[l];
+  return 0;
+}
+
+int wm_energy(wm_ctx *c, double *out) {
+  WM(need_state(c, ST_SORTED, "wm_energy"));
+  WM(set_device(c));
+  const DevParams &P = c->P;
+  const int nb = 1024;
+  const double pi = 4.0 * std::atan(1.0);
+  for (int isp = 0; isp < P.nsp; isp++) {
+    launch_kinetic(P, c->soa[c->cur], c->cstart[c->cur], isp, c->partial, nb, c->st);
+    CU(cudaMemcpyAsync(c->h_partial, c->partial, nb * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    double s = 0.0;
+    for (int k = 0; k < nb; k++) s += c->h_partial[k];
+    out[isp] = s;
+  }
+  launch_field_energy(P, c->f.uf, c->partial, nb, c->st);
+  CU(cudaMemcpyAsync(c->h_partial, c->partial, nb * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  double sb = 0.0, se = 0.0;
+  for (int k = 0; k < nb; k++) {
+    sb += c->h_partial[2 * k];
+    se += c->h_partial[2 * k + 1];
+  }
+  out[P.nsp] = se / (8 * pi);
+  out[P.nsp + 1] = sb / (8 * pi);
+  return 0;
+}
+
+int wm_moments(wm_ctx *c, double *mom) {
+  WM(need_state(c, ST_SORTED, "wm_moments"));
+  if (!mom) return fail("wm_moments: null argument");
+  if (c->P.nsize > 1) return fail("wm_moments: multi-rank bc__mom not implemented yet");
+  WM(set_device(c));
+  const DevParams &P = c->P;
+  // mom_calc__accl: half-step acceleration into the idle store (mom_calc.f90:34,48-164)
+  launch_tmpf(P, c->f.uf, c->f.tmpf, c->st);
+  const int mode = M_PUSH | M_NOMOVE | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
+  launch_pass1(mode, P, p1args(c, c->soa[c->cur], c->soa[c->cur ^ 1], P.delt * 0.5), c->st);
+  const size_t nm = (size_t)7 * (P.nx + 3) * (P.nyl + 2) * P.nsp;
+  CU(cudaMemsetAsync(c->mom, 0, nm * sizeof(double), c->st));
+  launch_moments(P, c->soa[c->cur ^ 1], c->cstart[c->cur], c->mom, c->st);
+  c->launches += 3;
+  CU(cudaMemcpyAsync(mom, c->mom, nm * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  // bc__mom on the host copy (boundary_periodic.f90:571-636), single rank: ring neighbour is self
+  const int nxp = P.nx + 3, nyp = P.nyl + 2;
+  auto M = [&](int m, int i, int j, int isp) -> double & { return mom[(size_t)m + 7 * ((size_t)i + (size_t)nxp * ((size_t)j + (size_t)nyp * isp))]; };
+  for (int isp = 0; isp < P.nsp; isp++) {
+    for (int j = 0; j < nyp; j++)
+      for (int m = 0; m < 7; m++) {
+        M(m, 1, j, isp) += M(m, P.nx + 1, j, isp);   // nxgs += nxge+1
+        M(m, P.nx, j, isp) += M(m, 0, j, isp);       // nxge += nxgs-1
+      }
+    for (int i = 0; i < nxp; i++)
+      for (int m = 0; m < 7; m++) {
+        const double lo = M(m, i, 0, isp), hi = M(m, i, P.nyl + 1, isp);
+        M(m, i, P.nyl, isp) += lo;  // nye += (nup's) nys-1
+        M(m, i, 1, isp) += hi;      // nys += (ndown's) nye+1
+      }
+  }
+  return 0;
+}
+
+int wm_ic_weibel(wm_ctx *c, uint64_t seed, int32_t n0, double vti, double vte, double t_ani, double b0) {
+  if (!c) return fail("wm_ic_weibel: null context");
+  WM(set_device(c));
+  DevParams &P = c->P;
+  const long long n = (long long)n0 * P.nx * P.nyl;
+  if (n >= (1LL << 31) - 1) return fail("wm_ic_weibel: too many particles per species for one GPU");
+  WM(alloc_particles(c, n));
+  WM(ensure_migration_buffers(c, n));
+  launch_ic_weibel(P, c->soa[c->cur], c->cstart[c->cur], seed, n0, vti, vte, t_ani, c->st);
+  // uniform field Bz = b0 (app.f90:388-399), df = 0
+  const size_t ng = (size_t)P.pitch * (P.nyl + 4);
+  std::vector<double> h(ng * 6, 0.0);
+  for (size_t g = 0; g < ng; g++) h[g * 6 + 2] = b0;
+  CU(cudaMemcpyAsync(c->f.uf, h.data(), ng * 6 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  CU(cudaMemsetAsync(c->f.df, 0, ng * 6 * sizeof(double), c->st));
+  CU(cudaStreamSynchronize(c->st));
+  CU(cudaGetLastError());
+  c->state = ST_SORTED;
+  return 0;
+}
+
+int wm_timing(wm_ctx *c, double ms[5], int64_t *launches, int32_t reset) {
+  if (!c) return fail("wm_timing: null context");
+  for (int k = 0; k < 5; k++) {
+    if (ms) ms[k] = c->ms[k];
+    if (reset) c->ms[k] = 0.0;
+  }
+  if (launches) *launches = c->launches;
+  if (reset) c->launches = 0;
+  return 0;
+}
+
+int wm_synchronize(wm_ctx *c) {
+  if (!c) return fail("wm_synchronize: null context");
+  WM(set_device(c));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// wm_internal.h -- device data model shared by the kernels and the C-ABI host layer.
+//
+// Data layout in HBM (one context = one y-slab, rows nys..nye, full x extent):
+//  * particles: SoA per component (x, y, ux, uy, uz, id), species s at offset s*cap,
+//    globally cell-sorted: cell = (j-nys)*nx + (i-nxgs); cell c of species s owns slots
+//    [cstart[s][c], cstart[s][c+1]).  The reference's cumcnt(i,j,s) is
+//    cstart[s][cell(i,j)] - cstart[s][cell(nxgs,j)] and np2(j,s) is the row total.
+//  * grid arrays: the reference's own AoS layout incl. 2 ghost cells per side,
+//    uf/df/tmpf (6, nx+4, nyl+4), uj/gkl/CG vectors (3, nx+4, nyl+4).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/wumingpic2d.h"
+
+namespace wm {
+
+constexpr int TX = 16;           // tile: cells in x
+constexpr int TY = 8;            // tile: rows
+constexpr int WINX = TX + 2;     // destination window (particles move < 1 cell per step)
+constexpr int WINY = TY + 2;
+constexpr int WIN = WINX * WINY; // 180 < 256: fits the 8-bit window field of a tag
+constexpr int JX = TX + 4;       // current tile incl. the +-2 stencil halo
+constexpr int JY = TY + 4;
+constexpr int P1_THREADS = 256;
+constexpr int GRP = 8;           // threads that share one cell's accumulators
+constexpr uint32_t TAG_DEAD = 0xFFFFFFFFu;
+constexpr int TAG_SHIFT = 24;
+constexpr uint32_t TAG_RANK_MASK = (1u << TAG_SHIFT) - 1u;
+
+struct PartSoA {
+  double *x, *y, *ux, *uy, *uz;
+  long long *id;
+};
+
+struct DevParams {
+  int nx, nyl;      // local cells
+  int nxgs, nys;    // global index of local cell (0,0)
+  int nygs, ny;     // global y range
+  int nsize;        // ranks on the ring
+  int pitch;        // nx + 4
+  int ntx, nty;     // tiles
+  int nsp;
+  int ncell;        // nx * nyl
+  long long cap;    // per-species slot capacity
+  double delx, delt, c, cc, inv_cc;
+  double xlen, ylen;            // nx*delx, ny*delx
+  double q[WM_NSP_MAX], r[WM_NSP_MAX];
+  double f1, f2, f3, f4, f5, gfac, pi4dt;  // field.f90:53-57, 4*pi*delt
+};
+
+// error bits written by kernels into the context's device flag word
+enum : unsigned {
+  ERR_MOVED_TOO_FAR = 1u,   // a particle left the +-1 cell window (CFL violated / NaN)
+  ERR_CAPACITY = 2u,        // particle slots exhausted ("memory over", boundary_periodic.f90:231-234)
+  ERR_SENDBUF = 4u,         // migration buffer exhausted
+  ERR_BAD_CELL = 8u,        // uploaded particle outside the slab
+  ERR_TAG_RANK = 16u        // more than 2^24 particles from one tile into one cell
+};
+
+struct Pass1Args {
+  PartSoA src, dst;         // dst == src for the in-place fused pass
+  const int *cstart;        // [nsp][ncell+1]
+  const double *tmpf;       // cell-centred fields, AoS6 padded
+  double *uj;               // AoS3 padded, accumulated with RED.ADD.F64
+  int *gcnt;                // [nsp][ncell] destination-cell counters / cursors
+  int *tilebase;            // [ntiles][nsp][WIN]
+  uint32_t *tag;            // [nsp*cap]
+  double *send[2];          // leavers: [dir][isp] AoS records, sendcap each   (dir 0 = down)
+  int *sendcnt;             // [2][nsp]
+  int sendcap;
+  unsigned *err;
+  double delt_push;         // delt (push) or delt/2 (mom_calc__accl)
+};
+
+struct Timers;
+
+}  // namespace wm
