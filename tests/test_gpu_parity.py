@@ -91,7 +91,7 @@ def test_push(warm, exact):
             a, b = gp[isp, jl, :n], ref[isp, jl, :n]
             assert np.array_equal(a[:, 5].view(np.int64), b[:, 5].view(np.int64))
             if exact:
-                assert np.array_equal(a, b), "EXACT push must be bit-identical to the CPU path"
+                assert np.array_equal(a.view(np.int64), b.view(np.int64)), "EXACT push must be bit-identical to the CPU path"
             else:
                 ex, eu = particle_err(a[:, :5], b[:, :5], prm["nx"], prm["vte"])
                 assert ex <= TOL and eu <= TOL
@@ -167,7 +167,7 @@ def test_fused_step_matches_oracle(exact):
     a, b = flatten_by_id(up, np2), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
     assert np.array_equal(a[0], b[0])
     if exact:
-        assert np.array_equal(a[2], b[2]), "first step from identical fields: bit-identical particles"
+        assert np.array_equal(a[2].view(np.int64), b[2].view(np.int64)), "first step from identical fields: bit-identical particles"
     ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
     assert ex <= TOL and eu <= TOL
     # a few more steps: still within tolerance (errors grow slowly before chaos sets in)
