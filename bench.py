@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the per-timestep PIC hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], SURVEY 8d "Config 2"): Weibel set-up, synthetic uniform
+Maxwellian, nx = 4096, 512 rows per GPU (N GPUs -> 4096 x 512N grid; 8 GPUs = 4096 x 4096),
+64 particles per cell per species, e- + ion: 268,435,456 particles per GPU.  Weak scaling.
+
+A step = push + Esirkepov deposit + particle boundaries + field solve (CG) + migration + sort,
+i.e. the five calls of proj/weibel/app.f90:100-107, fused (wm_step).
+
+value   particle-steps/s, state resident in HBM, K steps timed with CUDA events on the library's
+        stream inside wm_step (first launch -> last completion), max over ranks.
+e2e     the same metric through wm_host_step: HOST arrays in the reference's layout (pinned), H2D of
+        up/uf/np2/cumcnt and D2H of the same inside the timed region, every step.
+roofline the fused push+deposit+boundary kernel: algorithmic 96 B per particle (48 B record read
+        once, written once) / its event-timed duration, vs the measured HBM copy peak.
+cpu_baseline the CPU oracle (a C++/OpenMP restatement of the reference path, NOT the Fortran
+        build, which cannot be produced here: no Fortran compiler, no MPI) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+NX, ROWS_PER_GPU, PPC = 4096, 512, 64
+SEED = 20260117
+ALG_BYTES_STEP = 192.0    # 4 x 48 B per particle-step
+ALG_BYTES_PASS1 = 96.0    # fused push+deposit+boundary pass: R 48 + W 48
+
+
+def weibel_params(nx, ny, n_ppc, cap_factor=1.25):
+    """proj/weibel/app.f90:245-255,292-303 with proj/weibel/config_sample.json physics."""
+    import math
+    c, gfac, cfl, delx = 1.0, 0.501, 1.0, 1.0
+    mass_ratio, sigma_e, omega_pe, v_the, v_thi, t_ani = 1.0, 0.0, 0.1, 0.1, 0.1, 5.0
+    delt = cfl * delx / c
+    wpe = omega_pe
+    wge = omega_pe * math.sqrt(sigma_e)
+    wpi = wpe / math.sqrt(mass_ratio)
+    wgi = wge / mass_ratio
+    r = [mass_ratio, 1.0]
+    q = [+math.sqrt(r[0] / (4 * math.pi * n_ppc / delx ** 2)) * wpi,
+         -math.sqrt(r[1] / (4 * math.pi * n_ppc / delx ** 2)) * wpe]
+    return dict(nx=nx, ny=ny, nranks=1, n0=n_ppc, np=int(math.ceil(n_ppc * nx * cap_factor)), nsp=2,
+                delx=delx, delt=delt, c=c, gfac=gfac, q=q, r=r, b0=r[0] * c / q[0] * wgi,
+                vti=v_thi, vte=v_the, t_ani=t_ani, nxgs=2, nygs=2)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.p = index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # under load = upper half of the samples (the region is short; idle samples bracket it)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": mx,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(steps, warmup, rows=32, nx=NX, ppc=PPC):
+    """The CPU oracle (timing build, all host threads) on a bounded sample of the workload:
+    same nx, ppc, physics and IC recipe, `rows` rows instead of 512 per GPU."""
+    import oracle_lib as O
+    prm = weibel_params(nx, rows, ppc)
+    w = O.World(prm, fast=True)
+    w.ic_weibel(SEED)
+    npart = 2 * nx * rows * ppc
+    if warmup:
+        w.step(warmup)
+    w.stage_times(reset=True)
+    t0 = time.perf_counter()
+    w.step(steps)
+    dt = time.perf_counter() - t0
+    st = w.stage_times()
+    cores = w.lib.orc_num_threads()
+    w.close()
+    return dict(value=npart * steps / dt, unit="particle-steps/s", cores=cores, kind="port",
+                sample="%dx%d grid, %d ppc/species x2 (%d particles), %d steps after %d warm-up; "
+                       "C++/OpenMP restatement of the reference CPU path (Fortran+MPI build impossible here)"
+                       % (nx, rows, ppc, npart, steps, warmup),
+                ms_per_step=1e3 * dt / steps,
+                stage_s=dict(zip(("push", "field+deposit", "bc_x", "bc_y", "sort"), [round(x, 4) for x in st])))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    base = cpu_reference_rate(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "particle-steps/sec (push+deposit+sort+field)", "value": base["value"],
+        "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "weibel 4096x(512 per GPU) 64 ppc/species e-/ion uniform Maxwellian; "
+                               "CPU arm runs a bounded 4096x32-row sample of it", "parallelism": "openmp%d" % base["cores"]},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU (default: the named workload)")
+    ap.add_argument("--nx", type=int, default=NX)
+    ap.add_argument("--ppc", type=int, default=PPC)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exact", action="store_true", help="bit-exact push arithmetic (WM_FLAG_EXACT_PUSH)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                   "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        raise SystemExit("WORLD_SIZE=%d but --gpus %d" % (world, args.gpus))
+
+    import numpy as np
+    import torch
+    import wumingpic2d_b200 as wm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    nx, rows, ppc = args.nx, args.rows, args.ppc
+    ny = rows * world
+    prm = weibel_params(nx, ny, ppc)
+    nys = 2 + rank * rows
+    nye = nys + rows - 1
+    ctx = wm.Context.from_params(prm, nys=nys, nye=nye, nrank=rank, nsize=world, device=local,
+                                 flags=wm.WM_FLAG_EXACT_PUSH if args.exact else 0)
+    if world > 1:
+        idbuf = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(idbuf, src=0)
+        ctx.comm_init(idbuf[0])
+    ctx.ic_weibel(SEED, ppc, prm["vti"], prm["vte"], prm["t_ani"], prm["b0"])
+    n_local = sum(ctx.particle_counts())
+    n_total = allsum(float(n_local))
+
+    # ---- resident throughput ---------------------------------------------------------------
+    ctx.step(args.warmup)
+    ctx.timing(reset=True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    ctx.step(args.steps)
+    ctx.synchronize()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ms, launches = ctx.timing(reset=True)
+    ms_step = allmax(ms[4]) / args.steps
+    wall_step = allmax(wall) * 1e3 / args.steps
+    value = n_total / (ms_step * 1e-3)
+    ms_pass1 = allmax(ms[0]) / args.steps
+    cg = ctx.cg_iters()
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    achieved = ALG_BYTES_PASS1 * n_local / (ms_pass1 * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "pass1_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_pass1<PUSH|DEPOSIT|BOUND> (fused push+deposit+boundary)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_kind, "alg_bytes_per_particle": ALG_BYTES_PASS1, "ms_per_launch": ms_pass1,
+                "whole_step": {"alg_bytes_per_particle_step": ALG_BYTES_STEP,
+                               "achieved": ALG_BYTES_STEP * n_local / (allmax(ms[4]) / args.steps * 1e-3) / 1e9,
+                               "frac": ALG_BYTES_STEP * n_local / (allmax(ms[4]) / args.steps * 1e-3) / 1e9 / peak}}
+    stage_ms = {"pass1_push_deposit_boundary": ms[0] / args.steps, "field_solve": ms[1] / args.steps,
+                "prep_migrate_scan": ms[2] / args.steps, "pass2_scatter": ms[3] / args.steps}
+
+    # ---- end to end through host arrays -------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            shape_up = ctx.shape_up()
+            nbytes_up = int(np.prod(shape_up)) * 8
+            up_t = torch.empty(nbytes_up // 8, dtype=torch.float64, pin_memory=True)
+            uf_t = torch.empty(int(np.prod(ctx.shape_uf())), dtype=torch.float64, pin_memory=True)
+            up = up_t.numpy().reshape(shape_up)
+            uf = uf_t.numpy().reshape(ctx.shape_uf())
+            _, np2, cum = ctx.download_particles(up)
+            uf[...] = ctx.download_field()
+            h2d = d2h = int(np2.sum()) * 48 + uf.nbytes + np2.nbytes + cum.nbytes
+            ctx.host_step(up, uf, np2, cum)  # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                ctx.host_step(up, uf, np2, cum)
+            barrier()
+            dt = allmax(time.perf_counter() - t0)
+            e2e = {"value": n_total * args.e2e_steps / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
+                   "api": "wm_host_step(up, uf, np2, cumcnt): pinned host arrays in the reference's Fortran layout"}
+            del up, uf, up_t, uf_t
+        except Exception as ex:  # keep the resident number even if host memory is short
+            e2e = {"value": None, "unit": "particle-steps/s", "error": str(ex)[:200]}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            b = cpu_reference_rate(steps=10, warmup=2)
+            cpu = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:
+            cpu = {"value": None, "error": str(ex)[:200]}
+
+    if rank == 0:
+        line = {
+            "metric": "particle-steps/sec (push+deposit+sort+field)", "value": value, "unit": "particle-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "weibel %dx%d grid (%d rows per GPU), %d ppc/species, e-/ion, uniform Maxwellian "
+                                   "(BASELINE configs[1] slab)" % (nx, ny, rows, ppc),
+                       "particles": int(n_total), "parallelism": "y-slab x%d" % world,
+                       "l2": "working set %.1f GB per GPU >> 126 MB L2" % (n_local * 96 / 1e9),
+                       "push_arithmetic": "exact" if args.exact else "fma", "cg_iters": cg},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "stage_ms": stage_ms, "wall_ms_per_step": wall_step,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

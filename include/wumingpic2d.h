@@ -139,9 +139,10 @@ int wm_moments(wm_ctx *ctx, double *mom);
 int wm_ic_weibel(wm_ctx *ctx, uint64_t seed, int32_t n0, double vti, double vte, double t_ani, double b0);
 
 /* ---- measurement hooks ----------------------------------------------------------- */
-/* device milliseconds (CUDA events on the context's stream) accumulated per stage by
- * wm_step since the last reset: [0] push+deposit+boundary kernel, [1] field solve,
- * [2] exchange+scan, [3] scatter pass, [4] whole step; launches = kernels launched */
+/* device milliseconds (CUDA events on the context's stream) accumulated by wm_step since the
+ * last reset: [0] the fused push+deposit+boundary kernel alone, [1] field solve,
+ * [2] cell-centre fields + clears + migration + prefix scan, [3] scatter pass,
+ * [4] whole wm_step calls (first launch to last completion); launches = kernels launched */
 int wm_timing(wm_ctx *ctx, double ms[5], int64_t *launches, int32_t reset);
 int wm_synchronize(wm_ctx *ctx);
 
