@@ -39,21 +39,6 @@ struct Ar {
   static __device__ __forceinline__ double sqrt_(double a) { return EX ? __dsqrt_rn(a) : sqrt(a); }
 };
 
-__device__ __forceinline__ int window_cell(const DevParams &P, int li0, int lj0, int w) {
-  // window index -> local cell index with the periodic wraps; -1 = outside the slab
-  int lx = w % WINX, ly = w / WINX;
-  int li = li0 - 1 + lx;
-  if (li < 0) li += P.nx;
-  if (li >= P.nx) li -= P.nx;
-  int lj = lj0 - 1 + ly;
-  if (P.nsize == 1) {
-    if (lj < 0) lj += P.nyl;
-    if (lj >= P.nyl) lj -= P.nyl;
-  }
-  if (li < 0 || li >= P.nx || lj < 0 || lj >= P.nyl) return -1;
-  return lj * P.nx + li;
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(P1_THREADS, 1) k_pass1(const DevParams P, const Pass1Args a) {
   constexpr bool PUSH = (MODE & M_PUSH) != 0;
@@ -334,7 +319,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) k_pass1(const DevParams P, cons
             } else {
               const int w = (cy + 1 + incy) * WINX + (cx + 1 + incx);
               const int rk = atomicAdd(&s_cnt[isp * WIN + w], 1);
-              tg = ((uint32_t)w << TAG_SHIFT) | (uint32_t)rk;
+              tg = TAG_ARRIVAL | ((uint32_t)w << TAG_WSHIFT) | (uint32_t)rk;
             }
             a.tag[so + p] = tg;
           }
@@ -409,7 +394,8 @@ __global__ void __launch_bounds__(P1_THREADS, 1) k_pass1(const DevParams P, cons
         }
         if (n > (int)TAG_RANK_MASK) atomicOr(a.err, ERR_TAG_RANK);
       }
-      a.tilebase[((size_t)tile * P.nsp + isp) * WIN + w] = base;
+      a.tilebase[((size_t)tile * P.nsp + isp) * (2 * WIN) + w] = base;
+      a.tilebase[((size_t)tile * P.nsp + isp) * (2 * WIN) + WIN + w] = base;
     }
   }
 }
@@ -419,14 +405,15 @@ __global__ void __launch_bounds__(256) k_pass2(const DevParams P, const PartSoA 
                                                const int *__restrict__ cstart_old, const int *__restrict__ cstart_new,
                                                const int *__restrict__ tilebase, const uint32_t *__restrict__ tag,
                                                unsigned *err) {
-  __shared__ int s_base[WM_NSP_MAX * WIN];
+  __shared__ int s_base[WM_NSP_MAX * 512];  // [isp][kind][256]: indexed by the top 9 bits of a tag
   const int tid = threadIdx.x, tile = blockIdx.x;
   const int li0 = (tile % P.ntx) * TX, lj0 = (tile / P.ntx) * TY;
   const int tw = min(TX, P.nx - li0), th = min(TY, P.nyl - lj0);
-  for (int e = tid; e < P.nsp * WIN; e += blockDim.x) {
-    const int isp = e / WIN, w = e - isp * WIN;
+  for (int e = tid; e < P.nsp * 2 * WIN; e += blockDim.x) {
+    const int isp = e / (2 * WIN), r = e - isp * (2 * WIN), kind = r / WIN, w = r - kind * WIN;
     const int cell = window_cell(P, li0, lj0, w);
-    s_base[e] = (cell < 0) ? -1 : tilebase[((size_t)tile * P.nsp + isp) * WIN + w] + cstart_new[(size_t)isp * (P.ncell + 1) + cell];
+    s_base[isp * 512 + kind * 256 + w] =
+        (cell < 0) ? -1 : tilebase[(size_t)tile * P.nsp * (2 * WIN) + e] + cstart_new[(size_t)isp * (P.ncell + 1) + cell];
   }
   __syncthreads();
   for (int isp = 0; isp < P.nsp; isp++) {
@@ -438,7 +425,7 @@ __global__ void __launch_bounds__(256) k_pass2(const DevParams P, const PartSoA 
       for (int p = beg + tid; p < end; p += blockDim.x) {
         const uint32_t t = tag[so + p];
         if (t == TAG_DEAD) continue;
-        const int d = s_base[isp * WIN + (t >> TAG_SHIFT)] + (int)(t & TAG_RANK_MASK);
+        const int d = s_base[isp * 512 + (t >> TAG_WSHIFT)] + (int)(t & TAG_RANK_MASK);
         if (d < 0 || d >= P.cap) {
           atomicOr(err, ERR_CAPACITY);
           continue;

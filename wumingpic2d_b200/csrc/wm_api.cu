@@ -467,7 +467,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   CU(cudaMalloc(&c->rowtmp, (size_t)P.pitch * 2 * 6 * sizeof(double)));
   CU(cudaMalloc(&c->mom, (size_t)7 * (nx + 3) * (nyl + 2) * P.nsp * sizeof(double)));
   CU(cudaMalloc(&c->gcnt, (size_t)P.nsp * P.ncell * sizeof(int)));
-  CU(cudaMalloc(&c->tilebase, (size_t)P.ntx * P.nty * P.nsp * WIN * sizeof(int)));
+  CU(cudaMalloc(&c->tilebase, (size_t)P.ntx * P.nty * P.nsp * 2 * WIN * sizeof(int)));
   CU(cudaMalloc(&c->scan_scratch, (size_t)scan_scratch_ints(P.ncell) * sizeof(int)));
   CU(cudaMalloc(&c->partial, 4096 * 2 * sizeof(double)));
   CU(cudaMallocHost(&c->h_partial, 4096 * 2 * sizeof(double)));
@@ -846,7 +846,10 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
     WM(zero_sort_state(c));
     const PartSoA &a = c->soa[c->cur];
     if (c->timing) CU(cudaEventRecord(c->ev[1], c->st));
-    launch_pass1(mode, P, p1args(c, a, a, P.delt), c->st);
+    if (c->cfg.flags & WM_FLAG_EXACT_PUSH)
+      launch_pass1(mode, P, p1args(c, a, a, P.delt), c->st);
+    else
+      launch_fused(P, p1args(c, a, a, P.delt), c->st);
     c->launches += 2;
     if (c->timing) CU(cudaEventRecord(c->ev[2], c->st));
     // rest of field__fdtd_i

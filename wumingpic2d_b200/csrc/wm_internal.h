@@ -19,14 +19,18 @@ constexpr int TX = 16;           // tile: cells in x
 constexpr int TY = 8;            // tile: rows
 constexpr int WINX = TX + 2;     // destination window (particles move < 1 cell per step)
 constexpr int WINY = TY + 2;
-constexpr int WIN = WINX * WINY; // 180 < 256: fits the 8-bit window field of a tag
+constexpr int WIN = WINX * WINY; // 180 < 255: fits the 8-bit window field of a tag
 constexpr int JX = TX + 4;       // current tile incl. the +-2 stencil halo
 constexpr int JY = TY + 4;
 constexpr int P1_THREADS = 256;
 constexpr int GRP = 8;           // threads that share one cell's accumulators
-constexpr uint32_t TAG_DEAD = 0xFFFFFFFFu;
-constexpr int TAG_SHIFT = 24;
-constexpr uint32_t TAG_RANK_MASK = (1u << TAG_SHIFT) - 1u;
+// sort tag of a particle: kind<<31 | window cell<<23 | rank.  kind 0 = stays in its cell (rank
+// counts the stayers of that cell in slot order), kind 1 = arrives in window cell w (rank from a
+// shared-memory counter).  The scatter pass adds tilebase[kind][w] + cstart_new[cell(w)].
+constexpr uint32_t TAG_DEAD = 0xFFFFFFFFu;   // left the slab (migrates to a neighbour rank)
+constexpr int TAG_WSHIFT = 23;
+constexpr uint32_t TAG_ARRIVAL = 0x80000000u;
+constexpr uint32_t TAG_RANK_MASK = (1u << TAG_WSHIFT) - 1u;
 
 struct PartSoA {
   double *x, *y, *ux, *uy, *uz;
@@ -55,7 +59,7 @@ enum : unsigned {
   ERR_CAPACITY = 2u,        // particle slots exhausted ("memory over", boundary_periodic.f90:231-234)
   ERR_SENDBUF = 4u,         // migration buffer exhausted
   ERR_BAD_CELL = 8u,        // uploaded particle outside the slab
-  ERR_TAG_RANK = 16u        // more than 2^24 particles from one tile into one cell
+  ERR_TAG_RANK = 16u        // more than 2^23 particles from one tile into one cell
 };
 
 struct Pass1Args {
@@ -64,7 +68,7 @@ struct Pass1Args {
   const double *tmpf;       // cell-centred fields, AoS6 padded
   double *uj;               // AoS3 padded, accumulated with RED.ADD.F64
   int *gcnt;                // [nsp][ncell] destination-cell counters / cursors
-  int *tilebase;            // [ntiles][nsp][WIN]
+  int *tilebase;            // [ntiles][nsp][2][WIN]  (kind 0 = stayers, 1 = arrivals)
   uint32_t *tag;            // [nsp*cap]
   double *send[2];          // leavers: [dir][isp] AoS records, sendcap each   (dir 0 = down)
   int *sendcnt;             // [2][nsp]
@@ -73,6 +77,21 @@ struct Pass1Args {
   double delt_push;         // delt (push) or delt/2 (mom_calc__accl)
 };
 
-struct Timers;
+#ifdef __CUDACC__
+// window index -> local cell index with the periodic wraps; -1 = outside the slab
+__device__ __forceinline__ int window_cell(const DevParams &P, int li0, int lj0, int w) {
+  int lx = w % WINX, ly = w / WINX;
+  int li = li0 - 1 + lx;
+  if (li < 0) li += P.nx;
+  if (li >= P.nx) li -= P.nx;
+  int lj = lj0 - 1 + ly;
+  if (P.nsize == 1) {
+    if (lj < 0) lj += P.nyl;
+    if (lj >= P.nyl) lj -= P.nyl;
+  }
+  if (li < 0 || li >= P.nx || lj < 0 || lj >= P.nyl) return -1;
+  return lj * P.nx + li;
+}
+#endif
 
 }  // namespace wm
