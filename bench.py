@@ -257,7 +257,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "pass1_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_pass1<PUSH|DEPOSIT|BOUND> (fused push+deposit+boundary)",
+    roofline = {"bound": "hbm", "kernel": "k_pass1<PUSH|DEPOSIT|BOUND> (exact)" if args.exact else "k_fused (push+deposit+boundary+histogram, one pass)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_kind, "alg_bytes_per_particle": ALG_BYTES_PASS1, "ms_per_launch": ms_pass1,
                 "whole_step": {"alg_bytes_per_particle_step": ALG_BYTES_STEP,

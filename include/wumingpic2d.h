@@ -129,8 +129,15 @@ int wm_cg_iters(wm_ctx *ctx, int32_t out[3]);  /* CG iterations of the last solv
 /* energy_history (proj/weibel/app.f90:479-545), this rank's share:
  * out[0..nsp-1] kinetic, out[nsp] = sum E^2/8pi, out[nsp+1] = sum B^2/8pi */
 int wm_energy(wm_ctx *ctx, double *out);
-/* mom_calc__accl + mom_calc__nvt + bc__mom (common/mom_calc.f90:48,167;
- * common/boundary_periodic.f90:571) -> host mom */
+/* mom_calc__accl (common/mom_calc.f90:48): half-step momenta into the device's idle particle
+ * store (the reference's `gp`); valid until the next call that moves or transfers particles */
+int wm_mom_calc__accl(wm_ctx *ctx);
+/* mom_calc__nvt (common/mom_calc.f90:167): seven moments with linear weights of the store
+ * written by wm_mom_calc__accl -> host mom, ghost sums not folded yet */
+int wm_mom_calc__nvt(wm_ctx *ctx, double *mom);
+/* bc__mom (common/boundary_periodic.f90:571): x fold, y fold over the rank ring; host mom in/out */
+int wm_boundary__mom(wm_ctx *ctx, double *mom);
+/* the three calls above without the intermediate host copies (proj/weibel/app.f90:121-123) */
 int wm_moments(wm_ctx *ctx, double *mom);
 
 /* Synthetic uniform Maxwellian of proj/weibel/app.f90:380-474 generated on the device

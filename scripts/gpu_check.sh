@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --fo
 ( timeout 600 python bench.py --impl reference --steps 5 --warmup 1 2>> $OUT/bench.err | tail -1 ) > $OUT/bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > $OUT/ncu_launch_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_pass -s 4 -c 4 -o $OUT/prof_pass \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_fused|k_pass2" -s 4 -c 2 -o $OUT/prof_pass \
     python bench.py --rows 128 --steps 2 --warmup 2 --no-e2e --no-cpu > $OUT/ncu_full.log 2>&1
 ls -la $OUT
 cat $OUT/pytest_gpu.log $OUT/bench.json $OUT/bench_ref.json

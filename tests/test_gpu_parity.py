@@ -238,6 +238,14 @@ def test_moments_match_oracle(warm):
     ref = w.array(0, O.MOM)
     # interior nodes only: ghosts hold pre-fold partial sums in both implementations
     assert rel_to_max(mom[:, 1:-1, 1:-1], ref[:, 1:-1, 1:-1]).max() <= 1e-12
+    # the same through the three reference procedures one by one (proj/weibel/app.f90:121-123)
+    _, w2 = make_world(prm["nx"], prm["ny"], prm["n0"], steps=6)
+    w2.mom_accl(); w2.mom_nvt()
+    c.mom_calc__accl()
+    raw = c.mom_calc__nvt()
+    assert rel_to_max(raw, w2.array(0, O.MOM)).max() <= 1e-12     # ghosts included, before the fold
+    c.bc__mom(raw)
+    assert rel_to_max(raw[:, 1:-1, 1:-1], ref[:, 1:-1, 1:-1]).max() <= 1e-12
     c.close()
 
 

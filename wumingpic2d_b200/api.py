@@ -48,7 +48,7 @@ EXPORTS = [
     "wm_particle_counts", "wm_particle__solv", "wm_field__ele_cur", "wm_boundary__curre",
     "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_sort__bucket",
     "wm_step", "wm_host_step", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
-    "wm_energy", "wm_moments", "wm_ic_weibel", "wm_timing", "wm_synchronize",
+    "wm_energy", "wm_moments", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_ic_weibel", "wm_timing", "wm_synchronize",
 ]
 
 
@@ -105,6 +105,9 @@ def load_library():
     lib.wm_cg_iters.argtypes = [P, I32]
     lib.wm_energy.argtypes = [P, D]
     lib.wm_moments.argtypes = [P, D]
+    lib.wm_mom_calc__accl.argtypes = [P]
+    lib.wm_mom_calc__nvt.argtypes = [P, D]
+    lib.wm_boundary__mom.argtypes = [P, D]
     lib.wm_ic_weibel.argtypes = [P, C.c_uint64, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]
     lib.wm_timing.argtypes = [P, D, C.POINTER(C.c_int64), C.c_int32]
     _lib = lib
@@ -262,6 +265,15 @@ class Context:
         mom = np.zeros(self.shape_mom())
         self._ck(self.lib.wm_moments(self.h, _d(mom)))
         return mom
+
+    def mom_calc__accl(self): self._ck(self.lib.wm_mom_calc__accl(self.h))
+
+    def mom_calc__nvt(self):
+        mom = np.zeros(self.shape_mom())
+        self._ck(self.lib.wm_mom_calc__nvt(self.h, _d(mom)))
+        return mom
+
+    def bc__mom(self, mom): self._ck(self.lib.wm_boundary__mom(self.h, _d(mom)))
 
     def ic_weibel(self, seed, n0, vti, vte, t_ani, b0):
         self._ck(self.lib.wm_ic_weibel(self.h, seed, n0, vti, vte, t_ani, b0))

@@ -114,6 +114,32 @@ __global__ void k_fold_y_local(const DevParams P, double *uj) {
   }
 }
 
+// mom: x fold of the single ghost column, all rows incl. ghosts   boundary_periodic.f90:579-584
+__global__ void k_mom_fold_x(const DevParams P, double *mom) {
+  const int nxp = P.nx + 3, nyp = P.nyl + 2;
+  const int n = P.nsp * nyp * 7;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int m = t % 7, row = t / 7;  // row = isp*nyp + j
+    double *r = mom + (size_t)row * nxp * 7 + m;
+    r[7 * 1] = r[7 * 1] + r[7 * (P.nx + 1)];  // nxgs += nxge+1
+    r[7 * P.nx] = r[7 * P.nx] + r[7 * 0];     // nxge += nxgs-1
+  }
+}
+
+// mom: y fold when the ring has one rank (the neighbour is this rank)    boundary_periodic.f90:586-633
+__global__ void k_mom_fold_y_local(const DevParams P, double *mom) {
+  const int nxp = P.nx + 3, nyp = P.nyl + 2;
+  const int w = nxp * 7;
+  const int n = P.nsp * w;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int isp = t / w, e = t - isp * w;
+    double *b = mom + (size_t)isp * nyp * w + e;
+    const double lo = b[0], hi = b[(size_t)(P.nyl + 1) * w];
+    b[(size_t)P.nyl * w] = b[(size_t)P.nyl * w] + lo;  // nye += (nup's) nys-1
+    b[(size_t)1 * w] = b[(size_t)1 * w] + hi;          // nys += (ndown's) nye+1
+  }
+}
+
 __global__ void k_add(double *__restrict__ dst, const double *__restrict__ src, long long n) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
     dst[t] = dst[t] + src[t];
@@ -439,6 +465,12 @@ void launch_fold_x(const DevParams &P, double *uj, cudaStream_t st) {
 }
 void launch_fold_y_local(const DevParams &P, double *uj, cudaStream_t st) {
   k_fold_y_local<<<gblocks((long long)P.pitch * 3), 256, 0, st>>>(P, uj);
+}
+void launch_mom_fold_x(const DevParams &P, double *mom, cudaStream_t st) {
+  k_mom_fold_x<<<gblocks((long long)P.nsp * (P.nyl + 2) * 7), 256, 0, st>>>(P, mom);
+}
+void launch_mom_fold_y_local(const DevParams &P, double *mom, cudaStream_t st) {
+  k_mom_fold_y_local<<<gblocks((long long)P.nsp * (P.nx + 3) * 7), 256, 0, st>>>(P, mom);
 }
 void launch_add_rows(double *dst, const double *src, long long n, cudaStream_t st) {
   k_add<<<gblocks(n), 256, 0, st>>>(dst, src, n);

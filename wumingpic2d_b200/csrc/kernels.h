@@ -42,6 +42,8 @@ void launch_fill_x(const DevParams &P, double *a, int ncomp, int ng, cudaStream_
 void launch_fill_y_local(const DevParams &P, double *a, int ncomp, int ng, cudaStream_t st);     // periodic y ghosts, nsize==1
 void launch_fold_x(const DevParams &P, double *uj, cudaStream_t st);                              // uj x fold + copy back
 void launch_fold_y_local(const DevParams &P, double *uj, cudaStream_t st);                        // uj y fold + refresh, nsize==1
+void launch_mom_fold_x(const DevParams &P, double *mom, cudaStream_t st);                        // mom x fold
+void launch_mom_fold_y_local(const DevParams &P, double *mom, cudaStream_t st);                  // mom y fold, nsize==1
 void launch_add_rows(double *dst, const double *src, long long n, cudaStream_t st);
 void launch_rhs(const DevParams &P, const FieldBufs &f, cudaStream_t st);
 void launch_cg_init(const DevParams &P, const FieldBufs &f, cudaStream_t st);      // phi<-df, b, sum b^2

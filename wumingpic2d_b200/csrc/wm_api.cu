@@ -91,6 +91,7 @@ struct wm_ctx {
   double ms[5] = {0, 0, 0, 0, 0};
   long long launches = 0;
   bool timing = true;
+  bool accl_valid = false;   // the idle store holds mom_calc__accl's half-step momenta
 };
 
 namespace {
@@ -578,6 +579,7 @@ static int stage_rows_h2d(wm_ctx *c, const double *up, const int32_t *np2, doubl
 
 int wm_upload_particles(wm_ctx *c, const double *up, const int32_t *np2) {
   if (!c || !up || !np2) return fail("wm_upload_particles: null argument");
+  c->accl_valid = false;
   WM(set_device(c));
   long long n[WM_NSP_MAX];
   WM(count_host(c, np2, n));
@@ -608,6 +610,7 @@ int wm_upload_particles(wm_ctx *c, const double *up, const int32_t *np2) {
 
 int wm_upload_particles_sorted(wm_ctx *c, const double *up, const int32_t *np2, const int32_t *cumcnt) {
   if (!c || !up || !np2 || !cumcnt) return fail("wm_upload_particles_sorted: null argument");
+  c->accl_valid = false;
   WM(set_device(c));
   long long n[WM_NSP_MAX];
   WM(count_host(c, np2, n));
@@ -652,6 +655,7 @@ int wm_upload_field(wm_ctx *c, const double *uf) {
 }
 
 static int download_store(wm_ctx *c, int buf, double *up, int32_t *np2, int32_t *cumcnt, double *stage_override) {
+  c->accl_valid = false;
   const DevParams &P = c->P;
   std::vector<int> cs((size_t)P.nsp * (P.ncell + 1));
   CU(cudaMemcpyAsync(cs.data(), c->cstart[c->cur], cs.size() * sizeof(int), cudaMemcpyDeviceToHost, c->st));
@@ -746,6 +750,7 @@ int wm_particle_counts(wm_ctx *c, int64_t *n) {
 // ---------------------------------------------------------------- stage calls
 int wm_particle__solv(wm_ctx *c) {
   WM(need_state(c, ST_SORTED, "wm_particle__solv"));
+  c->accl_valid = false;
   WM(set_device(c));
   launch_tmpf(c->P, c->f.uf, c->f.tmpf, c->st);
   const int mode = M_PUSH | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
@@ -833,6 +838,7 @@ int wm_sort__bucket(wm_ctx *c) {
 
 int wm_step(wm_ctx *c, int32_t nsteps) {
   WM(need_state(c, ST_SORTED, "wm_step"));
+  c->accl_valid = false;
   WM(set_device(c));
   const DevParams &P = c->P;
   const size_t ng = (size_t)P.pitch * (P.nyl + 4);
@@ -945,43 +951,95 @@ int wm_energy(wm_ctx *c, double *out) {
   return 0;
 }
 
-int wm_moments(wm_ctx *c, double *mom) {
-  WM(need_state(c, ST_SORTED, "wm_moments"));
-  if (!mom) return fail("wm_moments: null argument");
-  if (c->P.nsize > 1) return fail("wm_moments: multi-rank bc__mom not implemented yet");
+// bc__mom on the device copy: x fold, then the one-row y fold on the ring   boundary_periodic.f90:571-636
+static int bc_mom_device(wm_ctx *c) {
+  const DevParams &P = c->P;
+  launch_mom_fold_x(P, c->mom, c->st);
+  c->launches++;
+  if (P.nsize == 1) {
+    launch_mom_fold_y_local(P, c->mom, c->st);
+    c->launches++;
+    return 0;
+  }
+  if (!c->comm) return fail("nsize > 1 but wm_comm_init has not been called");
+  const size_t w = (size_t)(P.nx + 3) * 7;
+  const size_t nyp = (size_t)P.nyl + 2;
+  for (int isp = 0; isp < P.nsp; isp++) {
+    double *b = c->mom + (size_t)isp * nyp * w;
+    // my ghost row nys-1 -> ndown ; nup's is added into my nye
+    NC(ncclGroupStart());
+    NC(ncclSend(b, w, ncclDouble, c->ndown, c->comm, c->st));
+    NC(ncclRecv(c->rowtmp, w, ncclDouble, c->nup, c->comm, c->st));
+    NC(ncclGroupEnd());
+    launch_add_rows(b + (size_t)P.nyl * w, c->rowtmp, (long long)w, c->st);
+    // my ghost row nye+1 -> nup ; ndown's is added into my nys
+    NC(ncclGroupStart());
+    NC(ncclSend(b + (size_t)(P.nyl + 1) * w, w, ncclDouble, c->nup, c->comm, c->st));
+    NC(ncclRecv(c->rowtmp, w, ncclDouble, c->ndown, c->comm, c->st));
+    NC(ncclGroupEnd());
+    launch_add_rows(b + w, c->rowtmp, (long long)w, c->st);
+    c->launches += 2;
+  }
+  return 0;
+}
+
+static size_t mom_elems(const wm_ctx *c) { return (size_t)7 * (c->P.nx + 3) * (c->P.nyl + 2) * c->P.nsp; }
+
+int wm_mom_calc__accl(wm_ctx *c) {
+  WM(need_state(c, ST_SORTED, "wm_mom_calc__accl"));
   WM(set_device(c));
   const DevParams &P = c->P;
-  // mom_calc__accl: half-step acceleration into the idle store (mom_calc.f90:34,48-164)
+  // half-step acceleration into the idle store, positions copied (mom_calc.f90:34,48-164)
   launch_tmpf(P, c->f.uf, c->f.tmpf, c->st);
   const int mode = M_PUSH | M_NOMOVE | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
   launch_pass1(mode, P, p1args(c, c->soa[c->cur], c->soa[c->cur ^ 1], P.delt * 0.5), c->st);
-  const size_t nm = (size_t)7 * (P.nx + 3) * (P.nyl + 2) * P.nsp;
-  CU(cudaMemsetAsync(c->mom, 0, nm * sizeof(double), c->st));
-  launch_moments(P, c->soa[c->cur ^ 1], c->cstart[c->cur], c->mom, c->st);
-  c->launches += 3;
-  CU(cudaMemcpyAsync(mom, c->mom, nm * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  c->launches += 2;
+  CU(cudaGetLastError());
+  c->accl_valid = true;
+  return 0;
+}
+
+static int mom_nvt_device(wm_ctx *c) {
+  if (!c->accl_valid) return fail("wm_mom_calc__nvt: call wm_mom_calc__accl first (proj/weibel/app.f90:121-122)");
+  CU(cudaMemsetAsync(c->mom, 0, mom_elems(c) * sizeof(double), c->st));
+  launch_moments(c->P, c->soa[c->cur ^ 1], c->cstart[c->cur], c->mom, c->st);
+  c->launches++;
+  return 0;
+}
+
+int wm_mom_calc__nvt(wm_ctx *c, double *mom) {
+  WM(need_state(c, ST_SORTED, "wm_mom_calc__nvt"));
+  if (!mom) return fail("wm_mom_calc__nvt: null argument");
+  WM(set_device(c));
+  WM(mom_nvt_device(c));
+  CU(cudaMemcpyAsync(mom, c->mom, mom_elems(c) * sizeof(double), cudaMemcpyDeviceToHost, c->st));
   CU(cudaStreamSynchronize(c->st));
-  // bc__mom on the host copy (boundary_periodic.f90:571-636), single rank: ring neighbour is self
-  const int nxp = P.nx + 3, nyp = P.nyl + 2;
-  auto M = [&](int m, int i, int j, int isp) -> double & { return mom[(size_t)m + 7 * ((size_t)i + (size_t)nxp * ((size_t)j + (size_t)nyp * isp))]; };
-  for (int isp = 0; isp < P.nsp; isp++) {
-    for (int j = 0; j < nyp; j++)
-      for (int m = 0; m < 7; m++) {
-        M(m, 1, j, isp) += M(m, P.nx + 1, j, isp);   // nxgs += nxge+1
-        M(m, P.nx, j, isp) += M(m, 0, j, isp);       // nxge += nxgs-1
-      }
-    for (int i = 0; i < nxp; i++)
-      for (int m = 0; m < 7; m++) {
-        const double lo = M(m, i, 0, isp), hi = M(m, i, P.nyl + 1, isp);
-        M(m, i, P.nyl, isp) += lo;  // nye += (nup's) nys-1
-        M(m, i, 1, isp) += hi;      // nys += (ndown's) nye+1
-      }
-  }
+  return 0;
+}
+
+int wm_boundary__mom(wm_ctx *c, double *mom) {
+  if (!c || !mom) return fail("wm_boundary__mom: null argument");
+  WM(set_device(c));
+  CU(cudaMemcpyAsync(c->mom, mom, mom_elems(c) * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  WM(bc_mom_device(c));
+  CU(cudaMemcpyAsync(mom, c->mom, mom_elems(c) * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int wm_moments(wm_ctx *c, double *mom) {
+  if (!mom) return fail("wm_moments: null argument");
+  WM(wm_mom_calc__accl(c));
+  WM(mom_nvt_device(c));
+  WM(bc_mom_device(c));
+  CU(cudaMemcpyAsync(mom, c->mom, mom_elems(c) * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
   return 0;
 }
 
 int wm_ic_weibel(wm_ctx *c, uint64_t seed, int32_t n0, double vti, double vte, double t_ani, double b0) {
   if (!c) return fail("wm_ic_weibel: null context");
+  c->accl_valid = false;
   WM(set_device(c));
   DevParams &P = c->P;
   const long long n = (long long)n0 * P.nx * P.nyl;
