@@ -1,9 +1,10 @@
 #!/bin/bash
 # Quick GPU visit: parity tests, resident bench, ncu full capture of the particle kernels (small slab).
+# Usage: bash scripts/gpu_quick.sh <tag> [noncu]
 TAG=${1:-quick}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 ) > $OUT/pytest_gpu.log
+( timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 ) > $OUT/pytest_gpu.log
 ( timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu 2> $OUT/bench.err | tail -1 ) > $OUT/bench.json
 if [ "$2" != "noncu" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_fused|k_pass2" -s 4 -c 2 -o $OUT/prof_pass \

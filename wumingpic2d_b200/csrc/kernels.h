@@ -10,6 +10,8 @@ enum { M_PUSH = 1, M_DEPOSIT = 2, M_BOUND = 4, M_EXACT = 8, M_NOMOVE = 16 };
 void launch_pass1(int mode, const DevParams &P, const Pass1Args &a, cudaStream_t st);
 // fused push + deposit + particle boundaries + histogram, FMA arithmetic (fused_kernel.cu)
 void launch_fused(const DevParams &P, const Pass1Args &a, cudaStream_t st);
+// second generation: accumulators split over the 8 lanes of a cell (fused2_kernel.cu)
+void launch_fused2(const DevParams &P, const Pass1Args &a, cudaStream_t st);
 void launch_pass2(const DevParams &P, const PartSoA &src, const PartSoA &dst, const int *cstart_old,
                   const int *cstart_new, const int *tilebase, const uint32_t *tag, unsigned *err, cudaStream_t st);
 int scan_scratch_ints(int n);

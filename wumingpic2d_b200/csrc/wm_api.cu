@@ -91,6 +91,7 @@ struct wm_ctx {
   double ms[5] = {0, 0, 0, 0, 0};
   long long launches = 0;
   bool timing = true;
+  int fused_variant = 1;     // WM_FUSED=2 selects k_fused2 (lane-split accumulators; slower so far: profiles/r01c)
   bool accl_valid = false;   // the idle store holds mom_calc__accl's half-step momenta
 };
 
@@ -397,6 +398,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
     return fail("wm_create: no CUDA device available (this library has no CPU fallback)");
   wm_ctx *c = new wm_ctx();
   c->cfg = *g;
+  if (const char *v = getenv("WM_FUSED")) c->fused_variant = atoi(v);
   if (g->device >= 0) {
     c->dev = g->device;
   } else {
@@ -854,8 +856,10 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
     if (c->timing) CU(cudaEventRecord(c->ev[1], c->st));
     if (c->cfg.flags & WM_FLAG_EXACT_PUSH)
       launch_pass1(mode, P, p1args(c, a, a, P.delt), c->st);
-    else
+    else if (c->fused_variant == 1)
       launch_fused(P, p1args(c, a, a, P.delt), c->st);
+    else
+      launch_fused2(P, p1args(c, a, a, P.delt), c->st);
     c->launches += 2;
     if (c->timing) CU(cudaEventRecord(c->ev[2], c->st));
     // rest of field__fdtd_i
