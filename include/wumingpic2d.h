@@ -152,6 +152,8 @@ int wm_ic_weibel(wm_ctx *ctx, uint64_t seed, int32_t n0, double vti, double vte,
  * [4] whole wm_step calls (first launch to last completion); launches = kernels launched */
 int wm_timing(wm_ctx *ctx, double ms[5], int64_t *launches, int32_t reset);
 int wm_synchronize(wm_ctx *ctx);
+/* how often wm_step had to rebuild the particle layout because a cell segment overflowed */
+int wm_layout_rebuilds(wm_ctx *ctx, int64_t *n);
 
 #ifdef __cplusplus
 }

@@ -275,3 +275,30 @@ def test_call_order_is_enforced(warm):
     with pytest.raises(wm.WmError):
         c.sort__bucket()            # boundary not applied yet
     c.close()
+
+
+@pytest.mark.parametrize("env", [{"WM_INPLACE": "0"}, {"WM_SLACK": "0.4"}, {"WM_SLACK": "12"}, {"WM_FUSED": "2"}])
+def test_sort_variants_match_oracle(env, monkeypatch):
+    """wm_step with (a) the tag + scatter sort, (b) the in-place sort with so little segment slack that
+    segments overflow and the layout is rebuilt nearly every step, (c) generous slack, (d) k_fused2:
+    per-cell counts bit-exact and particles/fields within tolerance in every case."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    prm, w = make_world(40, 24, 16)
+    s = oracle_state(w)
+    c = ctx_for(prm)
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    c.upload_field(s["uf"])
+    for _ in range(3):
+        w.step(4)
+        c.step(4)
+        up, np2, cum = c.download_particles()
+        assert np.array_equal(cum, w.array(0, O.CUMCNT)), "per-cell counts must be bit-exact"
+        a, b = flatten_by_id(up, np2), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+        ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+        assert ex <= 1e-9 and eu <= 1e-9
+        assert rel_to_max(c.download_field(), w.array(0, O.UF)).max() <= 1e-9
+    if env.get("WM_SLACK") == "0.4":
+        assert c.rebuilds() > 0, "the overflow -> rebuild path was not exercised"
+    c.close()

@@ -48,7 +48,7 @@ EXPORTS = [
     "wm_particle_counts", "wm_particle__solv", "wm_field__ele_cur", "wm_boundary__curre",
     "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_sort__bucket",
     "wm_step", "wm_host_step", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
-    "wm_energy", "wm_moments", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_ic_weibel", "wm_timing", "wm_synchronize",
+    "wm_energy", "wm_moments", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_ic_weibel", "wm_timing", "wm_synchronize", "wm_layout_rebuilds",
 ]
 
 
@@ -110,6 +110,7 @@ def load_library():
     lib.wm_boundary__mom.argtypes = [P, D]
     lib.wm_ic_weibel.argtypes = [P, C.c_uint64, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]
     lib.wm_timing.argtypes = [P, D, C.POINTER(C.c_int64), C.c_int32]
+    lib.wm_layout_rebuilds.argtypes = [P, C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 
@@ -277,6 +278,11 @@ class Context:
 
     def ic_weibel(self, seed, n0, vti, vte, t_ani, b0):
         self._ck(self.lib.wm_ic_weibel(self.h, seed, n0, vti, vte, t_ani, b0))
+
+    def rebuilds(self):
+        n = C.c_int64()
+        self._ck(self.lib.wm_layout_rebuilds(self.h, C.byref(n)))
+        return n.value
 
     def timing(self, reset=True):
         ms = (C.c_double * 5)()

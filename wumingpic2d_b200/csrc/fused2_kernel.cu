@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(FT, 4) k_fused2(const DevParams P, const Pass1
       int beg = 0, end = 0;
       if (valid) {
         beg = a.cstart[(size_t)isp * (P.ncell + 1) + cell];
-        end = a.cstart[(size_t)isp * (P.ncell + 1) + cell + 1];
+        end = beg + a.cnt[(size_t)isp * P.ncell + cell];
       }
       int nmax = end - beg;
       nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));

@@ -108,11 +108,21 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 
 }  // namespace
 
+// INPLACE = false: every particle gets a sort tag and k_pass2 scatters the whole store afterwards.
+// INPLACE = true : the sort only moves the particles that change cell.  Stayers are compacted to the
+//                  front of their own segment as they are written back (slot = running stayer count +
+//                  popc(ballot below me); never ahead of a slot that is still to be read).  A cell
+//                  changer is staged, ranked by a warp ballot, in the shadow of its quad in the idle
+//                  store (a.dst) with a tag (window cell, rank); k_place appends the staged records to
+//                  their new segments, k_mark_dead retires the vacated slots.  No scatter pass, no
+//                  per-particle tag, no global atomics in the particle loop.
+template <bool INPLACE>
 __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1Args a) {
   __shared__ __align__(128) double s_f[WINY * WINX * 6];
   __shared__ __align__(16) double s_j[3 * JY * JX];
   __shared__ int s_stay[WM_NSP_MAX * TX * TY];
   __shared__ int s_arr[WM_NSP_MAX * WIN];
+  __shared__ int s_nmv[INPLACE ? WM_NSP_MAX * NQ : 1];
   __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x;
@@ -165,7 +175,7 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
       int beg = 0, end = 0;
       if (valid) {
         beg = a.cstart[(size_t)isp * (P.ncell + 1) + cell];
-        end = a.cstart[(size_t)isp * (P.ncell + 1) + cell + 1];
+        end = beg + a.cnt[(size_t)isp * P.ncell + cell];
       }
       int nmax = end - beg;
       nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));
@@ -179,8 +189,13 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
       const double qf = qs * qf_base;  // q*delx*d_delt, field.f90:278
 
       int nst = 0;  // stayers of this (cell, species) so far
+      int nmv = 0;  // cell changers of this (quad, species) so far (INPLACE)
+      // staging region of this quad in the idle store: starts at the segment of the quad's first cell
+      const int qbeg = (INPLACE && cy < th && (q - cy * QX) * 4 < tw)
+                           ? a.cstart[(size_t)isp * (P.ncell + 1) + (lj0 + cy) * P.nx + li0 + (q - cy * QX) * 4]
+                           : 0;
       int p = beg + l8;
-      double nx_ = 0.0, ny_ = 0.0, nu1 = 0.0, nu2 = 0.0, nu3 = 0.0;
+      double nx_ = 0.0, ny_ = 0.0, nu1 = 0.0, nu2 = 0.0, nu3 = 0.0, nid = 0.0;
       if (p < end) {
         const double *b = px + so + p;
         nx_ = b[0];
@@ -188,11 +203,12 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
         nu1 = b[2 * cstride];
         nu2 = b[3 * cstride];
         nu3 = b[4 * cstride];
+        if (INPLACE) nid = b[5 * cstride];
       }
       for (int k = 0; k < nmax; k += 8) {
         const int pc = p;
         const bool active = pc < end;
-        const double x = nx_, y = ny_, u1 = nu1, u2 = nu2, u3 = nu3;
+        const double x = nx_, y = ny_, u1 = nu1, u2 = nu2, u3 = nu3, idc = nid;
         p += 8;
         if (p < end) {  // prefetch the next particle of this lane
           const double *b = px + so + p;
@@ -201,9 +217,10 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
           nu1 = b[2 * cstride];
           nu2 = b[3 * cstride];
           nu3 = b[4 * cstride];
+          if (INPLACE) nid = b[5 * cstride];  // the id moves with the record (bit pattern)
         }
         bool stay = false;
-        double xn = 0.0, yn = 0.0;
+        double xn = 0.0, yn = 0.0, un1 = 0.0, un2 = 0.0, un3 = 0.0;
         if (active) {
           // ---- second order shape function about the sorted cell       particle.f90:97-105
           const double hx = x - cxh, hy = y - cyh;
@@ -243,14 +260,16 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
           uvm1 = fma(fac2r, fma(uvm5, f2, -(uvm6 * f1)), uvm1);
           uvm2 = fma(fac2r, fma(uvm6, f0, -(uvm4 * f2)), uvm2);
           uvm3 = fma(fac2r, fma(uvm4, f1, -(uvm5 * f0)), uvm3);
-          const double un1 = fma(fac1, f3, uvm1), un2 = fma(fac1, f4, uvm2), un3 = fma(fac1, f5, uvm3);
+          un1 = fma(fac1, f3, uvm1);
+          un2 = fma(fac1, f4, uvm2);
+          un3 = fma(fac1, f5, uvm3);
           // ---- move                                                      particle.f90:156-161
           const double uu = fma(un3, un3, fma(un2, un2, un1 * un1));
           const double wmove = rsqrt_fast(fma(uu, inv_cc, 1.0));
           const double dtw = delt * wmove;
           xn = fma(un1, dtw, x);
           yn = fma(un2, dtw, y);
-          {
+          if (!INPLACE) {
             double *b = px + so + pc;
             b[2 * cstride] = un1;
             b[3 * cstride] = un2;
@@ -324,11 +343,23 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
         }
         // ---- sort bookkeeping                                             sort.f90:57-62
         const unsigned bal = __ballot_sync(0xffffffffu, stay);
+        const unsigned balm = INPLACE ? __ballot_sync(0xffffffffu, active && !stay) : 0u;  // changers + leavers
         if (active) {
           const unsigned m8 = (bal >> (grp * 8)) & 0xffu;
+          const int srank = nst + __popc(m8 & below);  // my rank among the stayers of this cell
           uint32_t tg;
           if (stay) {
-            tg = ((uint32_t)((cy + 1) * WINX + (cx + 1)) << TAG_WSHIFT) | (uint32_t)(nst + __popc(m8 & below));
+            tg = ((uint32_t)((cy + 1) * WINX + (cx + 1)) << TAG_WSHIFT) | (uint32_t)srank;
+            if (INPLACE) {
+              // stable compaction inside the segment: slot beg + srank <= pc
+              double *d = px + so + beg + srank;
+              d[0] = xn;
+              d[cstride] = yn;
+              d[2 * cstride] = un1;
+              d[3 * cstride] = un2;
+              d[4 * cstride] = un3;
+              if (beg + srank != pc) d[5 * cstride] = idc;
+            }
           } else {
             // cell changers: periodic wraps with round-toward -inf adds  boundary_periodic.f90:74,82-88,124,147-154
             int incx = (xn >= di1) - (xn < di), incy = (yn >= dj1) - (yn < dj);
@@ -347,19 +378,29 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
             else if (yn >= yhi)
               yn = __dadd_rd(yn, -P.ylen);
             const bool leaves = (P.nsize > 1) && (j2 < P.nys || j2 >= P.nys + P.nyl);
+            const double idv = INPLACE ? idc : (leaves ? px[so + pc + 5 * cstride] : 0.0);  // id, bit pattern
+            if (INPLACE) {
+              // stage the record in the idle store, in the shadow of this quad (slot order = ballot rank)
+              double *d = a.dst.x + so + qbeg + nmv + __popc(balm & ((1u << lane) - 1u));
+              d[0] = xn;
+              d[cstride] = yn;
+              d[2 * cstride] = un1;
+              d[3 * cstride] = un2;
+              d[4 * cstride] = un3;
+              d[5 * cstride] = idv;
+            }
             if (leaves) {
               // record goes to the neighbour's edge row        boundary_periodic.f90:156-161,174-189
               const int dir = (j2 < P.nys) ? 0 : 1;
               const int pos = atomicAdd(&a.sendcnt[dir * P.nsp + isp], 1);
               if (pos < a.sendcap) {
                 double *rec = a.send[dir] + ((size_t)isp * a.sendcap + pos) * 6;
-                const double *b = px + so + pc;
                 rec[0] = xn;
                 rec[1] = yn;
-                rec[2] = b[2 * cstride];
-                rec[3] = b[3 * cstride];
-                rec[4] = b[4 * cstride];
-                rec[5] = b[5 * cstride];  // id, bit pattern
+                rec[2] = un1;
+                rec[3] = un2;
+                rec[4] = un3;
+                rec[5] = idv;
               } else {
                 atomicOr(a.err, ERR_SENDBUF);
               }
@@ -369,15 +410,23 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
               const int rk = atomicAdd(&s_arr[isp * WIN + w], 1);
               tg = TAG_ARRIVAL | ((uint32_t)w << TAG_WSHIFT) | (uint32_t)rk;
             }
+            if (INPLACE) a.tag[so + qbeg + nmv + __popc(balm & ((1u << lane) - 1u))] = tg;
           }
-          double *b = px + so + pc;
-          b[0] = xn;
-          b[cstride] = yn;
-          a.tag[so + pc] = tg;
+          if (!INPLACE) {
+            double *b = px + so + pc;
+            b[0] = xn;
+            b[cstride] = yn;
+            a.tag[so + pc] = tg;
+          }
           nst += __popc(m8);
         }
+        nmv += __popc(balm);
       }
-      if (valid && l8 == 0) s_stay[isp * (TX * TY) + cy * TX + cx] = nst;
+      if (INPLACE) {
+        if (valid && l8 == 0) a.cnt_tail[(size_t)isp * P.ncell + cell] = nst;  // arrivals are added by k_place
+        if (lane == 0) s_nmv[isp * NQ + q] = nmv;
+      }
+      if (!INPLACE && valid && l8 == 0) s_stay[isp * (TX * TY) + cy * TX + cx] = nst;
     }
 
     // ---- reduce-scatter the 65 partial sums over the 8 lanes of the cell   field.f90:304-310
@@ -428,6 +477,16 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
       if (v != 0.0) atomicAdd(&a.uj[((size_t)(lj0 + jy) * P.pitch + (li0 + jx)) * 3 + comp], v);
     }
   }
+  if (INPLACE) {
+    // ---- hand the tile's arrival counts per window cell and its staged-record counts to k_place
+    int *tb = a.tilebase + (size_t)tile * P.nsp * (2 * WIN);
+    for (int e = tid; e < P.nsp * WIN; e += FT) {
+      const int isp = e / WIN, w = e - isp * WIN;
+      tb[isp * (2 * WIN) + w] = s_arr[e];
+      if (w < NQ) tb[isp * (2 * WIN) + WIN + w] = s_nmv[isp * NQ + w];
+    }
+    return;
+  }
   // ---- reserve this tile's share of every destination cell                  sort.f90:57-62
   for (int e = tid; e < P.nsp * WIN; e += FT) {
     const int isp = e / WIN, w = e - isp * WIN;
@@ -452,7 +511,10 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
 }
 
 void launch_fused(const DevParams &P, const Pass1Args &a, cudaStream_t st) {
-  k_fused<<<P.ntx * P.nty, FT, 0, st>>>(P, a);
+  k_fused<false><<<P.ntx * P.nty, FT, 0, st>>>(P, a);
+}
+void launch_fused_inplace(const DevParams &P, const Pass1Args &a, cudaStream_t st) {
+  k_fused<true><<<P.ntx * P.nty, FT, 0, st>>>(P, a);
 }
 
 }  // namespace wm

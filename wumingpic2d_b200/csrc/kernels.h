@@ -13,21 +13,40 @@ void launch_fused(const DevParams &P, const Pass1Args &a, cudaStream_t st);
 // second generation: accumulators split over the 8 lanes of a cell (fused2_kernel.cu)
 void launch_fused2(const DevParams &P, const Pass1Args &a, cudaStream_t st);
 void launch_pass2(const DevParams &P, const PartSoA &src, const PartSoA &dst, const int *cstart_old,
-                  const int *cstart_new, const int *tilebase, const uint32_t *tag, unsigned *err, cudaStream_t st);
+                  const int *cstart_new, const int *tilebase, const uint32_t *tag, const double *keyx, unsigned *err,
+                  cudaStream_t st);
 int scan_scratch_ints(int n);
-int launch_scan(const int *in, int *out, int *scratch, int n, cudaStream_t st);
-void launch_incoming_tag(const DevParams &P, const double *rec, int n, int isp, int *gcnt, int *rank, unsigned *err,
-                         cudaStream_t st);
-void launch_incoming_scatter(const DevParams &P, const double *rec, int n, int isp, const int *cstart_new,
+// exclusive scan of cell_capacity(in[c], sl): sl = 0 gives the tight offsets (cumcnt), sl > 0 the segment offsets
+int launch_scan(const int *in, int *out, int *scratch, int n, float sl, cudaStream_t st);
+void launch_incoming_tag(const DevParams &P, const double *rec, int n, int isp, const int *spv, int *gcnt, int *rank,
+                         unsigned *err, cudaStream_t st);
+void launch_incoming_scatter(const DevParams &P, const double *rec, int n, int isp, const int *spv, const int *cstart_new,
                              const int *rank, const PartSoA &dst, unsigned *err, cudaStream_t st);
 void launch_aos2soa(const double *rec, long long n, size_t so, const PartSoA &dst, cudaStream_t st);
 void launch_soa2aos(const PartSoA &src, size_t so, long long n, double *rec, cudaStream_t st);
 void launch_bcx(const DevParams &P, double *x, const int *cstart, cudaStream_t st);
-void launch_ic_weibel(const DevParams &P, const PartSoA &dst, int *cstart, uint64_t seed, int n0, double vti,
-                      double vte, double t_ani, cudaStream_t st);
+void launch_ic_weibel(const DevParams &P, const PartSoA &dst, int *cstart, int *cnt, uint64_t seed, int n0, double vti,
+                      double vte, double t_ani, float sl, cudaStream_t st);
+void launch_relayout_from_aos(const DevParams &P, const double *rec, long long n, const int *tight, const int *cstart_dst,
+                              const PartSoA &dst, size_t so, unsigned *err, cudaStream_t st);
+void launch_relayout_to_aos(const DevParams &P, const PartSoA &key, const PartSoA &val, size_t so, const int *cstart_src,
+                            const int *tight, double *rec, cudaStream_t st);
+void launch_relayout_soa(const DevParams &P, const PartSoA &src, const int *cstart_src, const PartSoA &dst,
+                         const int *cstart_dst, size_t so, unsigned *err, cudaStream_t st);
+void launch_incoming_append(const DevParams &P, const double *rec, int n, int isp, const int *cstart, int *cnt_tail,
+                            const PartSoA &dst, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
+                            cudaStream_t st);
+// in-place sort: append the records staged by k_fused<INPLACE> to their new segments, retire vacated slots
+void launch_place(const DevParams &P, const PartSoA &stage, const PartSoA &dst, const int *cstart, int *cnt_new,
+                  const int *tilebase, const uint32_t *tag, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
+                  cudaStream_t st);
+void launch_mark_dead(const DevParams &P, double *x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st);
+// fused push + deposit + boundaries that moves cell changers itself (no tags, no scatter pass)
+void launch_fused_inplace(const DevParams &P, const Pass1Args &a, cudaStream_t st);
 void launch_kinetic(const DevParams &P, const PartSoA &src, const int *cstart, int isp, double *partial, int nblocks,
                     cudaStream_t st);
-void launch_moments(const DevParams &P, const PartSoA &src, const int *cstart, double *mom, cudaStream_t st);
+void launch_moments(const DevParams &P, const PartSoA &src, const double *keyx, const int *cstart, double *mom,
+                    cudaStream_t st);
 
 // ---- fields
 struct FieldBufs {

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) k_pass1(const DevParams P, cons
       const double di = (double)gi, dj = (double)gj;
       for (int isp = 0; isp < P.nsp; isp++) {
         const int beg = a.cstart[(size_t)isp * (P.ncell + 1) + cell];
-        const int end = a.cstart[(size_t)isp * (P.ncell + 1) + cell + 1];
+        const int end = beg + a.cnt[(size_t)isp * P.ncell + cell];
         const size_t so = (size_t)isp * P.cap;
         const double qs = P.q[isp];
         // particle.f90:90-92
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) k_pass1(const DevParams P, cons
 __global__ void __launch_bounds__(256) k_pass2(const DevParams P, const PartSoA src, const PartSoA dst,
                                                const int *__restrict__ cstart_old, const int *__restrict__ cstart_new,
                                                const int *__restrict__ tilebase, const uint32_t *__restrict__ tag,
-                                               unsigned *err) {
+                                               const double *__restrict__ keyx, unsigned *err) {
   __shared__ int s_base[WM_NSP_MAX * 512];  // [isp][kind][256]: indexed by the top 9 bits of a tag
   const int tid = threadIdx.x, tile = blockIdx.x;
   const int li0 = (tile % P.ntx) * TX, lj0 = (tile / P.ntx) * TY;
@@ -422,7 +422,8 @@ __global__ void __launch_bounds__(256) k_pass2(const DevParams P, const PartSoA 
       const int c0 = (lj0 + cy) * P.nx + li0;
       const int beg = cstart_old[(size_t)isp * (P.ncell + 1) + c0];
       const int end = cstart_old[(size_t)isp * (P.ncell + 1) + c0 + tw];
-      for (int p = beg + tid; p < end; p += blockDim.x) {
+      for (int p = beg + tid; p < end; p += blockDim.x) {  // capacity span of the tile row: skip gaps
+        if (!slot_live(keyx[so + p])) continue;  // gaps: only the sorted store marks them
         const uint32_t t = tag[so + p];
         if (t == TAG_DEAD) continue;
         const int d = s_base[isp * 512 + (t >> TAG_WSHIFT)] + (int)(t & TAG_RANK_MASK);
@@ -475,12 +476,12 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
   return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partial(const int *__restrict__ in, int *__restrict__ bsum, int n) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partial(const int *__restrict__ in, int *__restrict__ bsum, int n, float sl) {
   const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int s = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++)
-    if (base + k < n) s += in[base + k];
+    if (base + k < n) s += cell_capacity(in[base + k], sl);
   int tot;
   block_exclusive_scan(s, &tot);
   if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
@@ -505,12 +506,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_bsums(int *bsum, int nb) 
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const int *__restrict__ in, const int *__restrict__ bsum,
-                                                             int *__restrict__ out, int n) {
+                                                             int *__restrict__ out, int n, float sl) {
   const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS], s = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
-    v[k] = (base + k < n) ? in[base + k] : 0;
+    v[k] = (base + k < n) ? cell_capacity(in[base + k], sl) : 0;
     s += v[k];
   }
   int tot;
@@ -525,10 +526,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const int *__restri
 
 // ---------------------------------------------------------------- records <-> SoA
 // incoming records (uploads, migrated particles): rank inside the destination cell by global atomics
-__global__ void k_incoming_tag(const DevParams P, const double *__restrict__ rec, int n, int isp, int *gcnt,
-                               int *__restrict__ rank, unsigned *err) {
+// spv != nullptr: the species of record s is spv[s] (the overflow list mixes species)
+__global__ void k_incoming_tag(const DevParams P, const double *__restrict__ rec, int n, int isp, const int *__restrict__ spv,
+                               int *gcnt, int *__restrict__ rank, unsigned *err) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
+  if (spv) isp = spv[s];
   const int li = __double2int_rz(rec[(size_t)s * 6 + 0]) - P.nxgs;
   const int lj = __double2int_rz(rec[(size_t)s * 6 + 1]) - P.nys;
   if (li < 0 || li >= P.nx || lj < 0 || lj >= P.nyl) {
@@ -540,11 +543,12 @@ __global__ void k_incoming_tag(const DevParams P, const double *__restrict__ rec
 }
 
 __global__ void k_incoming_scatter(const DevParams P, const double *__restrict__ rec, int n, int isp,
-                                   const int *__restrict__ cstart_new, const int *__restrict__ rank, const PartSoA dst,
-                                   unsigned *err) {
+                                   const int *__restrict__ spv, const int *__restrict__ cstart_new,
+                                   const int *__restrict__ rank, const PartSoA dst, unsigned *err) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   if (rank[s] < 0) return;
+  if (spv) isp = spv[s];
   const double *r = rec + (size_t)s * 6;
   const int cell = (__double2int_rz(r[1]) - P.nys) * P.nx + (__double2int_rz(r[0]) - P.nxgs);
   const long long d = (long long)cstart_new[(size_t)isp * (P.ncell + 1) + cell] + rank[s];
@@ -592,6 +596,7 @@ __global__ void k_bcx(const DevParams P, double *x, const int *__restrict__ csta
     const int n = cstart[(size_t)isp * (P.ncell + 1) + P.ncell];
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
       double v = x[(size_t)isp * P.cap + s];
+      if (!slot_live(v)) continue;
       const int ipos = __double2int_rz(v);
       if (ipos < P.nxgs) {
         x[(size_t)isp * P.cap + s] = __dadd_rd(v, P.xlen);
@@ -616,8 +621,10 @@ __device__ __forceinline__ double rng_uniform(uint64_t seed, int isp, uint64_t g
   return ((double)(k >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-__global__ void k_ic_weibel(const DevParams P, const PartSoA dst, int *cstart, uint64_t seed, int n0, double vti,
-                            double vte, double t_ani) {
+// The x array of `dst` must have been filled with the dead pattern: only live slots are written.
+__global__ void k_ic_weibel(const DevParams P, const PartSoA dst, int *cstart, int *cnt, uint64_t seed, int n0, double vti,
+                            double vte, double t_ani, float sl) {
+  const int capc = cell_capacity(n0, sl);
   const long long npr = (long long)n0 * P.nx;
   const long long ntot = npr * P.nyl;
   const double PI = 3.14159265358979323846;
@@ -634,7 +641,9 @@ __global__ void k_ic_weibel(const DevParams P, const PartSoA dst, int *cstart, u
       const double rr1 = sqrt(-2 * log(1 - u1) + 1.0e-30);
       const double rr2 = sqrt(-2 * log(1 - u3) + 1.0e-30);
       const double sd = (isp & 1) ? vte : vti;
-      const size_t o = (size_t)isp * P.cap + s;
+      // evenly spaced x: slot ii of the row lies in cell (ii-1)/n0   (app.f90:315-328,408)
+      const long long cell = (long long)lj * P.nx + (ii - 1) / n0;
+      const size_t o = (size_t)isp * P.cap + (size_t)(cell * capc + (ii - 1) % n0);
       dst.x[o] = x;
       dst.y[o] = y;
       dst.ux[o] = sd * (rr1 * sin(2 * PI * u2));
@@ -645,7 +654,10 @@ __global__ void k_ic_weibel(const DevParams P, const PartSoA dst, int *cstart, u
   }
   // analytic cell offsets for the evenly spaced load (app.f90:315-328)
   for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c <= P.ncell; c += (long long)gridDim.x * blockDim.x)
-    for (int isp = 0; isp < P.nsp; isp++) cstart[(size_t)isp * (P.ncell + 1) + c] = (int)(c * n0);
+    for (int isp = 0; isp < P.nsp; isp++) {
+      cstart[(size_t)isp * (P.ncell + 1) + c] = (int)(c * capc);
+      if (c < P.ncell) cnt[(size_t)isp * P.ncell + c] = n0;
+    }
 }
 
 // kinetic energy per species (app.f90:507-519); one partial per block, summed on the host in order
@@ -656,6 +668,7 @@ __global__ void __launch_bounds__(256) k_kinetic(const DevParams P, const PartSo
   const size_t so = (size_t)isp * P.cap;
   double s = 0.0;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    if (!slot_live(src.x[so + p])) continue;
     const double u1 = src.ux[so + p], u2 = src.uy[so + p], u3 = src.uz[so + p];
     const double uu = u1 * u1 + u2 * u2 + u3 * u3;
     s += P.r[isp] * (sqrt(1 + uu / P.cc) - 1);
@@ -672,11 +685,13 @@ __global__ void __launch_bounds__(256) k_kinetic(const DevParams P, const PartSo
 }
 
 // moments with bilinear weights (mom_calc.f90:167-249): mom (7, nx+3, nyl+2, nsp), RED.ADD.F64
-__global__ void k_moments(const DevParams P, const PartSoA src, const int *__restrict__ cstart, double *mom) {
+__global__ void k_moments(const DevParams P, const PartSoA src, const double *__restrict__ keyx,
+                          const int *__restrict__ cstart, double *mom) {
   for (int isp = 0; isp < P.nsp; isp++) {
     const int n = cstart[(size_t)isp * (P.ncell + 1) + P.ncell];
     const size_t so = (size_t)isp * P.cap;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+      if (!slot_live(keyx[so + p])) continue;  // gaps of the idle store hold stale data
       const double x = src.x[so + p], y = src.y[so + p];
       const double u1 = src.ux[so + p], u2 = src.uy[so + p], u3 = src.uz[so + p];
       const int ih = __double2int_rz(x - 0.5), jh = __double2int_rz(y - 0.5);
@@ -695,6 +710,224 @@ __global__ void k_moments(const DevParams P, const PartSoA src, const int *__res
         atomicAdd(&m11[m], val[m] * dx * dy);
       }
     }
+  }
+}
+
+
+// ---------------------------------------------------------------- layout changes (order inside a cell is kept)
+__device__ __forceinline__ int cell_of(const DevParams &P, double x, double y) {
+  return (__double2int_rz(y) - P.nys) * P.nx + (__double2int_rz(x) - P.nxgs);
+}
+
+// tight, cell-sorted AoS records (a host upload) -> segments with slack
+__global__ void k_relayout_from_aos(const DevParams P, const double *__restrict__ rec, long long n,
+                                    const int *__restrict__ tight, const int *__restrict__ cstart_dst, const PartSoA dst,
+                                    size_t so, unsigned *err) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const double *r = rec + s * 6;
+  const int li = __double2int_rz(r[0]) - P.nxgs, lj = __double2int_rz(r[1]) - P.nys;
+  if (li < 0 || li >= P.nx || lj < 0 || lj >= P.nyl) {
+    atomicOr(err, ERR_BAD_CELL);
+    return;
+  }
+  const int cell = lj * P.nx + li;
+  const int k = (int)s - tight[cell];
+  if (k < 0 || k >= tight[cell + 1] - tight[cell]) {  // cumcnt inconsistent with the positions
+    atomicOr(err, ERR_BAD_CELL);
+    return;
+  }
+  if ((long long)cstart_dst[cell] + k >= P.cap) {
+    atomicOr(err, ERR_CAPACITY);
+    return;
+  }
+  const size_t o = so + (size_t)cstart_dst[cell] + k;
+  dst.x[o] = r[0];
+  dst.y[o] = r[1];
+  dst.ux[o] = r[2];
+  dst.uy[o] = r[3];
+  dst.uz[o] = r[4];
+  dst.id[o] = __double_as_longlong(r[5]);
+}
+
+// segments with slack -> tight AoS records.  `key` (the sorted store) gives liveness and the cell,
+// `val` the values (the same store, or the post-push store for wm_download_gp).
+__global__ void k_relayout_to_aos(const DevParams P, const PartSoA key, const PartSoA val, size_t so,
+                                  const int *__restrict__ cstart_src, const int *__restrict__ tight,
+                                  double *__restrict__ rec) {
+  const int span = cstart_src[P.ncell];
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < span; p += gridDim.x * blockDim.x) {
+    const double x = key.x[so + p];
+    if (!slot_live(x)) continue;
+    const int cell = cell_of(P, x, key.y[so + p]);
+    double *r = rec + ((size_t)tight[cell] + (p - cstart_src[cell])) * 6;
+    r[0] = val.x[so + p];
+    r[1] = val.y[so + p];
+    r[2] = val.ux[so + p];
+    r[3] = val.uy[so + p];
+    r[4] = val.uz[so + p];
+    r[5] = __longlong_as_double(val.id[so + p]);
+  }
+}
+
+// segments -> segments with different offsets (layout rebuild); dst.x must be dead-filled
+__global__ void k_relayout_soa(const DevParams P, const PartSoA src, const int *__restrict__ cstart_src, const PartSoA dst,
+                               const int *__restrict__ cstart_dst, size_t so, unsigned *err) {
+  const int span = cstart_src[P.ncell];
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < span; p += gridDim.x * blockDim.x) {
+    const double x = src.x[so + p];
+    if (!slot_live(x)) continue;
+    const double y = src.y[so + p];
+    const int cell = cell_of(P, x, y);
+    if ((long long)cstart_dst[cell] + (p - cstart_src[cell]) >= P.cap) {
+      atomicOr(err, ERR_CAPACITY);
+      continue;
+    }
+    const size_t o = so + (size_t)cstart_dst[cell] + (p - cstart_src[cell]);
+    dst.x[o] = x;
+    dst.y[o] = y;
+    dst.ux[o] = src.ux[so + p];
+    dst.uy[o] = src.uy[so + p];
+    dst.uz[o] = src.uz[so + p];
+    dst.id[o] = src.id[so + p];
+  }
+}
+
+// in-place sort: records arriving from a neighbour rank (or from the overflow list after a rebuild
+// is NOT needed: see wm_api.cu) are appended at the tail of their cell's segment
+__global__ void k_incoming_append(const DevParams P, const double *__restrict__ rec, int n, int isp,
+                                  const int *__restrict__ cstart, int *cnt_tail, const PartSoA dst, double *ovf, int *ovfsp,
+                                  int *ovfcnt, int ovfcap, unsigned *err) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const double *r = rec + (size_t)s * 6;
+  const int li = __double2int_rz(r[0]) - P.nxgs, lj = __double2int_rz(r[1]) - P.nys;
+  if (li < 0 || li >= P.nx || lj < 0 || lj >= P.nyl) {
+    atomicOr(err, ERR_BAD_CELL);
+    return;
+  }
+  const int cell = lj * P.nx + li;
+  const int *cs = cstart + (size_t)isp * (P.ncell + 1);
+  const int pos = atomicAdd(&cnt_tail[(size_t)isp * P.ncell + cell], 1);
+  if (pos < cs[cell + 1] - cs[cell]) {
+    const size_t o = (size_t)isp * P.cap + cs[cell] + pos;
+    dst.x[o] = r[0];
+    dst.y[o] = r[1];
+    dst.ux[o] = r[2];
+    dst.uy[o] = r[3];
+    dst.uz[o] = r[4];
+    dst.id[o] = __double_as_longlong(r[5]);
+  } else {
+    const int k = atomicAdd(ovfcnt, 1);
+    if (k < ovfcap) {
+      for (int e = 0; e < 6; e++) ovf[(size_t)k * 6 + e] = r[e];
+      ovfsp[k] = isp;
+    } else {
+      atomicOr(err, ERR_OVERFLOW);
+    }
+  }
+}
+
+// in-place sort, second half (the scatter of sort.f90:71-75 reduced to the particles that changed
+// cell).  k_fused<INPLACE> left, per tile, the number of arrivals it sends to every cell of its window
+// (tilebase[tile][isp][0][w]), the number of records it staged per quad (tilebase[tile][isp][1][q]),
+// the staged records themselves in the idle store and their tags, and cnt_new[cell] = stayers.
+// One CTA per tile reserves room at the tail of each destination segment and appends its records.
+constexpr int PL_THREADS = 256;
+constexpr int PL_NQ = (TX / 4) * TY;
+__global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const PartSoA stage, const PartSoA dst,
+                                                      const int *__restrict__ cstart, int *cnt_new,
+                                                      const int *__restrict__ tilebase, const uint32_t *__restrict__ tag,
+                                                      double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err) {
+  __shared__ int s_base[WM_NSP_MAX * WIN], s_end[WM_NSP_MAX * WIN];
+  __shared__ int s_off[WM_NSP_MAX * PL_NQ + 1], s_qbeg[WM_NSP_MAX * PL_NQ];
+  const int tid = threadIdx.x, tile = blockIdx.x;
+  const int li0 = (tile % P.ntx) * TX, lj0 = (tile / P.ntx) * TY;
+  const int tw = min(TX, P.nx - li0), th = min(TY, P.nyl - lj0);
+  const int *tb = tilebase + (size_t)tile * P.nsp * (2 * WIN);
+  for (int e = tid; e < P.nsp * WIN; e += PL_THREADS) {
+    const int isp = e / WIN, w = e - isp * WIN;
+    const int n = tb[isp * (2 * WIN) + w];
+    int base = -1, end = 0;
+    if (n > 0) {
+      const int cell = window_cell(P, li0, lj0, w);
+      if (cell < 0) {
+        atomicOr(err, ERR_MOVED_TOO_FAR);
+      } else {
+        const int *cs = cstart + (size_t)isp * (P.ncell + 1);
+        base = cs[cell] + atomicAdd(&cnt_new[(size_t)isp * P.ncell + cell], n);
+        end = cs[cell + 1];
+      }
+    }
+    s_base[e] = base;
+    s_end[e] = end;
+  }
+  if (tid == 0) {  // prefix over the (species, quad) staging regions
+    int acc = 0;
+    for (int r = 0; r < P.nsp * PL_NQ; r++) {
+      const int isp = r / PL_NQ, q = r - isp * PL_NQ;
+      s_off[r] = acc;
+      acc += tb[isp * (2 * WIN) + WIN + q];
+      const int cy = q / (TX / 4), cx0 = (q - cy * (TX / 4)) * 4;
+      s_qbeg[r] = (cy < th && cx0 < tw) ? cstart[(size_t)isp * (P.ncell + 1) + (lj0 + cy) * P.nx + li0 + cx0] : 0;
+    }
+    s_off[P.nsp * PL_NQ] = acc;
+  }
+  __syncthreads();
+  const int total = s_off[P.nsp * PL_NQ], nreg = P.nsp * PL_NQ;
+  const size_t cstride = (size_t)P.cap * P.nsp;
+  for (int k = tid; k < total; k += PL_THREADS) {
+    int lo = 0, hi = nreg;  // largest r with s_off[r] <= k
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_off[mid] <= k) lo = mid; else hi = mid;
+    }
+    const int isp = lo / PL_NQ;
+    const size_t so = (size_t)isp * P.cap;
+    const size_t sp = so + s_qbeg[lo] + (k - s_off[lo]);
+    const uint32_t t = tag[sp];
+    if (t == TAG_DEAD) continue;  // left the slab: already in the send buffer
+    const int w = (t >> TAG_WSHIFT) & 0xff, rk = (int)(t & TAG_RANK_MASK);
+    const int e = isp * WIN + w;
+    const double *r = stage.x + sp;
+    if (s_base[e] < 0) continue;
+    const int d = s_base[e] + rk;
+    if (d < s_end[e]) {
+      double *o = dst.x + so + d;
+      o[0] = r[0];
+      o[cstride] = r[cstride];
+      o[2 * cstride] = r[2 * cstride];
+      o[3 * cstride] = r[3 * cstride];
+      o[4 * cstride] = r[4 * cstride];
+      o[5 * cstride] = r[5 * cstride];
+    } else {  // segment full: park the record; the host rebuilds the layout after this step
+      const int kk = atomicAdd(ovfcnt, 1);
+      if (kk < ovfcap) {
+        for (int c = 0; c < 6; c++) ovf[(size_t)kk * 6 + c] = r[c * cstride];
+        ovfsp[kk] = isp;
+      } else {
+        atomicOr(err, ERR_OVERFLOW);
+      }
+    }
+  }
+}
+
+// in-place sort, last step: clamp the new counts to the segment capacity (the surplus is in the
+// overflow list) and retire the slots between the new and the old count
+__global__ void k_mark_dead(const DevParams P, double *x, const int *__restrict__ cstart, const int *__restrict__ cnt_old,
+                            int *cnt_new) {
+  const long long n = (long long)P.nsp * P.ncell;
+  for (long long wk = (long long)blockIdx.x * blockDim.x + threadIdx.x; wk < n; wk += (long long)gridDim.x * blockDim.x) {
+    const int isp = (int)(wk / P.ncell), cell = (int)(wk - (long long)isp * P.ncell);
+    const int *cs = cstart + (size_t)isp * (P.ncell + 1);
+    const int capc = cs[cell + 1] - cs[cell];
+    int nn = cnt_new[wk];
+    if (nn > capc) {
+      nn = capc;
+      cnt_new[wk] = nn;
+    }
+    double *xs = x + (size_t)isp * P.cap + cs[cell];
+    for (int p = nn; p < cnt_old[wk]; p++) xs[p] = dead_x();
   }
 }
 
@@ -719,28 +952,29 @@ void launch_pass1(int mode, const DevParams &P, const Pass1Args &a, cudaStream_t
 }
 
 void launch_pass2(const DevParams &P, const PartSoA &src, const PartSoA &dst, const int *cstart_old,
-                  const int *cstart_new, const int *tilebase, const uint32_t *tag, unsigned *err, cudaStream_t st) {
-  k_pass2<<<P.ntx * P.nty, 256, 0, st>>>(P, src, dst, cstart_old, cstart_new, tilebase, tag, err);
+                  const int *cstart_new, const int *tilebase, const uint32_t *tag, const double *keyx, unsigned *err,
+                  cudaStream_t st) {
+  k_pass2<<<P.ntx * P.nty, 256, 0, st>>>(P, src, dst, cstart_old, cstart_new, tilebase, tag, keyx, err);
 }
 
 int scan_scratch_ints(int n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
 
-int launch_scan(const int *in, int *out, int *scratch, int n, cudaStream_t st) {
+int launch_scan(const int *in, int *out, int *scratch, int n, float sl, cudaStream_t st) {
   const int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
   if (nb > SCAN_TILE) return 1;
-  k_scan_partial<<<nb, SCAN_THREADS, 0, st>>>(in, scratch, n);
+  k_scan_partial<<<nb, SCAN_THREADS, 0, st>>>(in, scratch, n, sl);
   k_scan_bsums<<<1, SCAN_THREADS, 0, st>>>(scratch, nb);
-  k_scan_final<<<nb, SCAN_THREADS, 0, st>>>(in, scratch, out, n);
+  k_scan_final<<<nb, SCAN_THREADS, 0, st>>>(in, scratch, out, n, sl);
   return 0;
 }
 
-void launch_incoming_tag(const DevParams &P, const double *rec, int n, int isp, int *gcnt, int *rank, unsigned *err,
-                         cudaStream_t st) {
-  if (n > 0) k_incoming_tag<<<(n + 255) / 256, 256, 0, st>>>(P, rec, n, isp, gcnt, rank, err);
+void launch_incoming_tag(const DevParams &P, const double *rec, int n, int isp, const int *spv, int *gcnt, int *rank,
+                         unsigned *err, cudaStream_t st) {
+  if (n > 0) k_incoming_tag<<<(n + 255) / 256, 256, 0, st>>>(P, rec, n, isp, spv, gcnt, rank, err);
 }
-void launch_incoming_scatter(const DevParams &P, const double *rec, int n, int isp, const int *cstart_new,
+void launch_incoming_scatter(const DevParams &P, const double *rec, int n, int isp, const int *spv, const int *cstart_new,
                              const int *rank, const PartSoA &dst, unsigned *err, cudaStream_t st) {
-  if (n > 0) k_incoming_scatter<<<(n + 255) / 256, 256, 0, st>>>(P, rec, n, isp, cstart_new, rank, dst, err);
+  if (n > 0) k_incoming_scatter<<<(n + 255) / 256, 256, 0, st>>>(P, rec, n, isp, spv, cstart_new, rank, dst, err);
 }
 void launch_aos2soa(const double *rec, long long n, size_t so, const PartSoA &dst, cudaStream_t st) {
   if (n > 0) k_aos2soa<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, n, so, dst);
@@ -748,19 +982,46 @@ void launch_aos2soa(const double *rec, long long n, size_t so, const PartSoA &ds
 void launch_soa2aos(const PartSoA &src, size_t so, long long n, double *rec, cudaStream_t st) {
   if (n > 0) k_soa2aos<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, so, n, rec);
 }
+void launch_relayout_from_aos(const DevParams &P, const double *rec, long long n, const int *tight, const int *cstart_dst,
+                              const PartSoA &dst, size_t so, unsigned *err, cudaStream_t st) {
+  if (n > 0) k_relayout_from_aos<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, rec, n, tight, cstart_dst, dst, so, err);
+}
+void launch_relayout_to_aos(const DevParams &P, const PartSoA &key, const PartSoA &val, size_t so, const int *cstart_src,
+                            const int *tight, double *rec, cudaStream_t st) {
+  k_relayout_to_aos<<<148 * 16, 256, 0, st>>>(P, key, val, so, cstart_src, tight, rec);
+}
+void launch_relayout_soa(const DevParams &P, const PartSoA &src, const int *cstart_src, const PartSoA &dst,
+                         const int *cstart_dst, size_t so, unsigned *err, cudaStream_t st) {
+  k_relayout_soa<<<148 * 16, 256, 0, st>>>(P, src, cstart_src, dst, cstart_dst, so, err);
+}
+void launch_incoming_append(const DevParams &P, const double *rec, int n, int isp, const int *cstart, int *cnt_tail,
+                            const PartSoA &dst, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
+                            cudaStream_t st) {
+  if (n > 0)
+    k_incoming_append<<<(n + 255) / 256, 256, 0, st>>>(P, rec, n, isp, cstart, cnt_tail, dst, ovf, ovfsp, ovfcnt, ovfcap, err);
+}
+void launch_place(const DevParams &P, const PartSoA &stage, const PartSoA &dst, const int *cstart, int *cnt_new,
+                  const int *tilebase, const uint32_t *tag, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
+                  cudaStream_t st) {
+  k_place<<<P.ntx * P.nty, PL_THREADS, 0, st>>>(P, stage, dst, cstart, cnt_new, tilebase, tag, ovf, ovfsp, ovfcnt, ovfcap, err);
+}
+void launch_mark_dead(const DevParams &P, double *x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st) {
+  k_mark_dead<<<148 * 16, 256, 0, st>>>(P, x, cstart, cnt_old, cnt_new);
+}
 void launch_bcx(const DevParams &P, double *x, const int *cstart, cudaStream_t st) {
   k_bcx<<<148 * 8, 256, 0, st>>>(P, x, cstart);
 }
-void launch_ic_weibel(const DevParams &P, const PartSoA &dst, int *cstart, uint64_t seed, int n0, double vti,
-                      double vte, double t_ani, cudaStream_t st) {
-  k_ic_weibel<<<148 * 16, 256, 0, st>>>(P, dst, cstart, seed, n0, vti, vte, t_ani);
+void launch_ic_weibel(const DevParams &P, const PartSoA &dst, int *cstart, int *cnt, uint64_t seed, int n0, double vti,
+                      double vte, double t_ani, float sl, cudaStream_t st) {
+  k_ic_weibel<<<148 * 16, 256, 0, st>>>(P, dst, cstart, cnt, seed, n0, vti, vte, t_ani, sl);
 }
 void launch_kinetic(const DevParams &P, const PartSoA &src, const int *cstart, int isp, double *partial, int nblocks,
                     cudaStream_t st) {
   k_kinetic<<<nblocks, 256, 0, st>>>(P, src, cstart, isp, partial);
 }
-void launch_moments(const DevParams &P, const PartSoA &src, const int *cstart, double *mom, cudaStream_t st) {
-  k_moments<<<148 * 8, 256, 0, st>>>(P, src, cstart, mom);
+void launch_moments(const DevParams &P, const PartSoA &src, const double *keyx, const int *cstart, double *mom,
+                    cudaStream_t st) {
+  k_moments<<<148 * 8, 256, 0, st>>>(P, src, keyx, cstart, mom);
 }
 
 }  // namespace wm

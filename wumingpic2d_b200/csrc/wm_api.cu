@@ -61,7 +61,16 @@ struct wm_ctx {
   // the other one is `gp` in stage mode and the scatter target in the fused step
   double *pbuf[2] = {nullptr, nullptr};
   PartSoA soa[2];
-  int *cstart[2] = {nullptr, nullptr};
+  int *cstart[2] = {nullptr, nullptr};   // [nsp][ncell+1] segment offsets of store b
+  int *cnt[2] = {nullptr, nullptr};      // [nsp][ncell]   live particles per segment of store b
+  int *cnt_tail = nullptr;               // [nsp][ncell]   append cursors of the in-place sort
+  int *tight = nullptr;                  // [nsp][ncell+1] scratch: exclusive scan of cnt (= cumcnt + row bases)
+  double *ovf = nullptr;                 // in-place sort overflow list
+  int *ovfsp = nullptr, *ovfcnt = nullptr, *ovfrank = nullptr, *h_ovf = nullptr;
+  int ovfcap = 0;
+  float slack = 6.0f;                    // segment slack in std deviations of the count change (WM_SLACK)
+  bool inplace = true;                   // WM_INPLACE=0 selects the tag + scatter sort for wm_step
+  long long rebuilds = 0;
   int cur = 0;
   int *gcnt = nullptr, *tilebase = nullptr, *scan_scratch = nullptr;
   uint32_t *tag = nullptr;
@@ -112,9 +121,14 @@ int alloc_particles(wm_ctx *c, long long need) {
     if (need <= c->P.cap) return 0;
     return fail("particle capacity %lld exceeded (need %lld); recreate the context with a larger wm_config.capacity", c->P.cap, need);
   }
-  long long cap = c->cfg.capacity > 0 ? c->cfg.capacity : (long long)std::ceil(1.25 * (double)need) + 1024;
+  // slots per species: every cell segment carries slack (wm_internal.h cell_capacity); by
+  // Cauchy-Schwarz sum_c cap(n_c) <= need + 8 ncell + slack sqrt(2 ncell need)
+  auto bound = [&](float sl) { return (double)need + 8.0 * c->P.ncell + (double)sl * std::sqrt(2.0 * c->P.ncell * (double)need); };
+  long long cap = c->cfg.capacity > 0 ? c->cfg.capacity : (long long)std::ceil(1.1 * bound(c->slack)) + 4096;
   if (cap < need) return fail("wm_config.capacity %lld < particles per species %lld", cap, need);
-  cap = (cap + 1) & ~1LL;
+  while (c->slack > 0.f && bound(c->slack) > (double)cap) c->slack = (c->slack > 0.5f) ? c->slack * 0.5f : 0.f;
+  if (c->slack <= 0.f) c->inplace = false;
+  cap = (cap + 3) & ~3LL;
   if (cap >= (1LL << 31) - 1) return fail("more than 2^31 particles per species per GPU are not supported");
   c->P.cap = cap;
   const int nsp = c->P.nsp;
@@ -122,7 +136,18 @@ int alloc_particles(wm_ctx *c, long long need) {
     CU(cudaMalloc(&c->pbuf[b], (size_t)cap * nsp * 6 * sizeof(double)));
     carve(c->soa[b], c->pbuf[b], cap, nsp);
     CU(cudaMalloc(&c->cstart[b], (size_t)nsp * (c->P.ncell + 1) * sizeof(int)));
+    CU(cudaMalloc(&c->cnt[b], (size_t)nsp * c->P.ncell * sizeof(int)));
+    CU(cudaMemset(c->pbuf[b], 0xFF, (size_t)cap * nsp * sizeof(double)));  // x: every slot dead
   }
+  CU(cudaMalloc(&c->cnt_tail, (size_t)nsp * c->P.ncell * sizeof(int)));
+  CU(cudaMalloc(&c->tight, (size_t)nsp * (c->P.ncell + 1) * sizeof(int)));
+  c->ovfcap = (int)std::min<long long>(std::max<long long>(need / 64, 1 << 16), 1 << 24);
+  CU(cudaMalloc(&c->ovf, (size_t)c->ovfcap * 6 * sizeof(double)));
+  CU(cudaMalloc(&c->ovfsp, (size_t)c->ovfcap * sizeof(int)));
+  CU(cudaMalloc(&c->ovfrank, (size_t)c->ovfcap * sizeof(int)));
+  CU(cudaMalloc(&c->ovfcnt, sizeof(int)));
+  CU(cudaMemset(c->ovfcnt, 0, sizeof(int)));
+  CU(cudaMallocHost(&c->h_ovf, sizeof(int)));
   CU(cudaMalloc(&c->tag, (size_t)cap * nsp * sizeof(uint32_t)));
   return 0;
 }
@@ -144,6 +169,7 @@ int check_errors(wm_ctx *c, const char *where) {
   if (e & ERR_SENDBUF) m += " migration buffer exhausted;";
   if (e & ERR_BAD_CELL) m += " particle outside the slab;";
   if (e & ERR_TAG_RANK) m += " more than 2^24 particles from one tile into one cell;";
+  if (e & ERR_OVERFLOW) m += " in-place sort overflow list exhausted (raise WM_SLACK or wm_config.capacity);";
   return fail("%s", m.c_str());
 }
 
@@ -273,6 +299,12 @@ Pass1Args p1args(wm_ctx *c, const PartSoA &src, const PartSoA &dst, double delt_
   a.src = src;
   a.dst = dst;
   a.cstart = c->cstart[c->cur];
+  a.cnt = c->cnt[c->cur];
+  a.cnt_tail = c->cnt_tail;
+  a.ovf = c->ovf;
+  a.ovfsp = c->ovfsp;
+  a.ovfcnt = c->ovfcnt;
+  a.ovfcap = c->ovfcap;
   a.tmpf = c->f.tmpf;
   a.uj = c->f.uj;
   a.gcnt = c->gcnt;
@@ -295,7 +327,7 @@ int zero_sort_state(wm_ctx *c) {
 
 // ring exchange of the leavers packed by the BOUND pass, then rank the arrivals
 // boundary_periodic.f90:173-189
-int migrate(wm_ctx *c) {
+int migrate(wm_ctx *c, bool inplace = false) {
   const DevParams &P = c->P;
   if (P.nsize == 1) return 0;
   if (!c->comm) return fail("nsize > 1 but wm_comm_init has not been called");
@@ -329,8 +361,12 @@ int migrate(wm_ctx *c) {
   for (int d = 0; d < 2; d++)
     for (int isp = 0; isp < nsp; isp++) {
       const size_t off = (size_t)isp * c->sendcap;
-      launch_incoming_tag(P, c->recv[d] + off * 6, c->n_in[d][isp], isp, c->gcnt,
-                          c->in_rank + (size_t)d * nsp * c->sendcap + off, c->d_err, c->st);
+      if (inplace)  // append at the tail of the destination segments of the current store
+        launch_incoming_append(P, c->recv[d] + off * 6, c->n_in[d][isp], isp, c->cstart[c->cur], c->cnt_tail, c->soa[c->cur],
+                               c->ovf, c->ovfsp, c->ovfcnt, c->ovfcap, c->d_err, c->st);
+      else
+        launch_incoming_tag(P, c->recv[d] + off * 6, c->n_in[d][isp], isp, nullptr, c->gcnt,
+                            c->in_rank + (size_t)d * nsp * c->sendcap + off, c->d_err, c->st);
       c->launches++;
     }
   return 0;
@@ -342,20 +378,38 @@ int scatter_arrivals(wm_ctx *c, int dstbuf) {
   for (int d = 0; d < 2; d++)
     for (int isp = 0; isp < P.nsp; isp++) {
       const size_t off = (size_t)isp * c->sendcap;
-      launch_incoming_scatter(P, c->recv[d] + off * 6, c->n_in[d][isp], isp, c->cstart[dstbuf],
+      launch_incoming_scatter(P, c->recv[d] + off * 6, c->n_in[d][isp], isp, nullptr, c->cstart[dstbuf],
                               c->in_rank + (size_t)d * P.nsp * c->sendcap + off, c->soa[dstbuf], c->d_err, c->st);
       c->launches++;
     }
   return 0;
 }
 
+// new layout of store `dstbuf` from the destination-cell counts in gcnt: cnt = gcnt, cstart = scan of capacities
 int scan_counts(wm_ctx *c, int dstbuf) {
   for (int isp = 0; isp < c->P.nsp; isp++) {
     if (launch_scan(c->gcnt + (size_t)isp * c->P.ncell, c->cstart[dstbuf] + (size_t)isp * (c->P.ncell + 1), c->scan_scratch,
-                    c->P.ncell, c->st))
+                    c->P.ncell, c->slack, c->st))
       return fail("grid too large for the prefix scan");
     c->launches += 3;
   }
+  CU(cudaMemcpyAsync(c->cnt[dstbuf], c->gcnt, (size_t)c->P.nsp * c->P.ncell * sizeof(int), cudaMemcpyDeviceToDevice, c->st));
+  return 0;
+}
+
+// exclusive scan of the live counts of the current store -> c->tight (the reference's cumcnt + row bases)
+int scan_tight(wm_ctx *c) {
+  for (int isp = 0; isp < c->P.nsp; isp++) {
+    if (launch_scan(c->cnt[c->cur] + (size_t)isp * c->P.ncell, c->tight + (size_t)isp * (c->P.ncell + 1), c->scan_scratch,
+                    c->P.ncell, 0.f, c->st))
+      return fail("grid too large for the prefix scan");
+    c->launches += 3;
+  }
+  return 0;
+}
+
+int fill_dead(wm_ctx *c, int buf) {
+  CU(cudaMemsetAsync(c->soa[buf].x, 0xFF, (size_t)c->P.cap * c->P.nsp * sizeof(double), c->st));
   return 0;
 }
 
@@ -399,6 +453,9 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   wm_ctx *c = new wm_ctx();
   c->cfg = *g;
   if (const char *v = getenv("WM_FUSED")) c->fused_variant = atoi(v);
+  if (const char *v = getenv("WM_SLACK")) c->slack = (float)atof(v);
+  if (const char *v = getenv("WM_INPLACE")) c->inplace = atoi(v) != 0;
+  if (g->flags & WM_FLAG_EXACT_PUSH) c->inplace = false;  // the exact path keeps the reference's two-pass structure
   if (g->device >= 0) {
     c->dev = g->device;
   } else {
@@ -497,6 +554,7 @@ int wm_destroy(wm_ctx *c) {
   for (int b = 0; b < 2; b++) {
     cudaFree(c->pbuf[b]);
     cudaFree(c->cstart[b]);
+    cudaFree(c->cnt[b]);
     cudaFree(c->send[b]);
     cudaFree(c->recv[b]);
   }
@@ -506,6 +564,13 @@ int wm_destroy(wm_ctx *c) {
                   (void *)c->f.red, (void *)c->f.cgstate, (void *)c->rowtmp, (void *)c->mom, (void *)c->partial,
                   (void *)c->d_err})
     cudaFree(p);
+  cudaFree(c->cnt_tail);
+  cudaFree(c->tight);
+  cudaFree(c->ovf);
+  cudaFree(c->ovfsp);
+  cudaFree(c->ovfrank);
+  cudaFree(c->ovfcnt);
+  cudaFreeHost(c->h_ovf);
   cudaFreeHost(c->h_partial);
   cudaFreeHost(c->h_err);
   cudaFreeHost(c->h_cg);
@@ -596,13 +661,14 @@ int wm_upload_particles(wm_ctx *c, const double *up, const int32_t *np2) {
   int *rank = reinterpret_cast<int *>(c->tag);
   long long off = 0;
   for (int isp = 0; isp < P.nsp; isp++) {
-    launch_incoming_tag(P, stage + off * 6, (int)n[isp], isp, c->gcnt, rank + off, c->d_err, c->st);
+    launch_incoming_tag(P, stage + off * 6, (int)n[isp], isp, nullptr, c->gcnt, rank + off, c->d_err, c->st);
     off += n[isp];
   }
   WM(scan_counts(c, c->cur));
+  WM(fill_dead(c, c->cur));
   off = 0;
   for (int isp = 0; isp < P.nsp; isp++) {
-    launch_incoming_scatter(P, stage + off * 6, (int)n[isp], isp, c->cstart[c->cur], rank + off, c->soa[c->cur], c->d_err, c->st);
+    launch_incoming_scatter(P, stage + off * 6, (int)n[isp], isp, nullptr, c->cstart[c->cur], rank + off, c->soa[c->cur], c->d_err, c->st);
     off += n[isp];
   }
   WM(check_errors(c, "wm_upload_particles"));
@@ -636,13 +702,22 @@ int wm_upload_particles_sorted(wm_ctx *c, const double *up, const int32_t *np2, 
     }
     o[P.ncell] = (int)base;
   }
-  CU(cudaMemcpyAsync(c->cstart[c->cur], cs.data(), cs.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
+  // tight offsets -> device, counts -> gcnt, segment layout with slack, then an order-preserving copy
+  std::vector<int> hc((size_t)P.nsp * P.ncell);
+  for (int isp = 0; isp < P.nsp; isp++)
+    for (int cl = 0; cl < P.ncell; cl++)
+      hc[(size_t)isp * P.ncell + cl] = cs[(size_t)isp * (P.ncell + 1) + cl + 1] - cs[(size_t)isp * (P.ncell + 1) + cl];
+  CU(cudaMemcpyAsync(c->tight, cs.data(), cs.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
+  CU(cudaMemcpyAsync(c->gcnt, hc.data(), hc.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
+  WM(scan_counts(c, c->cur));
+  WM(fill_dead(c, c->cur));
   long long off = 0;
   for (int isp = 0; isp < P.nsp; isp++) {
-    launch_aos2soa(stage + off * 6, n[isp], (size_t)isp * P.cap, c->soa[c->cur], c->st);
+    launch_relayout_from_aos(P, stage + off * 6, n[isp], c->tight + (size_t)isp * (P.ncell + 1),
+                             c->cstart[c->cur] + (size_t)isp * (P.ncell + 1), c->soa[c->cur], (size_t)isp * P.cap, c->d_err, c->st);
     off += n[isp];
   }
-  CU(cudaStreamSynchronize(c->st));  // cs goes out of scope
+  WM(check_errors(c, "wm_upload_particles_sorted"));  // also synchronises: cs, hc go out of scope
   c->state = ST_SORTED;
   return 0;
 }
@@ -660,14 +735,17 @@ static int download_store(wm_ctx *c, int buf, double *up, int32_t *np2, int32_t 
   c->accl_valid = false;
   const DevParams &P = c->P;
   std::vector<int> cs((size_t)P.nsp * (P.ncell + 1));
-  CU(cudaMemcpyAsync(cs.data(), c->cstart[c->cur], cs.size() * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  WM(scan_tight(c));
+  CU(cudaMemcpyAsync(cs.data(), c->tight, cs.size() * sizeof(int), cudaMemcpyDeviceToHost, c->st));
   CU(cudaStreamSynchronize(c->st));
   double *stage = stage_override ? stage_override : c->pbuf[buf ^ 1];
   long long off = 0;
   for (int isp = 0; isp < P.nsp; isp++) {
     const int *o = cs.data() + (size_t)isp * (P.ncell + 1);
     const long long n = o[P.ncell];
-    if (up) launch_soa2aos(c->soa[buf], (size_t)isp * P.cap, n, stage + off * 6, c->st);
+    if (up)
+      launch_relayout_to_aos(P, c->soa[c->cur], c->soa[buf], (size_t)isp * P.cap, c->cstart[c->cur] + (size_t)isp * (P.ncell + 1),
+                             c->tight + (size_t)isp * (P.ncell + 1), stage + off * 6, c->st);
     for (int jl = 0; jl < P.nyl; jl++) {
       const int rb = o[(size_t)jl * P.nx], re = o[(size_t)(jl + 1) * P.nx];
       if (re - rb > c->cfg.np) return fail("memory over (np2 > np): row %d species %d holds %d > np=%d (boundary_periodic.f90:231-234)", jl, isp, re - rb, c->cfg.np);
@@ -740,9 +818,10 @@ int wm_particle_counts(wm_ctx *c, int64_t *n) {
     for (int isp = 0; isp < c->P.nsp; isp++) n[isp] = 0;
     return 0;
   }
+  WM(scan_tight(c));
   for (int isp = 0; isp < c->P.nsp; isp++) {
     int v = 0;
-    CU(cudaMemcpyAsync(&v, c->cstart[c->cur] + (size_t)isp * (c->P.ncell + 1) + c->P.ncell, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(&v, c->tight + (size_t)isp * (c->P.ncell + 1) + c->P.ncell, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
     n[isp] = v;
   }
@@ -755,6 +834,7 @@ int wm_particle__solv(wm_ctx *c) {
   c->accl_valid = false;
   WM(set_device(c));
   launch_tmpf(c->P, c->f.uf, c->f.tmpf, c->st);
+  WM(fill_dead(c, c->cur ^ 1));  // gp: only live slots are written by the push
   const int mode = M_PUSH | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
   launch_pass1(mode, c->P, p1args(c, c->soa[c->cur], c->soa[c->cur ^ 1], c->P.delt), c->st);
   c->launches += 2;
@@ -818,7 +898,9 @@ int wm_sort__bucket(wm_ctx *c) {
   const int src = c->cur ^ 1, dst = c->cur;
   // the new offsets must not overwrite the old ones while pass 2 still reads them
   WM(scan_counts(c, src));
-  launch_pass2(c->P, c->soa[src], c->soa[dst], c->cstart[dst], c->cstart[src], c->tilebase, c->tag, c->d_err, c->st);
+  // wm_particle__solv dead-filled the gp store before the push, so its x marks the gaps by itself
+  WM(fill_dead(c, dst));
+  launch_pass2(c->P, c->soa[src], c->soa[dst], c->cstart[dst], c->cstart[src], c->tilebase, c->tag, c->soa[src].x, c->d_err, c->st);
   c->launches++;
   // arrivals use cstart[src] (new offsets) and go to soa[dst]
   {
@@ -827,14 +909,36 @@ int wm_sort__bucket(wm_ctx *c) {
       for (int d = 0; d < 2; d++)
         for (int isp = 0; isp < P.nsp; isp++) {
           const size_t off = (size_t)isp * c->sendcap;
-          launch_incoming_scatter(P, c->recv[d] + off * 6, c->n_in[d][isp], isp, c->cstart[src],
+          launch_incoming_scatter(P, c->recv[d] + off * 6, c->n_in[d][isp], isp, nullptr, c->cstart[src],
                                   c->in_rank + (size_t)d * P.nsp * c->sendcap + off, c->soa[dst], c->d_err, c->st);
           c->launches++;
         }
   }
   WM(check_errors(c, "wm_sort__bucket"));
-  std::swap(c->cstart[0], c->cstart[1]);  // new offsets now belong to store `cur`
+  std::swap(c->cstart[0], c->cstart[1]);  // new offsets and counts now belong to store `cur`
+  std::swap(c->cnt[0], c->cnt[1]);
   c->state = ST_SORTED;
+  return 0;
+}
+
+// Layout rebuild of the in-place sort: a segment overflowed during the last step, its surplus records
+// are in the overflow list.  New segment offsets with fresh slack from the current counts (+ the
+// parked records), order-preserving copy into the other store, then the parked records.
+static int rebuild_layout(wm_ctx *c, int novf) {
+  const DevParams &P = c->P;
+  const int dst = c->cur ^ 1;
+  if (novf > c->ovfcap) return fail("in-place sort: %d records overflowed their segments, list holds %d", novf, c->ovfcap);
+  CU(cudaMemcpyAsync(c->gcnt, c->cnt[c->cur], (size_t)P.nsp * P.ncell * sizeof(int), cudaMemcpyDeviceToDevice, c->st));
+  launch_incoming_tag(P, c->ovf, novf, 0, c->ovfsp, c->gcnt, c->ovfrank, c->d_err, c->st);
+  WM(scan_counts(c, dst));
+  WM(fill_dead(c, dst));
+  for (int isp = 0; isp < P.nsp; isp++)
+    launch_relayout_soa(P, c->soa[c->cur], c->cstart[c->cur] + (size_t)isp * (P.ncell + 1), c->soa[dst],
+                        c->cstart[dst] + (size_t)isp * (P.ncell + 1), (size_t)isp * P.cap, c->d_err, c->st);
+  launch_incoming_scatter(P, c->ovf, novf, 0, c->ovfsp, c->cstart[dst], c->ovfrank, c->soa[dst], c->d_err, c->st);
+  c->launches += 2 + P.nsp;
+  c->cur = dst;
+  c->rebuilds++;
   return 0;
 }
 
@@ -845,17 +949,21 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
   const DevParams &P = c->P;
   const size_t ng = (size_t)P.pitch * (P.nyl + 4);
   const int mode = M_PUSH | M_DEPOSIT | M_BOUND | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
+  const bool inplace = c->inplace && !(c->cfg.flags & WM_FLAG_EXACT_PUSH) && c->fused_variant == 1;
   CU(cudaEventRecord(c->ev_call[0], c->st));
   for (int it = 0; it < nsteps; it++) {
     if (c->timing) CU(cudaEventRecord(c->ev[0], c->st));
-    // particle__solv + ele_cur + bc__particle_x/y + histogram in one pass, in place
+    // particle__solv + ele_cur + bc__particle_x/y + (histogram | move of the cell changers) in one pass, in place
     launch_tmpf(P, c->f.uf, c->f.tmpf, c->st);
     CU(cudaMemsetAsync(c->f.uj, 0, ng * 3 * sizeof(double), c->st));
     WM(zero_sort_state(c));
+    if (inplace) CU(cudaMemsetAsync(c->ovfcnt, 0, sizeof(int), c->st));
     const PartSoA &a = c->soa[c->cur];
     if (c->timing) CU(cudaEventRecord(c->ev[1], c->st));
     if (c->cfg.flags & WM_FLAG_EXACT_PUSH)
       launch_pass1(mode, P, p1args(c, a, a, P.delt), c->st);
+    else if (inplace)
+      launch_fused_inplace(P, p1args(c, a, c->soa[c->cur ^ 1], P.delt), c->st);  // idle store = staging of the cell changers
     else if (c->fused_variant == 1)
       launch_fused(P, p1args(c, a, a, P.delt), c->st);
     else
@@ -865,19 +973,33 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
     // rest of field__fdtd_i
     WM(field_solve(c));
     if (c->timing) CU(cudaEventRecord(c->ev[3], c->st));
-    // migration, prefix scan
-    WM(migrate(c));
-    const int dst = c->cur ^ 1;
-    WM(scan_counts(c, dst));
-    if (c->timing) CU(cudaEventRecord(c->ev[4], c->st));
-    // sort__bucket scatter
-    launch_pass2(P, c->soa[c->cur], c->soa[dst], c->cstart[c->cur], c->cstart[dst], c->tilebase, c->tag, c->d_err, c->st);
-    c->launches++;
-    WM(scatter_arrivals(c, dst));
-    c->cur = dst;
+    if (inplace) {
+      // ring exchange of the leavers; arrivals are appended to their segments
+      WM(migrate(c, true));
+      if (c->timing) CU(cudaEventRecord(c->ev[4], c->st));
+      // sort__bucket, reduced to the cell changers: append them to their new segments
+      launch_place(P, c->soa[c->cur ^ 1], a, c->cstart[c->cur], c->cnt_tail, c->tilebase, c->tag, c->ovf, c->ovfsp, c->ovfcnt,
+                   c->ovfcap, c->d_err, c->st);
+      launch_mark_dead(P, a.x, c->cstart[c->cur], c->cnt[c->cur], c->cnt_tail, c->st);
+      c->launches += 2;
+      std::swap(c->cnt[c->cur], c->cnt_tail);  // cnt_tail held the new counts
+      CU(cudaMemcpyAsync(c->h_ovf, c->ovfcnt, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    } else {
+      // migration, prefix scan
+      WM(migrate(c));
+      const int dst = c->cur ^ 1;
+      WM(scan_counts(c, dst));
+      WM(fill_dead(c, dst));
+      if (c->timing) CU(cudaEventRecord(c->ev[4], c->st));
+      // sort__bucket scatter
+      launch_pass2(P, a, c->soa[dst], c->cstart[c->cur], c->cstart[dst], c->tilebase, c->tag, a.x, c->d_err, c->st);
+      c->launches++;
+      WM(scatter_arrivals(c, dst));
+      c->cur = dst;
+    }
+    CU(cudaEventRecord(c->ev[5], c->st));
+    CU(cudaEventSynchronize(c->ev[5]));
     if (c->timing) {
-      CU(cudaEventRecord(c->ev[5], c->st));
-      CU(cudaEventSynchronize(c->ev[5]));
       float t[5];
       for (int k = 0; k < 5; k++) CU(cudaEventElapsedTime(&t[k], c->ev[k], c->ev[k + 1]));
       c->ms[0] += t[1];
@@ -885,6 +1007,7 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
       c->ms[2] += t[0] + t[3];
       c->ms[3] += t[4];
     }
+    if (inplace && *c->h_ovf > 0) WM(rebuild_layout(c, *c->h_ovf));
   }
   CU(cudaEventRecord(c->ev_call[1], c->st));
   CU(cudaEventSynchronize(c->ev_call[1]));
@@ -995,6 +1118,7 @@ int wm_mom_calc__accl(wm_ctx *c) {
   const DevParams &P = c->P;
   // half-step acceleration into the idle store, positions copied (mom_calc.f90:34,48-164)
   launch_tmpf(P, c->f.uf, c->f.tmpf, c->st);
+  WM(fill_dead(c, c->cur ^ 1));
   const int mode = M_PUSH | M_NOMOVE | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
   launch_pass1(mode, P, p1args(c, c->soa[c->cur], c->soa[c->cur ^ 1], P.delt * 0.5), c->st);
   c->launches += 2;
@@ -1006,7 +1130,7 @@ int wm_mom_calc__accl(wm_ctx *c) {
 static int mom_nvt_device(wm_ctx *c) {
   if (!c->accl_valid) return fail("wm_mom_calc__nvt: call wm_mom_calc__accl first (proj/weibel/app.f90:121-122)");
   CU(cudaMemsetAsync(c->mom, 0, mom_elems(c) * sizeof(double), c->st));
-  launch_moments(c->P, c->soa[c->cur ^ 1], c->cstart[c->cur], c->mom, c->st);
+  launch_moments(c->P, c->soa[c->cur ^ 1], c->soa[c->cur].x, c->cstart[c->cur], c->mom, c->st);
   c->launches++;
   return 0;
 }
@@ -1050,7 +1174,9 @@ int wm_ic_weibel(wm_ctx *c, uint64_t seed, int32_t n0, double vti, double vte, d
   if (n >= (1LL << 31) - 1) return fail("wm_ic_weibel: too many particles per species for one GPU");
   WM(alloc_particles(c, n));
   WM(ensure_migration_buffers(c, n));
-  launch_ic_weibel(P, c->soa[c->cur], c->cstart[c->cur], seed, n0, vti, vte, t_ani, c->st);
+  WM(fill_dead(c, c->cur));
+  launch_ic_weibel(P, c->soa[c->cur], c->cstart[c->cur], c->cnt[c->cur], seed, n0, vti, vte, t_ani, c->slack, c->st);
+  if ((long long)cell_capacity(n0, c->slack) * P.ncell > P.cap) return fail("wm_ic_weibel: particle capacity too small for the segment slack");
   // uniform field Bz = b0 (app.f90:388-399), df = 0
   const size_t ng = (size_t)P.pitch * (P.nyl + 4);
   std::vector<double> h(ng * 6, 0.0);
@@ -1071,6 +1197,12 @@ int wm_timing(wm_ctx *c, double ms[5], int64_t *launches, int32_t reset) {
   }
   if (launches) *launches = c->launches;
   if (reset) c->launches = 0;
+  return 0;
+}
+
+int wm_layout_rebuilds(wm_ctx *c, int64_t *n) {
+  if (!c || !n) return fail("wm_layout_rebuilds: null argument");
+  *n = c->rebuilds;
   return 0;
 }
 

@@ -3,8 +3,11 @@
 // Data layout in HBM (one context = one y-slab, rows nys..nye, full x extent):
 //  * particles: SoA per component (x, y, ux, uy, uz, id), species s at offset s*cap,
 //    globally cell-sorted: cell = (j-nys)*nx + (i-nxgs); cell c of species s owns slots
-//    [cstart[s][c], cstart[s][c+1]).  The reference's cumcnt(i,j,s) is
-//    cstart[s][cell(i,j)] - cstart[s][cell(nxgs,j)] and np2(j,s) is the row total.
+//    [cstart[s][c], cstart[s][c] + cnt[s][c]); cstart[s][c+1] - cstart[s][c] is the segment's
+//    CAPACITY (count + slack, so that a step only has to move the ~15 % of particles that change
+//    cell; the layout is rebuilt when a segment overflows).  A slot is live iff x >= 0: gaps and
+//    holes hold an all-ones NaN.  The reference's cumcnt(i,j,s) is the exclusive prefix sum of
+//    cnt over the row and np2(j,s) the row total; both are produced exactly at download.
 //  * grid arrays: the reference's own AoS layout incl. 2 ghost cells per side,
 //    uf/df/tmpf (6, nx+4, nyl+4), uj/gkl/CG vectors (3, nx+4, nyl+4).
 #pragma once
@@ -59,12 +62,26 @@ enum : unsigned {
   ERR_CAPACITY = 2u,        // particle slots exhausted ("memory over", boundary_periodic.f90:231-234)
   ERR_SENDBUF = 4u,         // migration buffer exhausted
   ERR_BAD_CELL = 8u,        // uploaded particle outside the slab
-  ERR_TAG_RANK = 16u        // more than 2^23 particles from one tile into one cell
+  ERR_TAG_RANK = 16u,       // more than 2^23 particles from one tile into one cell
+  ERR_OVERFLOW = 32u        // in-place sort: overflow list exhausted
 };
+
+// capacity of a cell segment that holds n particles now: slack ~ sl standard deviations of the
+// change of a Poisson count between two layout rebuilds; sl = 0 -> tight
+__host__ __device__ inline int cell_capacity(int n, float sl) {
+  if (sl <= 0.f) return n;
+  return (n + 4 + (int)ceilf(sl * sqrtf(2.0f * (float)n)) + 3) & ~3;
+}
 
 struct Pass1Args {
   PartSoA src, dst;         // dst == src for the in-place fused pass
-  const int *cstart;        // [nsp][ncell+1]
+  const int *cstart;        // [nsp][ncell+1] segment offsets (capacity)
+  const int *cnt;           // [nsp][ncell]   live particles per segment
+  int *cnt_tail;            // [nsp][ncell]   in-place sort: append cursors (start = cnt)
+  double *ovf;              // in-place sort: records that did not fit their segment [ovfcap][6], isp in ovfsp
+  int *ovfsp;
+  int *ovfcnt;
+  int ovfcap;
   const double *tmpf;       // cell-centred fields, AoS6 padded
   double *uj;               // AoS3 padded, accumulated with RED.ADD.F64
   int *gcnt;                // [nsp][ncell] destination-cell counters / cursors
@@ -78,6 +95,9 @@ struct Pass1Args {
 };
 
 #ifdef __CUDACC__
+// a slot holds a particle iff x >= 0 (positions are >= nxgs >= 1); dead = all-ones NaN = memset 0xFF
+__device__ __forceinline__ bool slot_live(double x) { return x >= 0.0; }
+__device__ __forceinline__ double dead_x() { return __longlong_as_double(-1LL); }
 // window index -> local cell index with the periodic wraps; -1 = outside the slab
 __device__ __forceinline__ int window_cell(const DevParams &P, int li0, int lj0, int w) {
   int lx = w % WINX, ly = w / WINX;
