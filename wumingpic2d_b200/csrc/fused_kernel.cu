@@ -191,9 +191,13 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
       int nst = 0;  // stayers of this (cell, species) so far
       int nmv = 0;  // cell changers of this (quad, species) so far (INPLACE)
       // staging region of this quad in the idle store: starts at the segment of the quad's first cell
-      const int qbeg = (INPLACE && cy < th && (q - cy * QX) * 4 < tw)
-                           ? a.cstart[(size_t)isp * (P.ncell + 1) + (lj0 + cy) * P.nx + li0 + (q - cy * QX) * 4]
-                           : 0;
+      long long qrec = 0;
+      int qcap = 0;
+      if (INPLACE && cy < th && (q - cy * QX) * 4 < tw) {
+        const int c0 = (lj0 + cy) * P.nx + li0 + (q - cy * QX) * 4;
+        const int *cs = a.cstart + (size_t)isp * (P.ncell + 1);
+        stage_region(so_slots(P, isp) + cs[c0], so_slots(P, isp) + cs[min(c0 + 4, (lj0 + cy + 1) * P.nx)], &qrec, &qcap);
+      }
       int p = beg + l8;
       double nx_ = 0.0, ny_ = 0.0, nu1 = 0.0, nu2 = 0.0, nu3 = 0.0, nid = 0.0;
       if (p < end) {
@@ -379,16 +383,6 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
               yn = __dadd_rd(yn, -P.ylen);
             const bool leaves = (P.nsize > 1) && (j2 < P.nys || j2 >= P.nys + P.nyl);
             const double idv = INPLACE ? idc : (leaves ? px[so + pc + 5 * cstride] : 0.0);  // id, bit pattern
-            if (INPLACE) {
-              // stage the record in the idle store, in the shadow of this quad (slot order = ballot rank)
-              double *d = a.dst.x + so + qbeg + nmv + __popc(balm & ((1u << lane) - 1u));
-              d[0] = xn;
-              d[cstride] = yn;
-              d[2 * cstride] = un1;
-              d[3 * cstride] = un2;
-              d[4 * cstride] = un3;
-              d[5 * cstride] = idv;
-            }
             if (leaves) {
               // record goes to the neighbour's edge row        boundary_periodic.f90:156-161,174-189
               const int dir = (j2 < P.nys) ? 0 : 1;
@@ -410,7 +404,20 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
               const int rk = atomicAdd(&s_arr[isp * WIN + w], 1);
               tg = TAG_ARRIVAL | ((uint32_t)w << TAG_WSHIFT) | (uint32_t)rk;
             }
-            if (INPLACE) a.tag[so + qbeg + nmv + __popc(balm & ((1u << lane) - 1u))] = tg;
+            if (INPLACE) {
+              // stage the record (64 B: x y | ux uy | uz id | tag -) in the idle store, in the shadow of
+              // this quad; slot order = ballot rank, so the stores of a warp are contiguous
+              const int sk = nmv + __popc(balm & ((1u << lane) - 1u));
+              if (sk < qcap) {
+                double2 *d = reinterpret_cast<double2 *>(a.dst.x) + (size_t)(qrec + sk) * 4;
+                d[0] = make_double2(xn, yn);
+                d[1] = make_double2(un1, un2);
+                d[2] = make_double2(un3, idv);
+                d[3] = make_double2(__longlong_as_double((long long)tg), 0.0);
+              } else {
+                atomicOr(a.err, ERR_OVERFLOW);
+              }
+            }
           }
           if (!INPLACE) {
             double *b = px + so + pc;

@@ -835,17 +835,22 @@ __global__ void k_incoming_append(const DevParams P, const double *__restrict__ 
 // One CTA per tile reserves room at the tail of each destination segment and appends its records.
 constexpr int PL_THREADS = 256;
 constexpr int PL_NQ = (TX / 4) * TY;
-__global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const PartSoA stage, const PartSoA dst,
+constexpr int PL_MAX = 4096;  // records placed per round
+__global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const double2 *__restrict__ stage, const PartSoA dst,
                                                       const int *__restrict__ cstart, int *cnt_new,
-                                                      const int *__restrict__ tilebase, const uint32_t *__restrict__ tag,
-                                                      double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err) {
-  __shared__ int s_base[WM_NSP_MAX * WIN], s_end[WM_NSP_MAX * WIN];
-  __shared__ int s_off[WM_NSP_MAX * PL_NQ + 1], s_qbeg[WM_NSP_MAX * PL_NQ];
+                                                      const int *__restrict__ tilebase, double *ovf, int *ovfsp, int *ovfcnt,
+                                                      int ovfcap, unsigned *err) {
+  __shared__ int s_base[WM_NSP_MAX * WIN], s_end[WM_NSP_MAX * WIN], s_pref[WM_NSP_MAX * WIN + 1];
+  __shared__ int s_off[WM_NSP_MAX * PL_NQ + 1];
+  __shared__ long long s_rec0[WM_NSP_MAX * PL_NQ];
+  __shared__ int s_inv[PL_MAX];
   const int tid = threadIdx.x, tile = blockIdx.x;
   const int li0 = (tile % P.ntx) * TX, lj0 = (tile / P.ntx) * TY;
   const int tw = min(TX, P.nx - li0), th = min(TY, P.nyl - lj0);
   const int *tb = tilebase + (size_t)tile * P.nsp * (2 * WIN);
-  for (int e = tid; e < P.nsp * WIN; e += PL_THREADS) {
+  const int nreg = P.nsp * PL_NQ, nwin = P.nsp * WIN;
+  // room at the tail of every destination segment; arrival counts and staged-record counts to smem
+  for (int e = tid; e < nwin; e += PL_THREADS) {
     const int isp = e / WIN, w = e - isp * WIN;
     const int n = tb[isp * (2 * WIN) + w];
     int base = -1, end = 0;
@@ -861,54 +866,83 @@ __global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const P
     }
     s_base[e] = base;
     s_end[e] = end;
+    s_pref[e + 1] = n;
   }
-  if (tid == 0) {  // prefix over the (species, quad) staging regions
-    int acc = 0;
-    for (int r = 0; r < P.nsp * PL_NQ; r++) {
-      const int isp = r / PL_NQ, q = r - isp * PL_NQ;
-      s_off[r] = acc;
-      acc += tb[isp * (2 * WIN) + WIN + q];
-      const int cy = q / (TX / 4), cx0 = (q - cy * (TX / 4)) * 4;
-      s_qbeg[r] = (cy < th && cx0 < tw) ? cstart[(size_t)isp * (P.ncell + 1) + (lj0 + cy) * P.nx + li0 + cx0] : 0;
+  for (int r = tid; r < nreg; r += PL_THREADS) {
+    const int isp = r / PL_NQ, q = r - isp * PL_NQ;
+    const int cy = q / (TX / 4), cx0 = (q - cy * (TX / 4)) * 4;
+    long long rec0 = 0;
+    int cap = 0;
+    if (cy < th && cx0 < tw) {
+      const int c0 = (lj0 + cy) * P.nx + li0 + cx0;
+      const int *cs = cstart + (size_t)isp * (P.ncell + 1);
+      stage_region(so_slots(P, isp) + cs[c0], so_slots(P, isp) + cs[min(c0 + 4, (lj0 + cy + 1) * P.nx)], &rec0, &cap);
     }
-    s_off[P.nsp * PL_NQ] = acc;
+    s_rec0[r] = rec0;
+    s_off[r + 1] = min(tb[isp * (2 * WIN) + WIN + q], cap);
   }
   __syncthreads();
-  const int total = s_off[P.nsp * PL_NQ], nreg = P.nsp * PL_NQ;
+  if (tid == 0) {
+    s_pref[0] = 0;
+    for (int e = 0; e < nwin; e++) s_pref[e + 1] += s_pref[e];
+  }
+  if (tid == 32) {
+    s_off[0] = 0;
+    for (int r = 0; r < nreg; r++) s_off[r + 1] += s_off[r];
+  }
+  __syncthreads();
+  const int total = s_pref[nwin], nstaged = s_off[nreg];
   const size_t cstride = (size_t)P.cap * P.nsp;
-  for (int k = tid; k < total; k += PL_THREADS) {
-    int lo = 0, hi = nreg;  // largest r with s_off[r] <= k
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_off[mid] <= k) lo = mid; else hi = mid;
+  for (int j0 = 0; j0 < total; j0 += PL_MAX) {
+    // where does every staged record go in destination order?  (window cell, rank) -> position
+    for (int k = tid; k < nstaged; k += PL_THREADS) {
+      int lo = 0, hi = nreg;  // largest r with s_off[r] <= k
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= k) lo = mid; else hi = mid;
+      }
+      const long long ri = s_rec0[lo] + (k - s_off[lo]);
+      const uint32_t t = (uint32_t)__double_as_longlong(stage[ri * 4 + 3].x);
+      if (t == TAG_DEAD) continue;  // left the slab: already in the send buffer
+      const int e = (lo / PL_NQ) * WIN + (int)((t >> TAG_WSHIFT) & 0xff);
+      const int j = s_pref[e] + (int)(t & TAG_RANK_MASK) - j0;
+      if (j >= 0 && j < PL_MAX) s_inv[j] = (int)(ri - s_rec0[0]);
     }
-    const int isp = lo / PL_NQ;
-    const size_t so = (size_t)isp * P.cap;
-    const size_t sp = so + s_qbeg[lo] + (k - s_off[lo]);
-    const uint32_t t = tag[sp];
-    if (t == TAG_DEAD) continue;  // left the slab: already in the send buffer
-    const int w = (t >> TAG_WSHIFT) & 0xff, rk = (int)(t & TAG_RANK_MASK);
-    const int e = isp * WIN + w;
-    const double *r = stage.x + sp;
-    if (s_base[e] < 0) continue;
-    const int d = s_base[e] + rk;
-    if (d < s_end[e]) {
-      double *o = dst.x + so + d;
-      o[0] = r[0];
-      o[cstride] = r[cstride];
-      o[2 * cstride] = r[2 * cstride];
-      o[3 * cstride] = r[3 * cstride];
-      o[4 * cstride] = r[4 * cstride];
-      o[5 * cstride] = r[5 * cstride];
-    } else {  // segment full: park the record; the host rebuilds the layout after this step
-      const int kk = atomicAdd(ovfcnt, 1);
-      if (kk < ovfcap) {
-        for (int c = 0; c < 6; c++) ovf[(size_t)kk * 6 + c] = r[c * cstride];
-        ovfsp[kk] = isp;
-      } else {
-        atomicOr(err, ERR_OVERFLOW);
+    __syncthreads();
+    // consecutive threads write consecutive slots of the same destination segment
+    const int nj = min(PL_MAX, total - j0);
+    for (int j = tid; j < nj; j += PL_THREADS) {
+      const long long ri = s_rec0[0] + s_inv[j];
+      const double2 r0 = stage[ri * 4], r1 = stage[ri * 4 + 1], r2 = stage[ri * 4 + 2];
+      const uint32_t t = (uint32_t)__double_as_longlong(stage[ri * 4 + 3].x);
+      int lo = 0, hi = nwin;  // largest e with s_pref[e] <= j0 + j
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_pref[mid] <= j0 + j) lo = mid; else hi = mid;
+      }
+      const int e = lo, isp = e / WIN;
+      if (s_base[e] < 0) continue;
+      const int d = s_base[e] + (int)(t & TAG_RANK_MASK);
+      if (d < s_end[e]) {
+        double *o = dst.x + (size_t)isp * P.cap + d;
+        o[0] = r0.x;
+        o[cstride] = r0.y;
+        o[2 * cstride] = r1.x;
+        o[3 * cstride] = r1.y;
+        o[4 * cstride] = r2.x;
+        o[5 * cstride] = r2.y;
+      } else {  // segment full: park the record; the host rebuilds the layout after this step
+        const int kk = atomicAdd(ovfcnt, 1);
+        if (kk < ovfcap) {
+          double *o = ovf + (size_t)kk * 6;
+          o[0] = r0.x; o[1] = r0.y; o[2] = r1.x; o[3] = r1.y; o[4] = r2.x; o[5] = r2.y;
+          ovfsp[kk] = isp;
+        } else {
+          atomicOr(err, ERR_OVERFLOW);
+        }
       }
     }
+    __syncthreads();
   }
 }
 
@@ -1000,10 +1034,10 @@ void launch_incoming_append(const DevParams &P, const double *rec, int n, int is
   if (n > 0)
     k_incoming_append<<<(n + 255) / 256, 256, 0, st>>>(P, rec, n, isp, cstart, cnt_tail, dst, ovf, ovfsp, ovfcnt, ovfcap, err);
 }
-void launch_place(const DevParams &P, const PartSoA &stage, const PartSoA &dst, const int *cstart, int *cnt_new,
-                  const int *tilebase, const uint32_t *tag, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
-                  cudaStream_t st) {
-  k_place<<<P.ntx * P.nty, PL_THREADS, 0, st>>>(P, stage, dst, cstart, cnt_new, tilebase, tag, ovf, ovfsp, ovfcnt, ovfcap, err);
+void launch_place(const DevParams &P, const double *stage, const PartSoA &dst, const int *cstart, int *cnt_new,
+                  const int *tilebase, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err, cudaStream_t st) {
+  k_place<<<P.ntx * P.nty, PL_THREADS, 0, st>>>(P, reinterpret_cast<const double2 *>(stage), dst, cstart, cnt_new, tilebase, ovf,
+                                               ovfsp, ovfcnt, ovfcap, err);
 }
 void launch_mark_dead(const DevParams &P, double *x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st) {
   k_mark_dead<<<148 * 16, 256, 0, st>>>(P, x, cstart, cnt_old, cnt_new);

@@ -978,7 +978,7 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
       WM(migrate(c, true));
       if (c->timing) CU(cudaEventRecord(c->ev[4], c->st));
       // sort__bucket, reduced to the cell changers: append them to their new segments
-      launch_place(P, c->soa[c->cur ^ 1], a, c->cstart[c->cur], c->cnt_tail, c->tilebase, c->tag, c->ovf, c->ovfsp, c->ovfcnt,
+      launch_place(P, c->pbuf[c->cur ^ 1], a, c->cstart[c->cur], c->cnt_tail, c->tilebase, c->ovf, c->ovfsp, c->ovfcnt,
                    c->ovfcap, c->d_err, c->st);
       launch_mark_dead(P, a.x, c->cstart[c->cur], c->cnt[c->cur], c->cnt_tail, c->st);
       c->launches += 2;
