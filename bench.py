@@ -257,14 +257,14 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "pass1_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_pass1<PUSH|DEPOSIT|BOUND> (exact)" if args.exact else "k_fused (push+deposit+boundary+histogram, one pass)",
+    roofline = {"bound": "hbm", "kernel": "k_pass1<PUSH|DEPOSIT|BOUND> (exact)" if args.exact else "k_fused<INPLACE> (push + Esirkepov deposit + particle boundaries + in-place cell sort of the stayers, one pass)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_kind, "alg_bytes_per_particle": ALG_BYTES_PASS1, "ms_per_launch": ms_pass1,
                 "whole_step": {"alg_bytes_per_particle_step": ALG_BYTES_STEP,
                                "achieved": ALG_BYTES_STEP * n_local / (allmax(ms[4]) / args.steps * 1e-3) / 1e9,
                                "frac": ALG_BYTES_STEP * n_local / (allmax(ms[4]) / args.steps * 1e-3) / 1e9 / peak}}
-    stage_ms = {"pass1_push_deposit_boundary": ms[0] / args.steps, "field_solve": ms[1] / args.steps,
-                "prep_migrate_scan": ms[2] / args.steps, "pass2_scatter": ms[3] / args.steps}
+    stage_ms = {"fused_push_deposit_boundary_sort": ms[0] / args.steps, "field_solve": ms[1] / args.steps,
+                "prep_and_migration": ms[2] / args.steps, "sort_place_cell_changers": ms[3] / args.steps}
 
     # ---- end to end through host arrays -------------------------------------------------------
     e2e = None
@@ -311,7 +311,9 @@ def main():
                                    "(BASELINE configs[1] slab)" % (nx, ny, rows, ppc),
                        "particles": int(n_total), "parallelism": "y-slab x%d" % world,
                        "l2": "working set %.1f GB per GPU >> 126 MB L2" % (n_local * 96 / 1e9),
-                       "push_arithmetic": "exact" if args.exact else "fma", "cg_iters": cg},
+                       "push_arithmetic": "exact" if args.exact else "fma", "cg_iters": cg,
+                       "sort": "tag+scatter" if (args.exact or os.environ.get("WM_INPLACE") == "0") else "in-place",
+                       "layout_rebuilds": ctx.rebuilds()},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "stage_ms": stage_ms, "wall_ms_per_step": wall_step,
         }
