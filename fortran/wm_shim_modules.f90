@@ -231,3 +231,74 @@ contains
   end subroutine mom_calc__nvt
 
 end module mom_calc
+
+
+!> proj/reconnection/boundary_reconnection.f90 (reflecting / conducting x walls, periodic y).
+!! The app selects it by `use boundary_reconnection, bc__init => boundary_reconnection__init, ...`
+!! (proj/reconnection/app.f90:6-13); nothing else changes.
+module boundary_reconnection
+  use wm_cabi
+  implicit none
+  private
+  public :: boundary_reconnection__init
+  public :: boundary_reconnection__dfield, boundary_reconnection__particle_x, boundary_reconnection__particle_y
+  public :: boundary_reconnection__curre, boundary_reconnection__phi, boundary_reconnection__mom
+contains
+
+  subroutine boundary_reconnection__init(ndim_in,np_in,nsp_in,nxgs_in,nxge_in,nygs_in,nyge_in,nys_in,nye_in, &
+                            nup_in,ndown_in,mnpi_in,mnpr_in,ncomw_in,nerr_in,nstat_in,          &
+                            delx_in,delt_in,c_in)
+    use mpi
+    integer, intent(in) :: ndim_in, np_in, nsp_in
+    integer, intent(in) :: nxgs_in, nxge_in, nygs_in, nyge_in, nys_in, nye_in
+    integer, intent(in) :: nup_in, ndown_in, mnpi_in, mnpr_in, ncomw_in, nerr_in, nstat_in(:)
+    real(8), intent(in) :: delx_in, delt_in, c_in
+    integer :: nerr, nrank, nsize
+    call MPI_COMM_RANK(ncomw_in, nrank, nerr)
+    call MPI_COMM_SIZE(ncomw_in, nsize, nerr)
+    cfg%nrank = nrank; cfg%nsize = nsize
+    comm_world = ncomw_in
+    bc_kind = WM_BC_RECONNECTION
+    have_ring = .true.
+    call wm_shim__try_create()
+  end subroutine boundary_reconnection__init
+
+  !> the device library takes the wall positions from nxgs/nxge; the apps pass nxs = nxgs, nxe = nxge
+  subroutine boundary_reconnection__particle_x(up,np2,nxs,nxe)
+    integer, intent(in)    :: nxs, nxe
+    integer, intent(in)    :: np2(cfg%nys:cfg%nye,cfg%nsp)
+    real(8), intent(inout) :: up(cfg%ndim,cfg%np,cfg%nys:cfg%nye,cfg%nsp)
+    if (nxs /= cfg%nxgs .or. nxe /= cfg%nxge) then
+       write(6,*) 'boundary_reconnection__particle_x: nxs/nxe must equal nxgs/nxge'
+       stop
+    end if
+    call wm_check(wm_boundary__particle_x(ctx), 'boundary_reconnection__particle_x')
+  end subroutine boundary_reconnection__particle_x
+
+  subroutine boundary_reconnection__particle_y(up,np2)
+    integer, intent(inout) :: np2(cfg%nys:cfg%nye,cfg%nsp)
+    real(8), intent(inout) :: up(cfg%ndim,cfg%np,cfg%nys:cfg%nye,cfg%nsp)
+    call wm_check(wm_boundary__particle_y(ctx), 'boundary_reconnection__particle_y')
+  end subroutine boundary_reconnection__particle_y
+
+  subroutine boundary_reconnection__dfield(df,nxs,nxe,nys,nye,nxgs,nxge)
+    integer, intent(in)    :: nxs, nxe, nys, nye, nxgs, nxge
+    real(8), intent(inout) :: df(6,nxgs-2:nxge+2,nys-2:nye+2)
+  end subroutine boundary_reconnection__dfield
+
+  subroutine boundary_reconnection__curre(uj,nxs,nxe,nys,nye,nxgs,nxge)
+    integer, intent(in)    :: nxs, nxe, nys, nye, nxgs, nxge
+    real(8), intent(inout) :: uj(3,nxgs-2:nxge+2,nys-2:nye+2)
+  end subroutine boundary_reconnection__curre
+
+  subroutine boundary_reconnection__phi(phi,nxs,nxe,nys,nye,l)
+    integer, intent(in)    :: nxs, nxe, nys, nye, l
+    real(8), intent(inout) :: phi(nxs-1:nxe+1,nys-1:nye+1)
+  end subroutine boundary_reconnection__phi
+
+  subroutine boundary_reconnection__mom(mom)
+    real(8), intent(inout) :: mom(7,cfg%nxgs-1:cfg%nxge+1,cfg%nys-1:cfg%nye+1,cfg%nsp)
+    call wm_check(wm_boundary__mom(ctx, mom), 'boundary_reconnection__mom')
+  end subroutine boundary_reconnection__mom
+
+end module boundary_reconnection

@@ -38,7 +38,12 @@ extern "C" {
 #define WM_UNIQUE_ID_BYTES 128
 
 /* boundary plugin (the module chosen by `use ... => bc__*` in proj/<problem>/app.f90:6-13) */
-enum { WM_BC_PERIODIC = 0 };
+enum {
+  WM_BC_PERIODIC = 0,      /* common/boundary_periodic.f90 (proj/weibel)                                         */
+  WM_BC_RECONNECTION = 1   /* proj/reconnection/boundary_reconnection.f90: reflecting particles / conducting     */
+                           /* fields at the x walls nxs+1, nxe-1; periodic y                                     */
+  /* proj/shock/boundary_shock.f90 (moving injection wall, nxe changes in time) is not implemented yet          */
+};
 
 /* flags */
 enum {

@@ -344,6 +344,8 @@ void bc_curre(orc_world *w) {
   // my nye-1,nye -> nup; ndown's go to my nys-2,nys-1                                 :464-493
   pack(3);
   unpack(false, 3, false);
+  // the wall modules end after the y exchange (proj/reconnection/boundary_reconnection.f90:364-502)
+  if (w->c.bc != ORC_BC_PERIODIC) return;
   // x fold + copy back                                                                :495-506
   for (Rank &k : w->R) {
     V v{w, &k};
@@ -419,6 +421,21 @@ void bc_dfield(orc_world *w) {
       }
     }
   }
+  if (w->c.bc == ORC_BC_RECONNECTION) {
+    // conducting walls: odd / even mirror  (proj/reconnection/boundary_reconnection.f90:349-359)
+    for (Rank &k : w->R) {
+      V v{w, &k};
+      for (int j = k.nys - 2; j <= k.nye + 2; j++) {
+        k.df[v.F6(1, nxs - 1, j)] = -k.df[v.F6(1, nxs, j)];
+        for (int cidx = 2; cidx <= 4; cidx++) k.df[v.F6(cidx, nxs - 1, j)] = k.df[v.F6(cidx, nxs + 1, j)];
+        for (int cidx = 5; cidx <= 6; cidx++) k.df[v.F6(cidx, nxs - 1, j)] = -k.df[v.F6(cidx, nxs, j)];
+        k.df[v.F6(1, nxe, j)] = -k.df[v.F6(1, nxe - 1, j)];
+        for (int cidx = 2; cidx <= 4; cidx++) k.df[v.F6(cidx, nxe + 1, j)] = k.df[v.F6(cidx, nxe - 1, j)];
+        for (int cidx = 5; cidx <= 6; cidx++) k.df[v.F6(cidx, nxe, j)] = -k.df[v.F6(cidx, nxe - 1, j)];
+      }
+    }
+    return;
+  }
   // x ghosts by periodic copy                                                          :347-352
   for (Rank &k : w->R) {
     V v{w, &k};
@@ -433,7 +450,7 @@ void bc_dfield(orc_world *w) {
 }
 
 // boundary_periodic.f90:511-568 ; which: 0 = phi, 1 = p
-void bc_phi(orc_world *w, int which, int /*l*/) {
+void bc_phi(orc_world *w, int which, int l) {
   const int nxs = w->nxs, nxe = w->nxe;
   const int nr = (int)w->R.size();
   std::vector<std::vector<double>> snd(nr, std::vector<double>(w->nx));
@@ -458,6 +475,18 @@ void bc_phi(orc_world *w, int which, int /*l*/) {
     V v{w, &k};
     for (int i = nxs; i <= nxe; i++) arr(k)[v.PH(i, k.nys - 1)] = snd[k.ndown][i - nxs];
   }
+  if (w->c.bc == ORC_BC_RECONNECTION) {
+    // l = 1 (Bx) odd, l = 2,3 even at the left wall; zero at the right wall
+    // (proj/reconnection/boundary_reconnection.f90:557-577)
+    for (Rank &k : w->R) {
+      V v{w, &k};
+      for (int j = k.nys - 1; j <= k.nye + 1; j++) {
+        arr(k)[v.PH(nxs - 1, j)] = (l == 1) ? -arr(k)[v.PH(nxs, j)] : arr(k)[v.PH(nxs + 1, j)];
+        arr(k)[v.PH(nxe + 1, j)] = 0.0;
+      }
+    }
+    return;
+  }
   for (Rank &k : w->R) {  // :563-566
     V v{w, &k};
     for (int j = k.nys - 1; j <= k.nye + 1; j++) {
@@ -471,6 +500,33 @@ void bc_phi(orc_world *w, int which, int /*l*/) {
 void bc_particle_x(orc_world *w) {
   const int nxgs = w->nxgs, nxge = w->nxge;
   const double delx = w->delx;
+  if (w->c.bc == ORC_BC_RECONNECTION) {
+    // reflecting walls at nxs+1 and nxe-1  (proj/reconnection/boundary_reconnection.f90:61-99)
+    const int nxs = w->nxs, nxe = w->nxe;
+    for (Rank &k : w->R) {
+      V v{w, &k};
+      for (int isp = 1; isp <= w->nsp; isp++) {
+#pragma omp parallel for
+        for (int j = k.nys; j <= k.nye; j++)
+          for (int ii = 1; ii <= k.np2[v.NP2(j, isp)]; ii++) {
+            double *r = &k.gp[v.UP(1, ii, j, isp)];
+            const int ipos = (int)(r[0] / delx);
+            if (ipos < nxs + 1) {
+              r[0] = 2. * (nxs + 1) * delx - r[0];
+              r[2] = -r[2];
+              r[3] = -r[3];
+              r[4] = -r[4];
+            } else if (ipos >= nxe - 1) {
+              r[0] = 2. * (nxe - 1) * delx - r[0];
+              r[2] = -r[2];
+              r[3] = -r[3];
+              r[4] = -r[4];
+            }
+          }
+      }
+    }
+    return;
+  }
   for (Rank &k : w->R) {
     V v{w, &k};
     for (int isp = 1; isp <= w->nsp; isp++) {
@@ -869,8 +925,13 @@ void bc_mom(orc_world *w) {
     for (int isp = 1; isp <= w->nsp; isp++)
       for (int j = k.nys - 1; j <= k.nye + 1; j++)
         for (int m = 1; m <= nk; m++) {
-          k.mom[v.MOM(m, nxgs, j, isp)] = k.mom[v.MOM(m, nxgs, j, isp)] + k.mom[v.MOM(m, nxge + 1, j, isp)];
-          k.mom[v.MOM(m, nxge, j, isp)] = k.mom[v.MOM(m, nxge, j, isp)] + k.mom[v.MOM(m, nxgs - 1, j, isp)];
+          if (w->c.bc == ORC_BC_PERIODIC) {
+            k.mom[v.MOM(m, nxgs, j, isp)] = k.mom[v.MOM(m, nxgs, j, isp)] + k.mom[v.MOM(m, nxge + 1, j, isp)];
+            k.mom[v.MOM(m, nxge, j, isp)] = k.mom[v.MOM(m, nxge, j, isp)] + k.mom[v.MOM(m, nxgs - 1, j, isp)];
+          } else {  // walls: the ghost column folds back onto its own side (boundary_reconnection.f90:590-595)
+            k.mom[v.MOM(m, nxgs, j, isp)] = k.mom[v.MOM(m, nxgs, j, isp)] + k.mom[v.MOM(m, nxgs - 1, j, isp)];
+            k.mom[v.MOM(m, nxge, j, isp)] = k.mom[v.MOM(m, nxge, j, isp)] + k.mom[v.MOM(m, nxge + 1, j, isp)];
+          }
         }
   }
   const int n = nk * (nxge - nxgs + 3);
@@ -926,7 +987,7 @@ extern "C" {
 
 orc_world *orc_create(const orc_config *cfg) {
   if (cfg->nsp < 1 || cfg->nsp > ORC_NSP_MAX || cfg->nranks < 1 || cfg->ny < cfg->nranks) return nullptr;
-  if (cfg->bc != ORC_BC_PERIODIC) return nullptr;
+  if (cfg->bc != ORC_BC_PERIODIC && cfg->bc != ORC_BC_RECONNECTION) return nullptr;
   orc_world *w = new orc_world();
   w->c = *cfg;
   w->nx = cfg->nx;

@@ -35,7 +35,11 @@ extern "C" {
 #define ORC_NSP_MAX 4
 
 /* boundary kinds (the "plugin" chosen by use-renaming in proj/<problem>/app.f90:6-13) */
-enum { ORC_BC_PERIODIC = 0 };
+enum {
+  ORC_BC_PERIODIC = 0,      /* common/boundary_periodic.f90 (weibel)                                        */
+  ORC_BC_RECONNECTION = 1   /* proj/reconnection/boundary_reconnection.f90: conducting/reflecting x walls,   */
+                            /* periodic y                                                                     */
+};
 
 typedef struct orc_config {
   int32_t nx, ny;      /* global grid: nxge-nxgs+1, nyge-nygs+1            */

@@ -49,3 +49,40 @@ def particle_err(rec_a, rec_b, xscale, vth):
     ex = np.abs(rec_a[:, :2] - rec_b[:, :2]).max() / xscale
     eu = (np.abs(rec_a[:, 2:] - rec_b[:, 2:]) / np.maximum(np.abs(rec_b[:, 2:]), vth)).max()
     return ex, eu
+
+
+def make_wall_world(nx, ny, ppc, nranks=1, steps=0, seed=7, b0=0.02, **kw):
+    """A reconnection-type world (proj/reconnection: reflecting/conducting x walls, periodic y) with a
+    neutral uniform plasma between the walls and a Harris-like By(x) = b0 tanh((x - xc)/lam).
+    The IC is written into gp and bucket-sorted by the oracle (the restart path, app.f90:351-352)."""
+    prm = O.weibel_params(nx, ny, ppc, nranks=nranks, **kw)
+    prm["bc"] = O.BC_RECONNECTION
+    w = O.World(prm)
+    rng = np.random.default_rng(seed)
+    nxgs, nygs = prm["nxgs"], prm["nygs"]
+    xlo, xhi = nxgs + 1, nxgs + nx - 3          # particles live in cells nxs+1 .. nxe-2 (nxe = nxgs+nx-1)
+    npr = ppc * (xhi - xlo + 1)
+    gid = 0
+    for rk in range(nranks):
+        nys, nye = w.bounds(rk)
+        gp, np2 = w.array(rk, O.GP), w.array(rk, O.NP2)
+        uf = w.array(rk, O.UF)
+        ii = np.arange(uf.shape[1]) + (nxgs - 2)
+        uf[:, :, 1] = b0 * np.tanh((ii[None, :] - (nxgs + nx / 2.0)) / 3.0)
+        for jl in range(nye - nys + 1):
+            # the same sequence for any rank count: seed by global row
+            r = np.random.default_rng([seed, nys + jl])
+            x = r.uniform(xlo, xhi + 1, npr)
+            y = (nys + jl) + r.uniform(0, 1, npr)
+            for isp in range(2):
+                u = r.normal(0.0, prm["vte"], (npr, 3))
+                gp[isp, jl, :npr, 0], gp[isp, jl, :npr, 1] = x, y
+                gp[isp, jl, :npr, 2:5] = u
+                gp[isp, jl, :npr, 5].view(np.int64)[:] = -(np.arange(npr) + 1 + (nys - nygs + jl) * npr)
+                np2[isp, jl] = npr
+    w.sort_bucket()
+    for rk in range(nranks):
+        w.array(rk, O.GP)[...] = w.array(rk, O.UP)
+    if steps:
+        w.step(steps)
+    return prm, w

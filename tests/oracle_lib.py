@@ -16,6 +16,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 NSP_MAX = 4
 UP, GP, UF, DF, UJ, GKL, MOM = range(7)
 NP2, CUMCNT = 16, 17
+BC_PERIODIC, BC_RECONNECTION = 0, 1
 
 
 class OrcConfig(C.Structure):
@@ -104,7 +105,7 @@ class World:
         self.lib = load(fast)
         cfg = OrcConfig()
         cfg.nx, cfg.ny, cfg.nxgs, cfg.nygs = prm["nx"], prm["ny"], prm.get("nxgs", 2), prm.get("nygs", 2)
-        cfg.nranks, cfg.np, cfg.nsp, cfg.bc = prm["nranks"], prm["np"], prm["nsp"], 0
+        cfg.nranks, cfg.np, cfg.nsp, cfg.bc = prm["nranks"], prm["np"], prm["nsp"], prm.get("bc", 0)
         cfg.delx, cfg.delt, cfg.c, cfg.gfac = prm["delx"], prm["delt"], prm["c"], prm["gfac"]
         for s in range(prm["nsp"]):
             cfg.q[s] = prm["q"][s]

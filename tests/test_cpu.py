@@ -98,3 +98,25 @@ def test_oracle_rng_is_decomposition_independent():
     u = a[2][:, 2:]
     assert abs(u[:, 0].std() - 0.1) < 5e-3 and abs(u[:, 2].std() - 0.5) < 2.5e-2
     w1.close(); w4.close()
+
+
+@pytest.mark.parametrize("nranks", [1, 3])
+def test_oracle_reconnection_walls(nranks):
+    """proj/reconnection boundary module in the oracle: particles stay between the reflecting walls,
+    their number is conserved, total energy is conserved to 5e-3, and the slab decomposition does
+    not change the answer."""
+    from helpers import make_wall_world
+    prm, w = make_wall_world(32, 18, 8, nranks=nranks)
+    _, w1 = make_wall_world(32, 18, 8, nranks=1)
+    e0 = w.energy().sum()
+    w.step(15)
+    w1.step(15)
+    ids, sp, rec = w.particles_by_id()
+    assert len(ids) == 2 * 8 * (32 - 3) * 18
+    assert rec[:, 0].min() >= prm["nxgs"] + 1 and rec[:, 0].max() < prm["nxgs"] + 32 - 2
+    assert abs(w.energy().sum() - e0) <= 5e-3 * e0   # not an equilibrium: fields build up from noise
+    i1, s1, r1 = w1.particles_by_id()
+    assert np.array_equal(ids, i1) and np.abs(rec - r1).max() <= 1e-12
+    assert np.abs(w.global_field() - w1.global_field()).max() <= 1e-13
+    assert w.cg_iters() == w1.cg_iters()
+    w.close(); w1.close()

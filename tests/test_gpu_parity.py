@@ -302,3 +302,40 @@ def test_sort_variants_match_oracle(env, monkeypatch):
     if env.get("WM_SLACK") == "0.4":
         assert c.rebuilds() > 0, "the overflow -> rebuild path was not exercised"
     c.close()
+
+
+@pytest.mark.parametrize("env", [{}, {"WM_INPLACE": "0"}])
+def test_reconnection_walls_match_oracle(env, monkeypatch):
+    """WM_BC_RECONNECTION (proj/reconnection/boundary_reconnection.f90): reflecting particle walls at
+    nxs+1 / nxe-1 with momentum flip, conducting-wall rules for df and the CG vectors, no x fold of the
+    current; fused step and the stage calls against the oracle's restatement of that module."""
+    import wumingpic2d_b200 as wm
+    from helpers import make_wall_world
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    prm, w = make_wall_world(40, 20, 10)
+    s = oracle_state(w)
+    for flags in (0, wm.WM_FLAG_EXACT_PUSH):
+        _, w = make_wall_world(40, 20, 10)
+        c = ctx_for(prm, flags=flags)
+        c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+        c.upload_field(s["uf"])
+        for it in range(8):
+            w.step(1)
+            if it == 5:   # one step through the five stage calls (bc__particle_x = k_bcx reflects)
+                c.particle__solv(); c.field__fdtd_i(); c.bc__particle_x(); c.bc__particle_y(); c.sort__bucket()
+            else:
+                c.step(1)
+            assert c.cg_iters() == w.cg_iters()
+            up, np2, cum = c.download_particles()
+            assert np.array_equal(cum, w.array(0, O.CUMCNT)), "per-cell counts must be bit-exact (step %d)" % it
+            a, b = flatten_by_id(up, np2), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+            ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+            tol = 1e-12 if it == 0 else 1e-10
+            assert ex <= tol and eu <= tol
+            assert rel_to_max(c.download_field(), w.array(0, O.UF)).max() <= tol
+        w.mom_accl(); w.mom_nvt(); w.bc_mom()
+        mom = c.moments()
+        assert rel_to_max(mom[:, 1:-1, 1:-1], w.array(0, O.MOM)[:, 1:-1, 1:-1]).max() <= 1e-10
+        c.close(); w.close()

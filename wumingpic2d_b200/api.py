@@ -16,6 +16,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 WM_NSP_MAX = 2
 WM_BC_PERIODIC = 0
+WM_BC_RECONNECTION = 1
 WM_FLAG_EXACT_PUSH = 1
 
 
@@ -158,7 +159,7 @@ class Context:
         return cls(np_cap=prm["np"], nxgs=nxgs, nxge=nxgs + prm["nx"] - 1, nygs=nygs, nyge=nyge,
                    nys=nygs if nys is None else nys, nye=nyge if nye is None else nye,
                    delx=prm["delx"], delt=prm["delt"], c=prm["c"], q=prm["q"], r=prm["r"],
-                   gfac=prm["gfac"], nsp=prm["nsp"], nrank=nrank, **kw)
+                   gfac=prm["gfac"], nsp=prm["nsp"], nrank=nrank, bc=kw.pop("bc", prm.get("bc", WM_BC_PERIODIC)), **kw)
 
     def _ck(self, rc):
         if rc:

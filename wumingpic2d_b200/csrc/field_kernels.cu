@@ -79,6 +79,22 @@ __global__ void k_fill_y_local(const DevParams P, double *a, int ncomp, int ng) 
   }
 }
 
+// df x boundary at conducting walls, all rows incl. ghosts   proj/reconnection/boundary_reconnection.f90:349-359
+// (one ghost column per side; Bx, Ey, Ez odd about the wall and pinned on it, By, Bz, Ex even)
+__global__ void k_wall_x_dfield(const DevParams P, double *df) {
+  const int n = P.nyl + 4;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    double *row = df + pidx(P, 0, t - 2) * 6;  // row[6*li + c], li = 0 is nxs
+    const int e = P.nx - 1;                    // nxe
+    row[6 * (-1) + 0] = -row[6 * 0 + 0];
+    for (int c = 1; c <= 3; c++) row[6 * (-1) + c] = row[6 * 1 + c];
+    for (int c = 4; c <= 5; c++) row[6 * (-1) + c] = -row[6 * 0 + c];
+    row[6 * e + 0] = -row[6 * (e - 1) + 0];
+    for (int c = 1; c <= 3; c++) row[6 * (e + 1) + c] = row[6 * (e - 1) + c];
+    for (int c = 4; c <= 5; c++) row[6 * e + c] = -row[6 * (e - 1) + c];
+  }
+}
+
 // uj: x fold then copy back, all rows                               boundary_periodic.f90:495-506
 __global__ void k_fold_x(const DevParams P, double *uj) {
   const int n = (P.nyl + 4) * 3;
@@ -121,8 +137,13 @@ __global__ void k_mom_fold_x(const DevParams P, double *mom) {
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     const int m = t % 7, row = t / 7;  // row = isp*nyp + j
     double *r = mom + (size_t)row * nxp * 7 + m;
-    r[7 * 1] = r[7 * 1] + r[7 * (P.nx + 1)];  // nxgs += nxge+1
-    r[7 * P.nx] = r[7 * P.nx] + r[7 * 0];     // nxge += nxgs-1
+    if (P.bc == WM_BC_PERIODIC) {
+      r[7 * 1] = r[7 * 1] + r[7 * (P.nx + 1)];  // nxgs += nxge+1
+      r[7 * P.nx] = r[7 * P.nx] + r[7 * 0];     // nxge += nxgs-1
+    } else {  // walls: boundary_reconnection.f90:590-595
+      r[7 * 1] = r[7 * 1] + r[7 * 0];                     // nxgs += nxgs-1
+      r[7 * P.nx] = r[7 * P.nx] + r[7 * (P.nx + 1)];      // nxge += nxge+1
+    }
   }
 }
 
@@ -216,6 +237,18 @@ __device__ __forceinline__ void nbr(const DevParams &P, int li, int lj, size_t &
   yp = pidx(P, li, ljp);
 }
 
+// x neighbours of component l of a CG vector.  Periodic: the wrapped column.  Conducting walls
+// (proj/reconnection/boundary_reconnection.f90:557-577): left ghost = -phi(nxs) for l = 1 (Bx, odd) and
+// phi(nxs+1) for l = 2,3 (even); right ghost = 0.
+__device__ __forceinline__ double nb_xm(const DevParams &P, const double *a, int l, int li, size_t o, size_t xm) {
+  if (P.bc != WM_BC_PERIODIC && li == 0) return (l == 0) ? -a[o * 3 + l] : a[(o + 1) * 3 + l];
+  return a[xm * 3 + l];
+}
+__device__ __forceinline__ double nb_xp(const DevParams &P, const double *a, int l, int li, size_t xp) {
+  if (P.bc != WM_BC_PERIODIC && li == P.nx - 1) return 0.0;
+  return a[xp * 3 + l];
+}
+
 // phi <- df(l), b <- f5*gkl(l) (in place), sum b^2                          field.f90:349-362
 __global__ void __launch_bounds__(256) k_cg_init(const DevParams P, const double *__restrict__ df, double *gkl,
                                                  double *__restrict__ phi, double *red, CgCtl *ctl) {
@@ -248,7 +281,8 @@ __global__ void __launch_bounds__(256) k_cg_resid0(const DevParams P, const doub
     nbr(P, li, lj, xm, xp, ym, yp);
 #pragma unroll
     for (int l = 0; l < 3; l++) {
-      const double rr = b[o * 3 + l] + phi[ym * 3 + l] + phi[xm * 3 + l] - P.f4 * phi[o * 3 + l] + phi[xp * 3 + l] + phi[yp * 3 + l];
+      const double rr = b[o * 3 + l] + phi[ym * 3 + l] + nb_xm(P, phi, l, li, o, xm) - P.f4 * phi[o * 3 + l] +
+                        nb_xp(P, phi, l, li, xp) + phi[yp * 3 + l];
       r[o * 3 + l] = rr;
       p[o * 3 + l] = rr;
       s[l] = s[l] + rr * rr;
@@ -292,7 +326,7 @@ __global__ void __launch_bounds__(256) k_cg_ap(const DevParams P, const double *
     for (int l = 0; l < 3; l++) {
       if (!act[l]) continue;
       const double pc = p[o * 3 + l];
-      const double av = -p[ym * 3 + l] - p[xm * 3 + l] + P.f4 * pc - p[xp * 3 + l] - p[yp * 3 + l];
+      const double av = -p[ym * 3 + l] - nb_xm(P, p, l, li, o, xm) + P.f4 * pc - nb_xp(P, p, l, li, xp) - p[yp * 3 + l];
       ap[o * 3 + l] = av;
       const double rr = r[o * 3 + l];
       s[l] = s[l] + rr * rr;
@@ -455,6 +489,10 @@ void launch_tmpf(const DevParams &P, const double *uf, double *tmpf, cudaStream_
   k_tmpf<<<gblocks((long long)(P.nx + 2) * (P.nyl + 2)), 256, 0, st>>>(P, uf, tmpf);
 }
 void launch_fill_x(const DevParams &P, double *a, int ncomp, int ng, cudaStream_t st) {
+  if (P.bc != WM_BC_PERIODIC) {  // only df takes this path (the CG vectors apply their wall rule in place)
+    k_wall_x_dfield<<<gblocks((long long)P.nyl + 4), 256, 0, st>>>(P, a);
+    return;
+  }
   k_fill_x<<<gblocks((long long)(P.nyl + 4) * 2 * ng * ncomp), 256, 0, st>>>(P, a, ncomp, ng);
 }
 void launch_fill_y_local(const DevParams &P, double *a, int ncomp, int ng, cudaStream_t st) {

@@ -345,6 +345,30 @@ __global__ void __launch_bounds__(FT, 2) k_fused(const DevParams P, const Pass1A
             acc[60] = fma(hx0, vy4, acc[60]); acc[61] = fma(hx1, vy4, acc[61]); acc[62] = fma(hx2_, vy4, acc[62]); acc[63] = fma(hx3, vy4, acc[63]); acc[64] = fma(hx4, vy4, acc[64]);
           }
         }
+        // ---- reflecting x walls (after the deposit, which uses the position before the boundary)
+        //      proj/reconnection/boundary_reconnection.f90:61-99
+        if (P.bc != WM_BC_PERIODIC && active) {
+          bool flip = false;
+          if (xn < P.xwlo) {
+            xn = P.xw2lo - xn;
+            flip = true;
+          } else if (xn >= P.xwhi) {
+            xn = P.xw2hi - xn;
+            flip = true;
+          }
+          if (flip) {
+            un1 = -un1;
+            un2 = -un2;
+            un3 = -un3;
+            if (!INPLACE) {
+              double *b = px + so + pc;
+              b[2 * cstride] = un1;
+              b[3 * cstride] = un2;
+              b[4 * cstride] = un3;
+            }
+            stay = !(xn < di || xn >= di1 || yn < dj || yn >= dj1);
+          }
+        }
         // ---- sort bookkeeping                                             sort.f90:57-62
         const unsigned bal = __ballot_sync(0xffffffffu, stay);
         const unsigned balm = INPLACE ? __ballot_sync(0xffffffffu, active && !stay) : 0u;  // changers + leavers

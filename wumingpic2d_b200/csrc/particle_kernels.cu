@@ -291,7 +291,25 @@ __global__ void __launch_bounds__(P1_THREADS, 1) k_pass1(const DevParams P, cons
             // periodic wraps with round-toward -inf adds      boundary_periodic.f90:74,82-88,124,147-154
             const int j2 = gj + incy;  // unwrapped destination row
             const int ic = __double2int_rz(xn), jc = __double2int_rz(yn);
-            if (ic < P.nxgs)
+            if (P.bc != WM_BC_PERIODIC) {
+              // reflecting walls                     proj/reconnection/boundary_reconnection.f90:82-92
+              bool flip = false;
+              if (xn < P.xwlo) {
+                xn = A::sub(P.xw2lo, xn);
+                flip = true;
+              } else if (xn >= P.xwhi) {
+                xn = A::sub(P.xw2hi, xn);
+                flip = true;
+              }
+              if (flip) {
+                if (PUSH) {
+                  un1 = -un1;
+                  un2 = -un2;
+                  un3 = -un3;
+                }
+                incx = __double2int_rz(xn) - gi;  // the sort goes by the reflected position
+              }
+            } else if (ic < P.nxgs)
               xn = __dadd_rd(xn, P.xlen);
             else if (ic >= P.nxgs + P.nx)
               xn = __dadd_rd(xn, -P.xlen);
@@ -591,13 +609,24 @@ __global__ void k_soa2aos(const PartSoA src, size_t so, long long n, double *__r
 }
 
 // stand-alone x wrap (stage mode)                                  boundary_periodic.f90:61-96
-__global__ void k_bcx(const DevParams P, double *x, const int *__restrict__ cstart) {
+__global__ void k_bcx(const DevParams P, const PartSoA g, const int *__restrict__ cstart) {
+  double *x = g.x;
   for (int isp = 0; isp < P.nsp; isp++) {
     const int n = cstart[(size_t)isp * (P.ncell + 1) + P.ncell];
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
       double v = x[(size_t)isp * P.cap + s];
       if (!slot_live(v)) continue;
       const int ipos = __double2int_rz(v);
+      if (P.bc != WM_BC_PERIODIC) {  // reflecting walls   proj/reconnection/boundary_reconnection.f90:82-92
+        const size_t o = (size_t)isp * P.cap + s;
+        if (v < P.xwlo || v >= P.xwhi) {
+          x[o] = (v < P.xwlo ? P.xw2lo : P.xw2hi) - v;
+          g.ux[o] = -g.ux[o];
+          g.uy[o] = -g.uy[o];
+          g.uz[o] = -g.uz[o];
+        }
+        continue;
+      }
       if (ipos < P.nxgs) {
         x[(size_t)isp * P.cap + s] = __dadd_rd(v, P.xlen);
       } else if (ipos >= P.nxgs + P.nx) {
@@ -1042,8 +1071,8 @@ void launch_place(const DevParams &P, const double *stage, const PartSoA &dst, c
 void launch_mark_dead(const DevParams &P, double *x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st) {
   k_mark_dead<<<148 * 16, 256, 0, st>>>(P, x, cstart, cnt_old, cnt_new);
 }
-void launch_bcx(const DevParams &P, double *x, const int *cstart, cudaStream_t st) {
-  k_bcx<<<148 * 8, 256, 0, st>>>(P, x, cstart);
+void launch_bcx(const DevParams &P, const PartSoA &g, const int *cstart, cudaStream_t st) {
+  k_bcx<<<148 * 8, 256, 0, st>>>(P, g, cstart);
 }
 void launch_ic_weibel(const DevParams &P, const PartSoA &dst, int *cstart, int *cnt, uint64_t seed, int n0, double vti,
                       double vte, double t_ani, float sl, cudaStream_t st) {

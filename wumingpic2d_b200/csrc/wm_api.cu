@@ -225,8 +225,10 @@ int bc_curre(wm_ctx *c) {
     WM(ring_rows(c, uj, 3, 0, c->ndown, nyl, c->nup, 2));
     WM(ring_rows(c, uj, 3, nyl - 2, c->nup, -2, c->ndown, 2));
   }
-  launch_fold_x(c->P, uj, c->st);
-  c->launches++;
+  if (c->P.bc == WM_BC_PERIODIC) {  // the wall modules end after the y exchange (boundary_reconnection.f90:364-502)
+    launch_fold_x(c->P, uj, c->st);
+    c->launches++;
+  }
   return 0;
 }
 
@@ -440,7 +442,8 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   *out = nullptr;
   if (g->ndim != 6) return fail("wm_create: ndim must be 6 (x,y,ux,uy,uz,id)");
   if (g->nsp < 1 || g->nsp > WM_NSP_MAX) return fail("wm_create: nsp must be 1..%d", WM_NSP_MAX);
-  if (g->bc != WM_BC_PERIODIC) return fail("wm_create: only the periodic boundary module is implemented");
+  if (g->bc != WM_BC_PERIODIC && g->bc != WM_BC_RECONNECTION)
+    return fail("wm_create: boundary kind %d not implemented (periodic and reconnection walls are)", g->bc);
   if (g->delx != 1.0) return fail("wm_create: delx must be 1 (common/sort.f90:60 keys on int(x) without /delx; all apps use delx=1)");
   const int nx = g->nxge - g->nxgs + 1, ny = g->nyge - g->nygs + 1, nyl = g->nye - g->nys + 1;
   if (nx < 4 || nyl < 2 || ny < nyl) return fail("wm_create: grid too small (nx>=4, rows per rank>=2)");
@@ -456,6 +459,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   if (const char *v = getenv("WM_SLACK")) c->slack = (float)atof(v);
   if (const char *v = getenv("WM_INPLACE")) c->inplace = atoi(v) != 0;
   if (g->flags & WM_FLAG_EXACT_PUSH) c->inplace = false;  // the exact path keeps the reference's two-pass structure
+  if (g->bc != WM_BC_PERIODIC) c->fused_variant = 1;      // k_fused2 has no wall reflection
   if (g->device >= 0) {
     c->dev = g->device;
   } else {
@@ -477,6 +481,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   P.nygs = g->nygs;
   P.ny = ny;
   P.nsize = g->nsize;
+  P.bc = g->bc;
   P.pitch = nx + 4;
   P.ntx = (nx + TX - 1) / TX;
   P.nty = (nyl + TY - 1) / TY;
@@ -490,6 +495,11 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   P.inv_cc = 1.0 / P.cc;
   P.xlen = nx * g->delx;
   P.ylen = ny * g->delx;
+  // walls of boundary_reconnection.f90:82-92 (nxs = nxgs, nxe = nxge; delx = 1 so int(x/delx) < n <=> x < n)
+  P.xwlo = (g->nxgs + 1) * g->delx;
+  P.xwhi = (g->nxge - 1) * g->delx;
+  P.xw2lo = 2. * (g->nxgs + 1) * g->delx;
+  P.xw2hi = 2. * (g->nxge - 1) * g->delx;
   for (int s = 0; s < g->nsp; s++) {
     P.q[s] = g->q[s];
     P.r[s] = g->r[s];
@@ -872,7 +882,7 @@ int wm_field__fdtd_i(wm_ctx *c) {
 int wm_boundary__particle_x(wm_ctx *c) {
   WM(need_state(c, ST_PUSHED, "wm_boundary__particle_x"));
   WM(set_device(c));
-  launch_bcx(c->P, c->soa[c->cur ^ 1].x, c->cstart[c->cur], c->st);
+  launch_bcx(c->P, c->soa[c->cur ^ 1], c->cstart[c->cur], c->st);
   c->launches++;
   CU(cudaGetLastError());
   return 0;

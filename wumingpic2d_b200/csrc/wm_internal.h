@@ -45,6 +45,7 @@ struct DevParams {
   int nxgs, nys;    // global index of local cell (0,0)
   int nygs, ny;     // global y range
   int nsize;        // ranks on the ring
+  int bc;           // WM_BC_*: x boundary kind (y is periodic over the rank ring in every kind)
   int pitch;        // nx + 4
   int ntx, nty;     // tiles
   int nsp;
@@ -52,6 +53,8 @@ struct DevParams {
   long long cap;    // per-species slot capacity
   double delx, delt, c, cc, inv_cc;
   double xlen, ylen;            // nx*delx, ny*delx
+  double xwlo, xwhi;            // reflecting walls at (nxs+1)*delx, (nxe-1)*delx (wall kinds)
+  double xw2lo, xw2hi;          // 2.*(nxs+1)*delx, 2.*(nxe-1)*delx as the reference computes them
   double q[WM_NSP_MAX], r[WM_NSP_MAX];
   double f1, f2, f3, f4, f5, gfac, pi4dt;  // field.f90:53-57, 4*pi*delt
 };
@@ -111,8 +114,10 @@ __host__ __device__ inline void stage_region(long long s0, long long s1, long lo
 __device__ __forceinline__ int window_cell(const DevParams &P, int li0, int lj0, int w) {
   int lx = w % WINX, ly = w / WINX;
   int li = li0 - 1 + lx;
-  if (li < 0) li += P.nx;
-  if (li >= P.nx) li -= P.nx;
+  if (P.bc == WM_BC_PERIODIC) {
+    if (li < 0) li += P.nx;
+    if (li >= P.nx) li -= P.nx;
+  }
   int lj = lj0 - 1 + ly;
   if (P.nsize == 1) {
     if (lj < 0) lj += P.nyl;
