@@ -7,7 +7,7 @@ mkdir -p $OUT
 ( timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 ) > $OUT/pytest_gpu.log
 ( timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu 2> $OUT/bench.err | tail -1 ) > $OUT/bench.json
 if [ "$2" != "noncu" ]; then
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_fused|k_pass2|k_place|k_mark_dead" -s 6 -c 3 -o $OUT/prof_pass \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_fused|k_place" -s 4 -c 2 -o $OUT/prof_pass \
     python bench.py --rows 128 --steps 2 --warmup 2 --no-e2e --no-cpu > $OUT/ncu_full.log 2>&1
 fi
 cat $OUT/pytest_gpu.log $OUT/bench.json; tail -3 $OUT/bench.err

@@ -42,6 +42,8 @@ void launch_place(const DevParams &P, const double *stage, const PartSoA &dst, c
 void launch_mark_dead(const DevParams &P, double *x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st);
 // fused push + deposit + boundaries that moves cell changers itself (no tags, no scatter pass)
 void launch_fused_inplace(const DevParams &P, const Pass1Args &a, cudaStream_t st);
+// the same, warp-specialised: push warps and deposit warps with different register budgets (fused3_kernel.cu)
+void launch_fused_ws(const DevParams &P, const Pass1Args &a, cudaStream_t st);
 void launch_kinetic(const DevParams &P, const PartSoA &src, const int *cstart, int isp, double *partial, int nblocks,
                     cudaStream_t st);
 void launch_moments(const DevParams &P, const PartSoA &src, const double *keyx, const int *cstart, double *mom,
