@@ -29,11 +29,12 @@ namespace wm {
 
 namespace {
 
-constexpr int FT = 384;          // threads per CTA: 8 push warps + 4 deposit warps
-constexpr int WS_TEAMS = 4;      // one deposit warp + one push warp per species
+constexpr int FT = 512;          // threads per CTA: 12 push warps + 4 deposit warps
+constexpr int WS_TEAMS = 4;      // a team = one deposit warp + WS_PPT push warps, one team per SM sub-partition
+constexpr int WS_PPT = 3;        // push warps per team
 constexpr int WS_NS = 4;         // ring slots per push warp
 constexpr int WS_REC = 6;        // doubles per record: hx hy | d2x d2y | q*vz flags
-constexpr int R_PUSH = 104, R_DEP = 232;
+constexpr int R_PUSH = 104, R_DEP = 200;  // 12*104 + 4*200 = 2048 = 64 K registers / 32 lanes
 constexpr int QX = TX / 4;       // quads per tile row
 constexpr int NQ = QX * TY;      // quads per tile
 
@@ -113,10 +114,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 constexpr size_t SM_F = 0;
 constexpr size_t SM_J = SM_F + sizeof(double) * WINY * WINX * 6;
 constexpr size_t SM_RING = SM_J + sizeof(double) * 3 * JY * JX;
-constexpr size_t SM_ARR = SM_RING + sizeof(double) * 2 * WS_TEAMS * WS_NS * 32 * WS_REC;
+constexpr size_t SM_ARR = SM_RING + sizeof(double) * WS_PPT * WS_TEAMS * WS_NS * 32 * WS_REC;
 constexpr size_t SM_NMV = SM_ARR + sizeof(int) * WM_NSP_MAX * WIN;
 constexpr size_t SM_BAR = (SM_NMV + sizeof(int) * WM_NSP_MAX * NQ + 7) / 8 * 8;
-constexpr size_t SM_TOTAL = SM_BAR + 8 * (1 + 2 * 2 * WS_TEAMS * WS_NS);
+constexpr size_t SM_TOTAL = SM_BAR + 8 * (1 + 2 * WS_PPT * WS_TEAMS * WS_NS);
 
 }  // namespace
 
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(FT, 1) k_fused_ws(const DevParams P, const Pas
   int *const s_nmv = reinterpret_cast<int *>(smem + SM_NMV);
   uint64_t *const s_bar = reinterpret_cast<uint64_t *>(smem + SM_BAR);        // TMA
   uint64_t *const s_full = s_bar + 1;                                          // [ring][slot]
-  uint64_t *const s_empty = s_full + 2 * WS_TEAMS * WS_NS;
+  uint64_t *const s_empty = s_full + WS_PPT * WS_TEAMS * WS_NS;
 
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(FT, 1) k_fused_ws(const DevParams P, const Pas
 
   if (tid == 0) {
     mbar_init(s_bar, 1);
-    for (int i = 0; i < 2 * WS_TEAMS * WS_NS; i++) {
+    for (int i = 0; i < WS_PPT * WS_TEAMS * WS_NS; i++) {
       mbar_init(&s_full[i], 32);
       mbar_init(&s_empty[i], 32);
     }
@@ -160,11 +161,14 @@ __global__ void __launch_bounds__(FT, 1) k_fused_ws(const DevParams P, const Pas
   const int wid = tid >> 5, lane = tid & 31;
   const int grp = lane >> 3, l8 = lane & 7;
 
-  if (wid < 2 * WS_TEAMS) {
+  if (wid < WS_PPT * WS_TEAMS) {
     // =====================================================================  PUSH warps
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R_PUSH));
     mbar_wait(s_bar, 0);
-    const int team = wid & (WS_TEAMS - 1), isp = wid / WS_TEAMS;
+    // work items of a team in order: (quad 0, species 0), (quad 0, species 1), (quad 1, species 0), ...;
+    // push warp j of the team takes items j, j + WS_PPT, ...: every item is one (quad, species), i.e. cell
+    // segments nobody else touches, so the in-place compaction needs no coordination between warps
+    const int team = wid & (WS_TEAMS - 1), pj = wid / WS_TEAMS;
     double *const ring = s_ring + (size_t)wid * WS_NS * 32 * WS_REC;
     uint64_t *const full = s_full + wid * WS_NS, *const empty = s_empty + wid * WS_NS;
     int bcount = 0;
@@ -174,14 +178,15 @@ __global__ void __launch_bounds__(FT, 1) k_fused_ws(const DevParams P, const Pas
     const double delt = P.delt, inv_cc = P.inv_cc, cc = P.cc;
     const double xlo = (double)P.nxgs, xhi = (double)(P.nxgs + P.nx);
     const double ylo = (double)P.nygs, yhi = (double)(P.nygs + P.ny);
-    if (isp < P.nsp) {
-      const size_t so = (size_t)isp * P.cap;
-      const double qs = P.q[isp];
-      // particle.f90:90-92
-      const double fac1 = qs / P.r[isp] * 0.5 * delt;
-      const double txxx = fac1 * fac1;
-      const double fac2 = qs * delt / P.r[isp];
-      for (int q = team; q < NQ; q += WS_TEAMS) {
+    {
+      for (int item = pj; item < (NQ / WS_TEAMS) * P.nsp; item += WS_PPT) {
+        const int isp = item % P.nsp, q = team + (item / P.nsp) * WS_TEAMS;
+        const size_t so = (size_t)isp * P.cap;
+        const double qs = P.q[isp];
+        // particle.f90:90-92
+        const double fac1 = qs / P.r[isp] * 0.5 * delt;
+        const double txxx = fac1 * fac1;
+        const double fac2 = qs * delt / P.r[isp];
         const int cy = q / QX, cx = (q - cy * QX) * 4 + grp;
         const bool valid = (cx < tw) && (cy < th);
         const int cell = (lj0 + cy) * P.nx + (li0 + cx);
@@ -416,10 +421,11 @@ __global__ void __launch_bounds__(FT, 1) k_fused_ws(const DevParams P, const Pas
   } else {
     // =====================================================================  DEPOSIT warps
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R_DEP));
-    const int team = wid - 2 * WS_TEAMS;
+    const int team = wid - WS_PPT * WS_TEAMS;
     const double qf_base = P.delx / P.delt;
-    int cb0 = 0, cb1 = 0;  // batches consumed from the ring of species 0 / 1
-    for (int q = team; q < NQ; q += WS_TEAMS) {
+    int cbr0 = 0, cbr1 = 0, cbr2 = 0;  // batches consumed from the rings of the team's push warps
+    for (int qi = 0; qi < NQ / WS_TEAMS; qi++) {
+      const int q = team + qi * WS_TEAMS;
       const int cy = q / QX, cx = (q - cy * QX) * 4 + grp;
       const bool valid = (cx < tw) && (cy < th);
       const int cell = (lj0 + cy) * P.nx + (li0 + cx);
@@ -443,15 +449,16 @@ __global__ void __launch_bounds__(FT, 1) k_fused_ws(const DevParams P, const Pas
 #pragma unroll 1
         for (int isp = 0; isp < 2; isp++) {
           if (k >= (isp ? nb1 : nb0)) continue;
-          const int r = isp * WS_TEAMS + team;
-          const int cb = isp ? cb1 : cb0;
+          const int pj = (qi * P.nsp + isp) % WS_PPT;  // the push warp that owns this (quad, species)
+          const int r = pj * WS_TEAMS + team;
+          const int cb = pj == 0 ? cbr0 : (pj == 1 ? cbr1 : cbr2);
           const int slot = cb % WS_NS;
           mbar_wait(&s_full[r * WS_NS + slot], (cb / WS_NS) & 1);
           const bool active = l8 + 8 * k < (isp ? n1 : n0);
           const double2 *rr = reinterpret_cast<const double2 *>(s_ring + (((size_t)r * WS_NS + slot) * 32 + lane) * WS_REC);
           const double2 r0 = rr[0], r1 = rr[1], r2 = rr[2];
           mbar_arrive(&s_empty[r * WS_NS + slot]);
-          if (isp) cb1++; else cb0++;
+          if (pj == 0) cbr0++; else if (pj == 1) cbr1++; else cbr2++;
           if (active) {
             const double hx = r0.x, hy = r0.y, d2x = r1.x, d2y = r1.y, qvz = r2.x;
             const long long fl = __double_as_longlong(r2.y);
