@@ -1,4 +1,4 @@
-// fused_kernel.cu -- the production particle pass of wm_step on sm_100a.
+// fused4_kernel.cu -- k_fused<INPLACE> with the deposit software-pipelined one iteration behind the push.
 //
 //  k_fused : particle__solv (common/particle.f90:83-169) + ele_cur (common/field.f90:189-316)
 //            + bc__particle_x/_y (common/boundary_periodic.f90:61-248) + the destination-cell
@@ -34,7 +34,7 @@ namespace wm {
 
 namespace {
 
-constexpr int FT_DEFAULT = 128;  // threads per CTA of the production configuration
+constexpr int PT = 128;  // threads per CTA
 constexpr int QX = TX / 4;       // quads per tile row
 constexpr int NQ = QX * TY;      // quads per tile
 
@@ -106,21 +106,87 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                : "memory");
 }
 
+// Esirkepov density decomposition of one particle into the cell's register-resident 4x5 + 5x4 + 5x5
+// block (field.f90:224-298), from its old offset (hx, hy) in the sorted cell, its new offset (d2x, d2y)
+// in the cell it ends up in, and the four "left / right neighbour cell" flags.  qf = q*delx/delt,
+// qvz = q*vz; both zero for a lane without particle (then every term is zero).
+__device__ __forceinline__ void esirkepov_acc(double (&acc)[65], double hx, double hy, double d2x, double d2y, bool xl,
+                                      bool xr, bool yl, bool yr, double qf, double qvz) {
+  const double hx2 = hx * hx, hy2 = hy * hy;
+  const double ex = fma(0.5, hx2, 0.125), ey = fma(0.5, hy2, 0.125);
+  const double sxm = fma(-0.5, hx, ex), sx0 = 0.75 - hx2, sxp = fma(0.5, hx, ex);
+  const double sym = fma(-0.5, hy, ey), sy0 = 0.75 - hy2, syp = fma(0.5, hy, ey);
+  // ---- Esirkepov density decomposition, factorised               field.f90:224-298
+  //  Jx block = Cx (x) Ty, Jy block = Tx (x) Cy, Jz block = Tx (x) Uy + Hx (x) Vy
+  //  T = S0 + DS/2, H = S0/2 + DS/3, C = running sum of -q*dx/dt*DS
+  double dsx0, dsx1, dsx2, dsx3, dsx4, dsy0, dsy1, dsy2, dsy3, dsy4;
+  {
+    const double d2 = d2x;
+    const double d22 = d2 * d2, e2 = fma(0.5, d22, 0.125);
+    const double s1 = fma(-0.5, d2, e2), s2_ = 0.75 - d22, s3 = fma(0.5, d2, e2);
+    dsx0 = xl ? s1 : 0.0;
+    dsx1 = (xl ? s2_ : (xr ? 0.0 : s1)) - sxm;
+    dsx2 = (xl ? s3 : (xr ? s1 : s2_)) - sx0;
+    dsx3 = (xl ? 0.0 : (xr ? s2_ : s3)) - sxp;
+    dsx4 = xr ? s3 : 0.0;
+  }
+  {
+    const double d2 = d2y;
+    const double d22 = d2 * d2, e2 = fma(0.5, d22, 0.125);
+    const double s1 = fma(-0.5, d2, e2), s2_ = 0.75 - d22, s3 = fma(0.5, d2, e2);
+    dsy0 = yl ? s1 : 0.0;
+    dsy1 = (yl ? s2_ : (yr ? 0.0 : s1)) - sym;
+    dsy2 = (yl ? s3 : (yr ? s1 : s2_)) - sy0;
+    dsy3 = (yl ? 0.0 : (yr ? s2_ : s3)) - syp;
+    dsy4 = yr ? s3 : 0.0;
+  }
+  // Jx: acc[b*4 + q] += cxv[q]*ty[b]
+  {
+    const double ty0 = 0.5 * dsy0, ty1 = fma(0.5, dsy1, sym), ty2 = fma(0.5, dsy2, sy0), ty3 = fma(0.5, dsy3, syp),
+                 ty4 = 0.5 * dsy4;
+    const double c0 = -qf * dsx0, c1 = fma(-qf, dsx1, c0), c2 = fma(-qf, dsx2, c1), c3 = qf * dsx4;
+    acc[0] = fma(c0, ty0, acc[0]);   acc[1] = fma(c1, ty0, acc[1]);   acc[2] = fma(c2, ty0, acc[2]);   acc[3] = fma(c3, ty0, acc[3]);
+    acc[4] = fma(c0, ty1, acc[4]);   acc[5] = fma(c1, ty1, acc[5]);   acc[6] = fma(c2, ty1, acc[6]);   acc[7] = fma(c3, ty1, acc[7]);
+    acc[8] = fma(c0, ty2, acc[8]);   acc[9] = fma(c1, ty2, acc[9]);   acc[10] = fma(c2, ty2, acc[10]); acc[11] = fma(c3, ty2, acc[11]);
+    acc[12] = fma(c0, ty3, acc[12]); acc[13] = fma(c1, ty3, acc[13]); acc[14] = fma(c2, ty3, acc[14]); acc[15] = fma(c3, ty3, acc[15]);
+    acc[16] = fma(c0, ty4, acc[16]); acc[17] = fma(c1, ty4, acc[17]); acc[18] = fma(c2, ty4, acc[18]); acc[19] = fma(c3, ty4, acc[19]);
+  }
+  {
+    const double tx0 = 0.5 * dsx0, tx1 = fma(0.5, dsx1, sxm), tx2 = fma(0.5, dsx2, sx0), tx3 = fma(0.5, dsx3, sxp),
+                 tx4 = 0.5 * dsx4;
+    // Jy: acc[20 + b*5 + q] += tx[q]*cyv[b]
+    {
+      const double c0 = -qf * dsy0, c1 = fma(-qf, dsy1, c0), c2 = fma(-qf, dsy2, c1), c3 = qf * dsy4;
+      acc[20] = fma(tx0, c0, acc[20]); acc[21] = fma(tx1, c0, acc[21]); acc[22] = fma(tx2, c0, acc[22]); acc[23] = fma(tx3, c0, acc[23]); acc[24] = fma(tx4, c0, acc[24]);
+      acc[25] = fma(tx0, c1, acc[25]); acc[26] = fma(tx1, c1, acc[26]); acc[27] = fma(tx2, c1, acc[27]); acc[28] = fma(tx3, c1, acc[28]); acc[29] = fma(tx4, c1, acc[29]);
+      acc[30] = fma(tx0, c2, acc[30]); acc[31] = fma(tx1, c2, acc[31]); acc[32] = fma(tx2, c2, acc[32]); acc[33] = fma(tx3, c2, acc[33]); acc[34] = fma(tx4, c2, acc[34]);
+      acc[35] = fma(tx0, c3, acc[35]); acc[36] = fma(tx1, c3, acc[36]); acc[37] = fma(tx2, c3, acc[37]); acc[38] = fma(tx3, c3, acc[38]); acc[39] = fma(tx4, c3, acc[39]);
+    }
+    // Jz: acc[40 + b*5 + q] += tx[q]*uy[b] + hx[q]*vy[b]     (uy = 0 for b = 0, 4)
+    const double third = 1.0 / 3.0;
+    const double hx0 = third * dsx0, hx1 = fma(third, dsx1, 0.5 * sxm), hx2_ = fma(third, dsx2, 0.5 * sx0),
+                 hx3 = fma(third, dsx3, 0.5 * sxp), hx4 = third * dsx4;
+    const double uy1 = qvz * sym, uy2 = qvz * sy0, uy3 = qvz * syp;
+    const double vy0 = qvz * dsy0, vy1 = qvz * dsy1, vy2 = qvz * dsy2, vy3 = qvz * dsy3, vy4 = qvz * dsy4;
+    acc[40] = fma(hx0, vy0, acc[40]); acc[41] = fma(hx1, vy0, acc[41]); acc[42] = fma(hx2_, vy0, acc[42]); acc[43] = fma(hx3, vy0, acc[43]); acc[44] = fma(hx4, vy0, acc[44]);
+    acc[45] = fma(hx0, vy1, fma(tx0, uy1, acc[45])); acc[46] = fma(hx1, vy1, fma(tx1, uy1, acc[46])); acc[47] = fma(hx2_, vy1, fma(tx2, uy1, acc[47]));
+    acc[48] = fma(hx3, vy1, fma(tx3, uy1, acc[48])); acc[49] = fma(hx4, vy1, fma(tx4, uy1, acc[49]));
+    acc[50] = fma(hx0, vy2, fma(tx0, uy2, acc[50])); acc[51] = fma(hx1, vy2, fma(tx1, uy2, acc[51])); acc[52] = fma(hx2_, vy2, fma(tx2, uy2, acc[52]));
+    acc[53] = fma(hx3, vy2, fma(tx3, uy2, acc[53])); acc[54] = fma(hx4, vy2, fma(tx4, uy2, acc[54]));
+    acc[55] = fma(hx0, vy3, fma(tx0, uy3, acc[55])); acc[56] = fma(hx1, vy3, fma(tx1, uy3, acc[56])); acc[57] = fma(hx2_, vy3, fma(tx2, uy3, acc[57]));
+    acc[58] = fma(hx3, vy3, fma(tx3, uy3, acc[58])); acc[59] = fma(hx4, vy3, fma(tx4, uy3, acc[59]));
+    acc[60] = fma(hx0, vy4, acc[60]); acc[61] = fma(hx1, vy4, acc[61]); acc[62] = fma(hx2_, vy4, acc[62]); acc[63] = fma(hx3, vy4, acc[63]); acc[64] = fma(hx4, vy4, acc[64]);
+  }
+        }
+
 }  // namespace
 
-// INPLACE = false: every particle gets a sort tag and k_pass2 scatters the whole store afterwards.
-// INPLACE = true : the sort only moves the particles that change cell.  Stayers are compacted to the
-//                  front of their own segment as they are written back (slot = running stayer count +
-//                  popc(ballot below me); never ahead of a slot that is still to be read).  A cell
-//                  changer is staged, ranked by a warp ballot, in the shadow of its quad in the idle
-//                  store (a.dst) with a tag (window cell, rank); k_place appends the staged records to
-//                  their new segments, k_mark_dead retires the vacated slots.  No scatter pass, no
-//                  per-particle tag, no global atomics in the particle loop.
+// Same data flow as k_fused<INPLACE> (fused_kernel.cu); see the comments (A)/(B) in the particle loop.
 // FT threads per CTA, MINB resident CTAs per SM: (128, 2) = 8 warps/SM at 255 registers.  CTAs of 96 or
 // 64 threads do not buy occupancy: registers are allocated per 4 warps, ptxas then caps at 168 and spills.
-template <bool INPLACE, int FT, int MINB>
-__global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pass1Args a) {
-  constexpr int FW = FT / 32;  // warps per CTA
+__global__ void __launch_bounds__(PT, 2) k_fused_pipe(const DevParams P, const Pass1Args a) {
+  constexpr bool INPLACE = true;
+  constexpr int FT = PT, FW = PT / 32;
   __shared__ __align__(128) double s_f[WINY * WINX * 6];
   __shared__ __align__(16) double s_j[3 * JY * JX];
   __shared__ int s_stay[WM_NSP_MAX * TX * TY];
@@ -173,19 +239,16 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
     double acc[65];
 #pragma unroll
     for (int e = 0; e < 65; e++) acc[e] = 0.0;
+    // deposit inputs of the previous iteration (software pipeline across iterations and species)
+    double p_hx = 0.0, p_hy = 0.0, p_d2x = 0.0, p_d2y = 0.0, p_qf = 0.0, p_qvz = 0.0;
+    bool p_xl = false, p_xr = false, p_yl = false, p_yr = false;
 
-    // segment bounds of both species at once: one memory round trip per quad instead of one per species
-    int beg0 = 0, cnt0 = 0, beg1 = 0, cnt1 = 0;
-    if (valid) {
-      beg0 = a.cstart[cell];
-      cnt0 = a.cnt[cell];
-      if (P.nsp > 1) {
-        beg1 = a.cstart[(size_t)(P.ncell + 1) + cell];
-        cnt1 = a.cnt[(size_t)P.ncell + cell];
-      }
-    }
     for (int isp = 0; isp < P.nsp; isp++) {
-      const int beg = isp ? beg1 : beg0, end = beg + (isp ? cnt1 : cnt0);
+      int beg = 0, end = 0;
+      if (valid) {
+        beg = a.cstart[(size_t)isp * (P.ncell + 1) + cell];
+        end = beg + a.cnt[(size_t)isp * P.ncell + cell];
+      }
       int nmax = end - beg;
       nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));
       nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
@@ -233,9 +296,12 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
           if (INPLACE) nid = b[5 * cstride];  // the id moves with the record (bit pattern)
         }
         bool stay = false;
-        int incx = 0, incy = 0;  // new cell - old cell, from the same comparisons the deposit uses
         double xn = 0.0, yn = 0.0, un1 = 0.0, un2 = 0.0, un3 = 0.0;
-        if (active) {
+        // (A) push of this lane's particle.  Unconditional straight-line code (a lane without particle runs
+        //     on zeros and is masked below), so that the scheduler can interleave it with (B).
+        double c_hx, c_hy, c_d2x, c_d2y, c_qvz, c_qf;
+        bool c_xl, c_xr, c_yl, c_yr;
+        {
           // ---- second order shape function about the sorted cell       particle.f90:97-105
           const double hx = x - cxh, hy = y - cyh;
           const double hx2 = hx * hx, hy2 = hy * hy;
@@ -283,80 +349,22 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
           const double dtw = delt * wmove;
           xn = fma(un1, dtw, x);
           yn = fma(un2, dtw, y);
-          if (!INPLACE) {
-            double *b = px + so + pc;
-            b[2 * cstride] = un1;
-            b[3 * cstride] = un2;
-            b[4 * cstride] = un3;
-          }
-          // ---- new cell relative to the old one (int() truncation == floor: positions > 0)
-          const bool xl = xn < di, xr = xn >= di1, yl = yn < dj, yr = yn >= dj1;
-          stay = !(xl | xr | yl | yr);
-          incx = (int)xr - (int)xl;
-          incy = (int)yr - (int)yl;
-          // ---- Esirkepov density decomposition, factorised               field.f90:224-298
-          //  Jx block = Cx (x) Ty, Jy block = Tx (x) Cy, Jz block = Tx (x) Uy + Hx (x) Vy
-          //  T = S0 + DS/2, H = S0/2 + DS/3, C = running sum of -q*dx/dt*DS
-          double dsx0, dsx1, dsx2, dsx3, dsx4, dsy0, dsy1, dsy2, dsy3, dsy4;
-          {
-            const double d2 = xn - (xl ? cxh - 1.0 : (xr ? cxh + 1.0 : cxh));
-            const double d22 = d2 * d2, e2 = fma(0.5, d22, 0.125);
-            const double s1 = fma(-0.5, d2, e2), s2_ = 0.75 - d22, s3 = fma(0.5, d2, e2);
-            dsx0 = xl ? s1 : 0.0;
-            dsx1 = (xl ? s2_ : (xr ? 0.0 : s1)) - sxm;
-            dsx2 = (xl ? s3 : (xr ? s1 : s2_)) - sx0;
-            dsx3 = (xl ? 0.0 : (xr ? s2_ : s3)) - sxp;
-            dsx4 = xr ? s3 : 0.0;
-          }
-          {
-            const double d2 = yn - (yl ? cyh - 1.0 : (yr ? cyh + 1.0 : cyh));
-            const double d22 = d2 * d2, e2 = fma(0.5, d22, 0.125);
-            const double s1 = fma(-0.5, d2, e2), s2_ = 0.75 - d22, s3 = fma(0.5, d2, e2);
-            dsy0 = yl ? s1 : 0.0;
-            dsy1 = (yl ? s2_ : (yr ? 0.0 : s1)) - sym;
-            dsy2 = (yl ? s3 : (yr ? s1 : s2_)) - sy0;
-            dsy3 = (yl ? 0.0 : (yr ? s2_ : s3)) - syp;
-            dsy4 = yr ? s3 : 0.0;
-          }
-          // Jx: acc[b*4 + q] += cxv[q]*ty[b]
-          {
-            const double ty0 = 0.5 * dsy0, ty1 = fma(0.5, dsy1, sym), ty2 = fma(0.5, dsy2, sy0), ty3 = fma(0.5, dsy3, syp),
-                         ty4 = 0.5 * dsy4;
-            const double c0 = -qf * dsx0, c1 = fma(-qf, dsx1, c0), c2 = fma(-qf, dsx2, c1), c3 = qf * dsx4;
-            acc[0] = fma(c0, ty0, acc[0]);   acc[1] = fma(c1, ty0, acc[1]);   acc[2] = fma(c2, ty0, acc[2]);   acc[3] = fma(c3, ty0, acc[3]);
-            acc[4] = fma(c0, ty1, acc[4]);   acc[5] = fma(c1, ty1, acc[5]);   acc[6] = fma(c2, ty1, acc[6]);   acc[7] = fma(c3, ty1, acc[7]);
-            acc[8] = fma(c0, ty2, acc[8]);   acc[9] = fma(c1, ty2, acc[9]);   acc[10] = fma(c2, ty2, acc[10]); acc[11] = fma(c3, ty2, acc[11]);
-            acc[12] = fma(c0, ty3, acc[12]); acc[13] = fma(c1, ty3, acc[13]); acc[14] = fma(c2, ty3, acc[14]); acc[15] = fma(c3, ty3, acc[15]);
-            acc[16] = fma(c0, ty4, acc[16]); acc[17] = fma(c1, ty4, acc[17]); acc[18] = fma(c2, ty4, acc[18]); acc[19] = fma(c3, ty4, acc[19]);
-          }
-          {
-            const double tx0 = 0.5 * dsx0, tx1 = fma(0.5, dsx1, sxm), tx2 = fma(0.5, dsx2, sx0), tx3 = fma(0.5, dsx3, sxp),
-                         tx4 = 0.5 * dsx4;
-            // Jy: acc[20 + b*5 + q] += tx[q]*cyv[b]
-            {
-              const double c0 = -qf * dsy0, c1 = fma(-qf, dsy1, c0), c2 = fma(-qf, dsy2, c1), c3 = qf * dsy4;
-              acc[20] = fma(tx0, c0, acc[20]); acc[21] = fma(tx1, c0, acc[21]); acc[22] = fma(tx2, c0, acc[22]); acc[23] = fma(tx3, c0, acc[23]); acc[24] = fma(tx4, c0, acc[24]);
-              acc[25] = fma(tx0, c1, acc[25]); acc[26] = fma(tx1, c1, acc[26]); acc[27] = fma(tx2, c1, acc[27]); acc[28] = fma(tx3, c1, acc[28]); acc[29] = fma(tx4, c1, acc[29]);
-              acc[30] = fma(tx0, c2, acc[30]); acc[31] = fma(tx1, c2, acc[31]); acc[32] = fma(tx2, c2, acc[32]); acc[33] = fma(tx3, c2, acc[33]); acc[34] = fma(tx4, c2, acc[34]);
-              acc[35] = fma(tx0, c3, acc[35]); acc[36] = fma(tx1, c3, acc[36]); acc[37] = fma(tx2, c3, acc[37]); acc[38] = fma(tx3, c3, acc[38]); acc[39] = fma(tx4, c3, acc[39]);
-            }
-            // Jz: acc[40 + b*5 + q] += tx[q]*uy[b] + hx[q]*vy[b]     (uy = 0 for b = 0, 4)
-            const double third = 1.0 / 3.0;
-            const double qvz = qs * (un3 * wmove);  // q*gvz, field.f90:270-272,295
-            const double hx0 = third * dsx0, hx1 = fma(third, dsx1, 0.5 * sxm), hx2_ = fma(third, dsx2, 0.5 * sx0),
-                         hx3 = fma(third, dsx3, 0.5 * sxp), hx4 = third * dsx4;
-            const double uy1 = qvz * sym, uy2 = qvz * sy0, uy3 = qvz * syp;
-            const double vy0 = qvz * dsy0, vy1 = qvz * dsy1, vy2 = qvz * dsy2, vy3 = qvz * dsy3, vy4 = qvz * dsy4;
-            acc[40] = fma(hx0, vy0, acc[40]); acc[41] = fma(hx1, vy0, acc[41]); acc[42] = fma(hx2_, vy0, acc[42]); acc[43] = fma(hx3, vy0, acc[43]); acc[44] = fma(hx4, vy0, acc[44]);
-            acc[45] = fma(hx0, vy1, fma(tx0, uy1, acc[45])); acc[46] = fma(hx1, vy1, fma(tx1, uy1, acc[46])); acc[47] = fma(hx2_, vy1, fma(tx2, uy1, acc[47]));
-            acc[48] = fma(hx3, vy1, fma(tx3, uy1, acc[48])); acc[49] = fma(hx4, vy1, fma(tx4, uy1, acc[49]));
-            acc[50] = fma(hx0, vy2, fma(tx0, uy2, acc[50])); acc[51] = fma(hx1, vy2, fma(tx1, uy2, acc[51])); acc[52] = fma(hx2_, vy2, fma(tx2, uy2, acc[52]));
-            acc[53] = fma(hx3, vy2, fma(tx3, uy2, acc[53])); acc[54] = fma(hx4, vy2, fma(tx4, uy2, acc[54]));
-            acc[55] = fma(hx0, vy3, fma(tx0, uy3, acc[55])); acc[56] = fma(hx1, vy3, fma(tx1, uy3, acc[56])); acc[57] = fma(hx2_, vy3, fma(tx2, uy3, acc[57]));
-            acc[58] = fma(hx3, vy3, fma(tx3, uy3, acc[58])); acc[59] = fma(hx4, vy3, fma(tx4, uy3, acc[59]));
-            acc[60] = fma(hx0, vy4, acc[60]); acc[61] = fma(hx1, vy4, acc[61]); acc[62] = fma(hx2_, vy4, acc[62]); acc[63] = fma(hx3, vy4, acc[63]); acc[64] = fma(hx4, vy4, acc[64]);
-          }
+          c_xl = xn < di; c_xr = xn >= di1; c_yl = yn < dj; c_yr = yn >= dj1;
+          stay = active && !(c_xl | c_xr | c_yl | c_yr);
+          // a lane without particle may have pushed garbage (partial tiles leave part of the field tile
+          // unloaded): all its deposit inputs are forced to zero, so every term of (B) is exactly zero
+          c_hx = active ? hx : 0.0;
+          c_hy = active ? hy : 0.0;
+          c_d2x = active ? xn - (c_xl ? cxh - 1.0 : (c_xr ? cxh + 1.0 : cxh)) : 0.0;
+          c_d2y = active ? yn - (c_yl ? cyh - 1.0 : (c_yr ? cyh + 1.0 : cyh)) : 0.0;
+          c_qvz = active ? qs * (un3 * wmove) : 0.0;  // q*gvz, field.f90:270-272,295
+          c_qf = active ? qf : 0.0;
         }
+        // (B) deposit of the particle this lane pushed one iteration ago: 80 independent DFMA that
+        //     fill the latency bubbles of the serial Boris chain above
+        esirkepov_acc(acc, p_hx, p_hy, p_d2x, p_d2y, p_xl, p_xr, p_yl, p_yr, p_qf, p_qvz);
+        p_hx = c_hx; p_hy = c_hy; p_d2x = c_d2x; p_d2y = c_d2y; p_qf = c_qf; p_qvz = c_qvz;
+        p_xl = c_xl; p_xr = c_xr; p_yl = c_yl; p_yr = c_yr;
         // ---- reflecting x walls (after the deposit, which uses the position before the boundary)
         //      proj/reconnection/boundary_reconnection.f90:61-99
         if (P.bc != WM_BC_PERIODIC && active) {
@@ -378,41 +386,48 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
               b[3 * cstride] = un2;
               b[4 * cstride] = un3;
             }
-            incx = (int)(xn >= di1) - (int)(xn < di);
-            stay = (incx | incy) == 0;
+            stay = !(xn < di || xn >= di1 || yn < dj || yn >= dj1);
           }
         }
         // ---- sort bookkeeping                                             sort.f90:57-62
-        if constexpr (INPLACE) {
-          const unsigned bal = __ballot_sync(0xffffffffu, stay);
-          const unsigned balm = __ballot_sync(0xffffffffu, active && !stay);  // changers + leavers
+        const unsigned bal = __ballot_sync(0xffffffffu, stay);
+        const unsigned balm = INPLACE ? __ballot_sync(0xffffffffu, active && !stay) : 0u;  // changers + leavers
+        if (active) {
           const unsigned m8 = (bal >> (grp * 8)) & 0xffu;
+          const int srank = nst + __popc(m8 & below);  // my rank among the stayers of this cell
+          uint32_t tg;
           if (stay) {
-            // stable compaction inside the segment: slot beg + rank among the stayers <= pc
-            const int ns = beg + nst + __popc(m8 & below);
-            double *d = px + so + ns;
-            d[0] = xn;
-            d[cstride] = yn;
-            d[2 * cstride] = un1;
-            d[3 * cstride] = un2;
-            d[4 * cstride] = un3;
-            if (ns != pc) d[5 * cstride] = idc;
-          } else if (active) {
-            // cell changer.  |move| < 1 cell (CFL), so the new cell is (gi + incx, gj + incy); anything else
-            // is an error (also catches NaN)
-            if (!(fabs(xn - cxh) < 1.5 && fabs(yn - cyh) < 1.5)) atomicOr(a.err, ERR_MOVED_TOO_FAR);
-            // periodic wraps with round-toward -inf adds   boundary_periodic.f90:74,82-88,124,147-154
-            const int gi2 = gi + incx, j2 = gj + incy;  // unwrapped destination cell
-            if (gi2 < P.nxgs)
+            tg = ((uint32_t)((cy + 1) * WINX + (cx + 1)) << TAG_WSHIFT) | (uint32_t)srank;
+            if (INPLACE) {
+              // stable compaction inside the segment: slot beg + srank <= pc
+              double *d = px + so + beg + srank;
+              d[0] = xn;
+              d[cstride] = yn;
+              d[2 * cstride] = un1;
+              d[3 * cstride] = un2;
+              d[4 * cstride] = un3;
+              if (beg + srank != pc) d[5 * cstride] = idc;
+            }
+          } else {
+            // cell changers: periodic wraps with round-toward -inf adds  boundary_periodic.f90:74,82-88,124,147-154
+            int incx = (xn >= di1) - (xn < di), incy = (yn >= dj1) - (yn < dj);
+            if (!(xn >= di - 1.0 && xn < di1 + 1.0 && yn >= dj - 1.0 && yn < dj1 + 1.0)) {
+              atomicOr(a.err, ERR_MOVED_TOO_FAR);  // also catches NaN
+              incx = (xn >= di1) ? 1 : ((xn < di) ? -1 : 0);
+              incy = (yn >= dj1) ? 1 : ((yn < dj) ? -1 : 0);
+            }
+            const int j2 = gj + incy;  // unwrapped destination row
+            if (xn < xlo)
               xn = __dadd_rd(xn, P.xlen);
-            else if (gi2 >= P.nxgs + P.nx)
+            else if (xn >= xhi)
               xn = __dadd_rd(xn, -P.xlen);
-            if (j2 < P.nygs)
+            if (yn < ylo)
               yn = __dadd_rd(yn, P.ylen);
-            else if (j2 >= P.nygs + P.ny)
+            else if (yn >= yhi)
               yn = __dadd_rd(yn, -P.ylen);
-            uint32_t tg;
-            if (P.nsize > 1 && (j2 < P.nys || j2 >= P.nys + P.nyl)) {
+            const bool leaves = (P.nsize > 1) && (j2 < P.nys || j2 >= P.nys + P.nyl);
+            const double idv = INPLACE ? idc : (leaves ? px[so + pc + 5 * cstride] : 0.0);  // id, bit pattern
+            if (leaves) {
               // record goes to the neighbour's edge row        boundary_periodic.f90:156-161,174-189
               const int dir = (j2 < P.nys) ? 0 : 1;
               const int pos = atomicAdd(&a.sendcnt[dir * P.nsp + isp], 1);
@@ -423,115 +438,41 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
                 rec[2] = un1;
                 rec[3] = un2;
                 rec[4] = un3;
-                rec[5] = idc;
+                rec[5] = idv;
               } else {
                 atomicOr(a.err, ERR_SENDBUF);
               }
               tg = TAG_DEAD;
             } else {
               const int w = (cy + 1 + incy) * WINX + (cx + 1 + incx);
-              tg = TAG_ARRIVAL | ((uint32_t)w << TAG_WSHIFT) | (uint32_t)atomicAdd(&s_arr[isp * WIN + w], 1);
+              const int rk = atomicAdd(&s_arr[isp * WIN + w], 1);
+              tg = TAG_ARRIVAL | ((uint32_t)w << TAG_WSHIFT) | (uint32_t)rk;
             }
-            // stage the record (64 B: x y | ux uy | uz id | tag -) in the idle store, in the shadow of
-            // this quad; slot order = ballot rank, so the stores of a warp are contiguous
-            const int sk = nmv + __popc(balm & ((1u << lane) - 1u));
-            if (sk < qcap) {
-              double2 *d = reinterpret_cast<double2 *>(a.dst.x) + (size_t)(qrec + sk) * 4;
-              d[0] = make_double2(xn, yn);
-              d[1] = make_double2(un1, un2);
-              d[2] = make_double2(un3, idc);
-              d[3] = make_double2(__longlong_as_double((long long)tg), 0.0);
-            } else {
-              atomicOr(a.err, ERR_OVERFLOW);
+            if (INPLACE) {
+              // stage the record (64 B: x y | ux uy | uz id | tag -) in the idle store, in the shadow of
+              // this quad; slot order = ballot rank, so the stores of a warp are contiguous
+              const int sk = nmv + __popc(balm & ((1u << lane) - 1u));
+              if (sk < qcap) {
+                double2 *d = reinterpret_cast<double2 *>(a.dst.x) + (size_t)(qrec + sk) * 4;
+                d[0] = make_double2(xn, yn);
+                d[1] = make_double2(un1, un2);
+                d[2] = make_double2(un3, idv);
+                d[3] = make_double2(__longlong_as_double((long long)tg), 0.0);
+              } else {
+                atomicOr(a.err, ERR_OVERFLOW);
+              }
             }
+          }
+          if (!INPLACE) {
+            double *b = px + so + pc;
+            b[0] = xn;
+            b[cstride] = yn;
+            a.tag[so + pc] = tg;
           }
           nst += __popc(m8);
-          nmv += __popc(balm);
-        } else {
-          const unsigned bal = __ballot_sync(0xffffffffu, stay);
-          const unsigned balm = INPLACE ? __ballot_sync(0xffffffffu, active && !stay) : 0u;  // changers + leavers
-          if (active) {
-            const unsigned m8 = (bal >> (grp * 8)) & 0xffu;
-            const int srank = nst + __popc(m8 & below);  // my rank among the stayers of this cell
-            uint32_t tg;
-            if (stay) {
-              tg = ((uint32_t)((cy + 1) * WINX + (cx + 1)) << TAG_WSHIFT) | (uint32_t)srank;
-              if (INPLACE) {
-                // stable compaction inside the segment: slot beg + srank <= pc
-                double *d = px + so + beg + srank;
-                d[0] = xn;
-                d[cstride] = yn;
-                d[2 * cstride] = un1;
-                d[3 * cstride] = un2;
-                d[4 * cstride] = un3;
-                if (beg + srank != pc) d[5 * cstride] = idc;
-              }
-            } else {
-              // cell changers: periodic wraps with round-toward -inf adds  boundary_periodic.f90:74,82-88,124,147-154
-              int incx = (xn >= di1) - (xn < di), incy = (yn >= dj1) - (yn < dj);
-              if (!(xn >= di - 1.0 && xn < di1 + 1.0 && yn >= dj - 1.0 && yn < dj1 + 1.0)) {
-                atomicOr(a.err, ERR_MOVED_TOO_FAR);  // also catches NaN
-                incx = (xn >= di1) ? 1 : ((xn < di) ? -1 : 0);
-                incy = (yn >= dj1) ? 1 : ((yn < dj) ? -1 : 0);
-              }
-              const int j2 = gj + incy;  // unwrapped destination row
-              if (xn < xlo)
-                xn = __dadd_rd(xn, P.xlen);
-              else if (xn >= xhi)
-                xn = __dadd_rd(xn, -P.xlen);
-              if (yn < ylo)
-                yn = __dadd_rd(yn, P.ylen);
-              else if (yn >= yhi)
-                yn = __dadd_rd(yn, -P.ylen);
-              const bool leaves = (P.nsize > 1) && (j2 < P.nys || j2 >= P.nys + P.nyl);
-              const double idv = INPLACE ? idc : (leaves ? px[so + pc + 5 * cstride] : 0.0);  // id, bit pattern
-              if (leaves) {
-                // record goes to the neighbour's edge row        boundary_periodic.f90:156-161,174-189
-                const int dir = (j2 < P.nys) ? 0 : 1;
-                const int pos = atomicAdd(&a.sendcnt[dir * P.nsp + isp], 1);
-                if (pos < a.sendcap) {
-                  double *rec = a.send[dir] + ((size_t)isp * a.sendcap + pos) * 6;
-                  rec[0] = xn;
-                  rec[1] = yn;
-                  rec[2] = un1;
-                  rec[3] = un2;
-                  rec[4] = un3;
-                  rec[5] = idv;
-                } else {
-                  atomicOr(a.err, ERR_SENDBUF);
-                }
-                tg = TAG_DEAD;
-              } else {
-                const int w = (cy + 1 + incy) * WINX + (cx + 1 + incx);
-                const int rk = atomicAdd(&s_arr[isp * WIN + w], 1);
-                tg = TAG_ARRIVAL | ((uint32_t)w << TAG_WSHIFT) | (uint32_t)rk;
-              }
-              if (INPLACE) {
-                // stage the record (64 B: x y | ux uy | uz id | tag -) in the idle store, in the shadow of
-                // this quad; slot order = ballot rank, so the stores of a warp are contiguous
-                const int sk = nmv + __popc(balm & ((1u << lane) - 1u));
-                if (sk < qcap) {
-                  double2 *d = reinterpret_cast<double2 *>(a.dst.x) + (size_t)(qrec + sk) * 4;
-                  d[0] = make_double2(xn, yn);
-                  d[1] = make_double2(un1, un2);
-                  d[2] = make_double2(un3, idv);
-                  d[3] = make_double2(__longlong_as_double((long long)tg), 0.0);
-                } else {
-                  atomicOr(a.err, ERR_OVERFLOW);
-                }
-              }
-            }
-            if (!INPLACE) {
-              double *b = px + so + pc;
-              b[0] = xn;
-              b[cstride] = yn;
-              a.tag[so + pc] = tg;
-            }
-            nst += __popc(m8);
-          }
-          nmv += __popc(balm);
         }
-        }
+        nmv += __popc(balm);
+      }
       if (INPLACE) {
         if (valid && l8 == 0) a.cnt_tail[(size_t)isp * P.ncell + cell] = nst;  // arrivals are added by k_place
         if (lane == 0) s_nmv[isp * NQ + q] = nmv;
@@ -539,6 +480,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
       if (!INPLACE && valid && l8 == 0) s_stay[isp * (TX * TY) + cy * TX + cx] = nst;
     }
 
+    esirkepov_acc(acc, p_hx, p_hy, p_d2x, p_d2y, p_xl, p_xr, p_yl, p_yr, p_qf, p_qvz);  // drain the pipeline
     // ---- reduce-scatter the 65 partial sums over the 8 lanes of the cell   field.f90:304-310
     {
       const bool h4 = (l8 & 4) != 0, h2 = (l8 & 2) != 0, h1 = (l8 & 1) != 0;
@@ -620,11 +562,8 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
   }
 }
 
-void launch_fused(const DevParams &P, const Pass1Args &a, cudaStream_t st) {
-  k_fused<false, FT_DEFAULT, 2><<<P.ntx * P.nty, FT_DEFAULT, 0, st>>>(P, a);
-}
-void launch_fused_inplace(const DevParams &P, const Pass1Args &a, cudaStream_t st) {
-  k_fused<true, FT_DEFAULT, 2><<<P.ntx * P.nty, FT_DEFAULT, 0, st>>>(P, a);
+void launch_fused_pipe(const DevParams &P, const Pass1Args &a, cudaStream_t st) {
+  k_fused_pipe<<<P.ntx * P.nty, PT, 0, st>>>(P, a);
 }
 
 }  // namespace wm

@@ -44,6 +44,8 @@ void launch_mark_dead(const DevParams &P, double *x, const int *cstart, const in
 void launch_fused_inplace(const DevParams &P, const Pass1Args &a, cudaStream_t st);
 // the same, warp-specialised: push warps and deposit warps with different register budgets (fused3_kernel.cu)
 void launch_fused_ws(const DevParams &P, const Pass1Args &a, cudaStream_t st);
+// k_fused<INPLACE> with the deposit of particle k interleaved with the push of particle k+1 (fused4_kernel.cu)
+void launch_fused_pipe(const DevParams &P, const Pass1Args &a, cudaStream_t st);
 void launch_kinetic(const DevParams &P, const PartSoA &src, const int *cstart, int isp, double *partial, int nblocks,
                     cudaStream_t st);
 void launch_moments(const DevParams &P, const PartSoA &src, const double *keyx, const int *cstart, double *mom,
