@@ -46,6 +46,8 @@ void launch_fused_inplace(const DevParams &P, const Pass1Args &a, cudaStream_t s
 void launch_fused_ws(const DevParams &P, const Pass1Args &a, cudaStream_t st);
 // k_fused<INPLACE> with the deposit of particle k interleaved with the push of particle k+1 (fused4_kernel.cu)
 void launch_fused_pipe(const DevParams &P, const Pass1Args &a, cudaStream_t st);
+// k_fused<INPLACE> with the deposit split into stayers (21 sums, in the loop) and movers (queued, drained per cell) (fused5_kernel.cu)
+void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaStream_t st);
 void launch_kinetic(const DevParams &P, const PartSoA &src, const int *cstart, int isp, double *partial, int nblocks,
                     cudaStream_t st);
 void launch_moments(const DevParams &P, const PartSoA &src, const double *keyx, const int *cstart, double *mom,

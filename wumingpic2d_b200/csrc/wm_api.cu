@@ -70,6 +70,7 @@ struct wm_ctx {
   int ovfcap = 0;
   float slack = 6.0f;                    // segment slack in std deviations of the count change (WM_SLACK)
   bool inplace = true;                   // WM_INPLACE=0 selects the tag + scatter sort for wm_step
+  int sm = 1;                            // stayer/mover split deposit (k_fused_sm); WM_SM=0 selects k_fused<INPLACE>
   bool pipe = false;                     // WM_PIPE=1: software-pipelined deposit (k_fused_pipe)
   bool ws = false;                       // WM_WS=1 selects the warp-specialised k_fused_ws (slower so far: profiles/r01h)
   long long rebuilds = 0;
@@ -462,6 +463,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   if (const char *v = getenv("WM_INPLACE")) c->inplace = atoi(v) != 0;
   if (const char *v = getenv("WM_WS")) c->ws = atoi(v) != 0;
   if (const char *v = getenv("WM_PIPE")) c->pipe = atoi(v) != 0;
+  if (const char *v = getenv("WM_SM")) c->sm = atoi(v);
   if (g->flags & WM_FLAG_EXACT_PUSH) c->inplace = false;  // the exact path keeps the reference's two-pass structure
   if (g->bc != WM_BC_PERIODIC) c->fused_variant = 1;      // k_fused2 has no wall reflection
   if (g->device >= 0) {
@@ -978,6 +980,8 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
       launch_pass1(mode, P, p1args(c, a, a, P.delt), c->st);
     else if (inplace && c->ws)
       launch_fused_ws(P, p1args(c, a, c->soa[c->cur ^ 1], P.delt), c->st);       // idle store = staging of the cell changers
+    else if (inplace && c->sm)
+      launch_fused_sm(P, p1args(c, a, c->soa[c->cur ^ 1], P.delt), c->sm, c->st);
     else if (inplace && c->pipe)
       launch_fused_pipe(P, p1args(c, a, c->soa[c->cur ^ 1], P.delt), c->st);
     else if (inplace)
