@@ -16,8 +16,8 @@
 //     block (the 21 stayer sums are the start values of their entries), reduce-scatter it with shuffles and add
 //     it once to the shared-memory current tile, as before.
 //  The loop body is ~130 instructions shorter per particle and needs 88 fewer registers: 3 CTAs (12 warps) per
-//  SM instead of 2.  A queue that fills up mid-cell (more than QCAP movers per cell) falls back to a slow path
-//  (shared-memory atomics from the mover's lane), so any density is handled correctly.
+//  SM instead of 2.  A queue that could fill up mid-cell (more than QCAP - 8 movers in a cell) is drained early and
+//  the particle loop re-entered, so any density is handled correctly.
 #include <cstdint>
 #include <cstdlib>
 
@@ -134,41 +134,51 @@ __device__ __forceinline__ void ds5(double dn, double sm, double s0, double sp, 
   d4 = r ? t3 : 0.0;
 }
 
-// Slow path: a mover whose cell queue is full adds its block straight to the current tile (shared-memory
-// atomics, 65 of them).  Never taken at the benchmark densities; keeps any density correct.
-__device__ __noinline__ void deposit_mover_slow(double *sj0, double hx, double hy, double dxn, double dyn, double qvz, double qf) {
-  double sx[3], sy[3], dx[5], dy[5];
-  shape3(hx, sx[0], sx[1], sx[2]);
-  shape3(hy, sy[0], sy[1], sy[2]);
-  ds5(dxn, sx[0], sx[1], sx[2], dx[0], dx[1], dx[2], dx[3], dx[4]);
-  ds5(dyn, sy[0], sy[1], sy[2], dy[0], dy[1], dy[2], dy[3], dy[4]);
-  double s0x[5] = {0.0, sx[0], sx[1], sx[2], 0.0}, s0y[5] = {0.0, sy[0], sy[1], sy[2], 0.0};
-  const double third = 1.0 / 3.0;
-  for (int b = 0; b < 5; b++) {
-    const double ty = fma(0.5, dy[b], s0y[b]);
-    double c = 0.0;
-    for (int q = 0; q < 4; q++) {
-      c = fma(-qf, dx[q], c);
-      const double v = c * ty;
-      if (v != 0.0) atomicAdd(sj0 + c_joff5.v[b * 4 + q], v);
-    }
+// weights of a queued mover: old shape function, DS of both directions, q*vz, q*dx/dt
+struct MoverW {
+  double sxm, sx0, sxp, sym, sy0, syp;
+  double dsx0, dsx1, dsx2, dsx3, dsx4, dsy0, dsy1, dsy2, dsy3, dsy4;
+  double qvz, qf;
+};
+__device__ __forceinline__ void mover_weights(const double2 *r, MoverW &w) {
+  const double2 r0 = r[0], r1 = r[1], r2 = r[2];
+  w.qvz = r2.x;
+  w.qf = r2.y;
+  shape3(r0.x, w.sxm, w.sx0, w.sxp);
+  shape3(r0.y, w.sym, w.sy0, w.syp);
+  ds5(r1.x, w.sxm, w.sx0, w.sxp, w.dsx0, w.dsx1, w.dsx2, w.dsx3, w.dsx4);
+  ds5(r1.y, w.sym, w.sy0, w.syp, w.dsy0, w.dsy1, w.dsy2, w.dsy3, w.dsy4);
+}
+
+// reduce-scatter NP (multiple of 8) partial sums over the 8 lanes of a cell with shuffles, then every lane adds
+// its NP/8 totals to the current tile; entry e < nvalid of v is entry ebase + e of the 65-sum block
+template <int NP>
+__device__ __forceinline__ void rs_add(double (&v)[NP], int l8, bool valid, double *sj0, int ebase, int nvalid) {
+  const bool h4 = (l8 & 4) != 0, h2 = (l8 & 2) != 0, h1 = (l8 & 1) != 0;
+#pragma unroll
+  for (int e = 0; e < NP / 2; e++) {
+    const double snd = h4 ? v[e] : v[e + NP / 2];
+    const double kp = h4 ? v[e + NP / 2] : v[e];
+    v[e] = kp + __shfl_xor_sync(0xffffffffu, snd, 4);
   }
-  {
-    double c = 0.0;
-    for (int b = 0; b < 4; b++) {
-      c = fma(-qf, dy[b], c);
-      for (int q = 0; q < 5; q++) {
-        const double v = fma(0.5, dx[q], s0x[q]) * c;
-        if (v != 0.0) atomicAdd(sj0 + c_joff5.v[20 + b * 5 + q], v);
-      }
-    }
+#pragma unroll
+  for (int e = 0; e < NP / 4; e++) {
+    const double snd = h2 ? v[e] : v[e + NP / 4];
+    const double kp = h2 ? v[e + NP / 4] : v[e];
+    v[e] = kp + __shfl_xor_sync(0xffffffffu, snd, 2);
   }
-  for (int b = 0; b < 5; b++)
-    for (int q = 0; q < 5; q++) {
-      const double tx = fma(0.5, dx[q], s0x[q]), hxq = fma(third, dx[q], 0.5 * s0x[q]);
-      const double v = fma(hxq, qvz * dy[b], tx * (qvz * s0y[b]));
-      if (v != 0.0) atomicAdd(sj0 + c_joff5.v[40 + b * 5 + q], v);
-    }
+#pragma unroll
+  for (int e = 0; e < NP / 8; e++) {
+    const double snd = h1 ? v[e] : v[e + NP / 8];
+    const double kp = h1 ? v[e + NP / 8] : v[e];
+    v[e] = kp + __shfl_xor_sync(0xffffffffu, snd, 1);
+  }
+  if (valid) {
+    const int i0 = (h4 ? NP / 2 : 0) + (h2 ? NP / 4 : 0) + (h1 ? NP / 8 : 0);
+#pragma unroll
+    for (int e = 0; e < NP / 8; e++)
+      if (i0 + e < nvalid && v[e] != 0.0) atomicAdd(sj0 + c_joff5.v[ebase + i0 + e], v[e]);
+  }
 }
 
 }  // namespace
@@ -238,10 +248,6 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
     const double *sf0 = &s_f[(cy * WINX + cx) * 6];
     double *const sj0 = &s_j[cy * JX + cx];
 
-    double sa[21];
-#pragma unroll
-    for (int e = 0; e < 21; e++) sa[e] = 0.0;
-    int qn = 0;  // movers queued for this cell
 
     // segment bounds of both species: loaded one quad ahead (nb*), so that the first particles of the next
     // quad can be prefetched while this one is being worked on
@@ -260,7 +266,20 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         }
       }
     }
-    for (int isp = 0; isp < P.nsp; isp++) {
+    // The cell is worked on in rounds: particle loop until both species are done or the mover queue of one of
+    // the quad's cells may overflow in the next iteration, then the drain.  One round per cell unless a cell has
+    // more than QCAP - 8 movers.  Across a drain only (isp, k0, nst, nmv) survive: the loop re-enters at
+    // iteration k0 of species isp and reloads its particle (a slot is never overwritten before it is read).
+    int isp = 0, k0 = 0;
+    int nst = 0;  // stayers of this (cell, species) so far
+    int nmv = 0;  // cell changers of this (quad, species) so far
+    do {
+    double sa[21];
+#pragma unroll
+    for (int e = 0; e < 21; e++) sa[e] = 0.0;
+    int qn = 0;  // movers queued for this cell
+    bool full = false;
+    while (isp < P.nsp && !full) {
       const int beg = isp ? beg1 : beg0, end = beg + (isp ? cnt1 : cnt0);
       int nmax = end - beg;
       nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));
@@ -273,8 +292,6 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
       const double fac2 = qs * delt / P.r[isp];
       const double qf = qs * qf_base;  // q*delx*d_delt, field.f90:278
 
-      int nst = 0;  // stayers of this (cell, species) so far
-      int nmv = 0;  // cell changers of this (quad, species) so far
       long long qrec = 0;
       int qcap = 0;
       if (cy < th && (q - cy * QX) * 4 < tw) {
@@ -282,16 +299,17 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         const int *cs = a.cstart + (size_t)isp * (P.ncell + 1);
         stage_region(so_slots(P, isp) + cs[c0], so_slots(P, isp) + cs[min(c0 + 4, (lj0 + cy + 1) * P.nx)], &qrec, &qcap);
       }
-      int p = beg + l8;
-      double nx_ = 0.0, ny_ = 0.0, nu1 = 0.0, nu2 = 0.0, nu3 = 0.0, nid = 0.0;
+      int p = beg + l8 + k0;
+      // the lane's current particle; the next one is loaded into the same registers as soon as the push is done
+      double x = 0.0, y = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0, idv = 0.0;
       if (p < end) {
         const double *b = px + so + p;
-        nx_ = b[0];
-        ny_ = b[cstride];
-        nu1 = b[2 * cstride];
-        nu2 = b[3 * cstride];
-        nu3 = b[4 * cstride];
-        nid = b[5 * cstride];
+        x = b[0];
+        y = b[cstride];
+        u1 = b[2 * cstride];
+        u2 = b[3 * cstride];
+        u3 = b[4 * cstride];
+        idv = b[5 * cstride];
       }
       {
         // first particle of what this lane works on next: the other species of this cell, then species 0 of the
@@ -304,30 +322,20 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
           for (int cpt = 0; cpt < 6; cpt++) asm volatile("prefetch.global.L1 [%0];" ::"l"(b + cpt * cstride));
         }
       }
-      for (int k = 0; k < nmax; k += 8) {
+      int k = k0;
+      for (; k < nmax; k += 8) {
         const int pc = p;
         const bool active = pc < end;
-        const double x = nx_, y = ny_, u1 = nu1, u2 = nu2, u3 = nu3, idc = nid;
-        p += 8;
-        if (p < end) {  // prefetch the next particle of this lane
-          const double *b = px + so + p;
-          nx_ = b[0];
-          ny_ = b[cstride];
-          nu1 = b[2 * cstride];
-          nu2 = b[3 * cstride];
-          nu3 = b[4 * cstride];
-          nid = b[5 * cstride];  // the id moves with the record (bit pattern)
-        }
         bool stay = false;   // stays in its cell for the sort (after the particle boundary)
         bool dmove = false;  // changes cell for the deposit (before the particle boundary)
-        int incx = 0, incy = 0;
-        double xn = 0.0, yn = 0.0, un1 = 0.0, un2 = 0.0, un3 = 0.0;
-        double hx = 0.0, hy = 0.0, dxn = 0.0, dyn = 0.0, qvz = 0.0;
+        int incx, incy;
+        double xn, yn, un1, un2, un3;
+        double hx, hy, dxn, dyn, qvz;
+        double sxm, sx0, sxp, sym, sy0, syp;
         if (active) {
           // ---- second order shape function about the sorted cell       particle.f90:97-105
           hx = x - cxh;
           hy = y - cyh;
-          double sxm, sx0, sxp, sym, sy0, syp;
           shape3(hx, sxm, sx0, sxp);
           shape3(hy, sym, sy0, syp);
           // ---- 3x3 gather of the six cell-centred components            particle.f90:107-129
@@ -381,6 +389,21 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
           incx = (int)xr - (int)xl;
           incy = (int)yr - (int)yl;
           qvz = qs * (un3 * wmove);  // q*gvz, field.f90:270-272,295
+        }
+        // ---- the record is consumed: fetch the lane's next particle into the same registers (the id moves with
+        //      the record, bit pattern).  Its latency is covered by the deposit and the sort bookkeeping.
+        const double idc = idv;
+        p += 8;
+        if (p < end) {
+          const double *b = px + so + p;
+          x = b[0];
+          y = b[cstride];
+          u1 = b[2 * cstride];
+          u2 = b[3 * cstride];
+          u3 = b[4 * cstride];
+          idv = b[5 * cstride];
+        }
+        {
           if (stay) {
             // ---- Esirkepov density decomposition of a stayer (inc = 0)     field.f90:224-298
             //  DS(-1,0,+1) = S1 - S0 = (A - h, -2A, A + h),  A = (d'-d)(d'+d)/2,  h = (d'-d)/2
@@ -417,17 +440,12 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
           const unsigned bald = __ballot_sync(0xffffffffu, dmove);
           const unsigned d8 = (bald >> (grp * 8)) & 0xffu;
           if (dmove) {
-            const int slot = qn + __popc(d8 & below);
-            if (slot < QCAP) {
-              double2 *r = myq + slot * 3;
-              r[0] = make_double2(hx, hy);
-              r[1] = make_double2(dxn, dyn);
-              r[2] = make_double2(qvz, qf);
-            } else if (DRAIN) {
-              deposit_mover_slow(sj0, hx, hy, dxn, dyn, qvz, qf);
-            }
+            double2 *r = myq + (qn + __popc(d8 & below)) * 3;  // qn <= QCAP - 8 here
+            r[0] = make_double2(hx, hy);
+            r[1] = make_double2(dxn, dyn);
+            r[2] = make_double2(qvz, qf);
           }
-          qn = min(qn + __popc(d8), QCAP);
+          qn += __popc(d8);
         }
         // ---- reflecting x walls (after the deposit, which uses the position before the boundary)
         //      proj/reconnection/boundary_reconnection.f90:61-99
@@ -513,105 +531,102 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         }
         nst += __popc(m8);
         nmv += __popc(balm);
-      }
-      if (valid && l8 == 0) a.cnt_tail[(size_t)isp * P.ncell + cell] = nst;  // arrivals are added by k_place
-      if (lane == 0) s_nmv[isp * NQ + q] = nmv;
-    }
-
-    // ---- drain the mover queue of the cell into the full block; the stayer sums are the start values
-    double acc[65];
-#pragma unroll
-    for (int e = 0; e < 65; e++) acc[e] = (stay_slot(e) >= 0) ? sa[stay_slot(e) >= 0 ? stay_slot(e) : 0] : 0.0;
-    if (DRAIN) {
-      __syncwarp();
-      int nqm = qn;
-      nqm = max(nqm, __shfl_xor_sync(0xffffffffu, nqm, 8));
-      nqm = max(nqm, __shfl_xor_sync(0xffffffffu, nqm, 16));
-      for (int k = l8; k - l8 < nqm; k += 8) {
-        if (k < qn) {
-          const double2 *r = myq + k * 3;
-          const double2 r0 = r[0], r1 = r[1], r2 = r[2];
-          const double qvz = r2.x, qf = r2.y;
-          double sxm, sx0, sxp, sym, sy0, syp;
-          shape3(r0.x, sxm, sx0, sxp);
-          shape3(r0.y, sym, sy0, syp);
-          double dsx0, dsx1, dsx2, dsx3, dsx4, dsy0, dsy1, dsy2, dsy3, dsy4;
-          ds5(r1.x, sxm, sx0, sxp, dsx0, dsx1, dsx2, dsx3, dsx4);
-          ds5(r1.y, sym, sy0, syp, dsy0, dsy1, dsy2, dsy3, dsy4);
-          //  Jx block = Cx (x) Ty, Jy block = Tx (x) Cy, Jz block = Tx (x) Uy + Hx (x) Vy
-          //  T = S0 + DS/2, H = S0/2 + DS/3, C = running sum of -q*dx/dt*DS
-          {
-            const double ty0 = 0.5 * dsy0, ty1 = fma(0.5, dsy1, sym), ty2 = fma(0.5, dsy2, sy0), ty3 = fma(0.5, dsy3, syp),
-                         ty4 = 0.5 * dsy4;
-            const double c0 = -qf * dsx0, c1 = fma(-qf, dsx1, c0), c2 = fma(-qf, dsx2, c1), c3 = qf * dsx4;
-            acc[0] = fma(c0, ty0, acc[0]);   acc[1] = fma(c1, ty0, acc[1]);   acc[2] = fma(c2, ty0, acc[2]);   acc[3] = fma(c3, ty0, acc[3]);
-            acc[4] = fma(c0, ty1, acc[4]);   acc[5] = fma(c1, ty1, acc[5]);   acc[6] = fma(c2, ty1, acc[6]);   acc[7] = fma(c3, ty1, acc[7]);
-            acc[8] = fma(c0, ty2, acc[8]);   acc[9] = fma(c1, ty2, acc[9]);   acc[10] = fma(c2, ty2, acc[10]); acc[11] = fma(c3, ty2, acc[11]);
-            acc[12] = fma(c0, ty3, acc[12]); acc[13] = fma(c1, ty3, acc[13]); acc[14] = fma(c2, ty3, acc[14]); acc[15] = fma(c3, ty3, acc[15]);
-            acc[16] = fma(c0, ty4, acc[16]); acc[17] = fma(c1, ty4, acc[17]); acc[18] = fma(c2, ty4, acc[18]); acc[19] = fma(c3, ty4, acc[19]);
-          }
-          {
-            const double tx0 = 0.5 * dsx0, tx1 = fma(0.5, dsx1, sxm), tx2 = fma(0.5, dsx2, sx0), tx3 = fma(0.5, dsx3, sxp),
-                         tx4 = 0.5 * dsx4;
-            {
-              const double c0 = -qf * dsy0, c1 = fma(-qf, dsy1, c0), c2 = fma(-qf, dsy2, c1), c3 = qf * dsy4;
-              acc[20] = fma(tx0, c0, acc[20]); acc[21] = fma(tx1, c0, acc[21]); acc[22] = fma(tx2, c0, acc[22]); acc[23] = fma(tx3, c0, acc[23]); acc[24] = fma(tx4, c0, acc[24]);
-              acc[25] = fma(tx0, c1, acc[25]); acc[26] = fma(tx1, c1, acc[26]); acc[27] = fma(tx2, c1, acc[27]); acc[28] = fma(tx3, c1, acc[28]); acc[29] = fma(tx4, c1, acc[29]);
-              acc[30] = fma(tx0, c2, acc[30]); acc[31] = fma(tx1, c2, acc[31]); acc[32] = fma(tx2, c2, acc[32]); acc[33] = fma(tx3, c2, acc[33]); acc[34] = fma(tx4, c2, acc[34]);
-              acc[35] = fma(tx0, c3, acc[35]); acc[36] = fma(tx1, c3, acc[36]); acc[37] = fma(tx2, c3, acc[37]); acc[38] = fma(tx3, c3, acc[38]); acc[39] = fma(tx4, c3, acc[39]);
-            }
-            const double third = 1.0 / 3.0;
-            const double hx0 = third * dsx0, hx1 = fma(third, dsx1, 0.5 * sxm), hx2_ = fma(third, dsx2, 0.5 * sx0),
-                         hx3 = fma(third, dsx3, 0.5 * sxp), hx4 = third * dsx4;
-            const double uy1 = qvz * sym, uy2 = qvz * sy0, uy3 = qvz * syp;
-            const double vy0 = qvz * dsy0, vy1 = qvz * dsy1, vy2 = qvz * dsy2, vy3 = qvz * dsy3, vy4 = qvz * dsy4;
-            acc[40] = fma(hx0, vy0, acc[40]); acc[41] = fma(hx1, vy0, acc[41]); acc[42] = fma(hx2_, vy0, acc[42]); acc[43] = fma(hx3, vy0, acc[43]); acc[44] = fma(hx4, vy0, acc[44]);
-            acc[45] = fma(hx0, vy1, fma(tx0, uy1, acc[45])); acc[46] = fma(hx1, vy1, fma(tx1, uy1, acc[46])); acc[47] = fma(hx2_, vy1, fma(tx2, uy1, acc[47]));
-            acc[48] = fma(hx3, vy1, fma(tx3, uy1, acc[48])); acc[49] = fma(hx4, vy1, fma(tx4, uy1, acc[49]));
-            acc[50] = fma(hx0, vy2, fma(tx0, uy2, acc[50])); acc[51] = fma(hx1, vy2, fma(tx1, uy2, acc[51])); acc[52] = fma(hx2_, vy2, fma(tx2, uy2, acc[52]));
-            acc[53] = fma(hx3, vy2, fma(tx3, uy2, acc[53])); acc[54] = fma(hx4, vy2, fma(tx4, uy2, acc[54]));
-            acc[55] = fma(hx0, vy3, fma(tx0, uy3, acc[55])); acc[56] = fma(hx1, vy3, fma(tx1, uy3, acc[56])); acc[57] = fma(hx2_, vy3, fma(tx2, uy3, acc[57]));
-            acc[58] = fma(hx3, vy3, fma(tx3, uy3, acc[58])); acc[59] = fma(hx4, vy3, fma(tx4, uy3, acc[59]));
-            acc[60] = fma(hx0, vy4, acc[60]); acc[61] = fma(hx1, vy4, acc[61]); acc[62] = fma(hx2_, vy4, acc[62]); acc[63] = fma(hx3, vy4, acc[63]); acc[64] = fma(hx4, vy4, acc[64]);
-          }
+        if (DRAIN && __any_sync(0xffffffffu, qn > QCAP - 8)) {  // the next iteration could overflow a queue: drain first
+          k += 8;
+          full = true;
+          break;
         }
       }
-      __syncwarp();
+      if (k >= nmax) {
+        if (valid && l8 == 0) a.cnt_tail[(size_t)isp * P.ncell + cell] = nst;  // arrivals are added by k_place
+        if (lane == 0) s_nmv[isp * NQ + q] = nmv;
+        isp++;
+        k0 = 0;
+        nst = 0;
+        nmv = 0;
+      } else {
+        k0 = k;
+      }
     }
 
-    // ---- reduce-scatter the 65 partial sums over the 8 lanes of the cell   field.f90:304-310
+    // ---- drain the mover queue of the cell: one pass per current component (Jz, Jx, Jy), so that at most 25
+    //      sums are live at a time; the stayer sums are the start values of their entries.  Each pass ends with
+    //      the reduce-scatter over the 8 lanes of the cell and one add per entry to the shared-memory tile
+    //      (field.f90:304-310).
     {
-      const bool h4 = (l8 & 4) != 0, h2 = (l8 & 2) != 0, h1 = (l8 & 1) != 0;
-      double t64 = acc[64];
-      t64 += __shfl_xor_sync(0xffffffffu, t64, 4);
-      t64 += __shfl_xor_sync(0xffffffffu, t64, 2);
-      t64 += __shfl_xor_sync(0xffffffffu, t64, 1);
+      __syncwarp();
+      int nqm = DRAIN ? qn : 0;
+      nqm = max(nqm, __shfl_xor_sync(0xffffffffu, nqm, 8));
+      nqm = max(nqm, __shfl_xor_sync(0xffffffffu, nqm, 16));
+      {  // Jz block = Tx (x) Uy + Hx (x) Vy     acc[40 + b*5 + q]
+        double v[32];
 #pragma unroll
-      for (int e = 0; e < 32; e++) {
-        const double snd = h4 ? acc[e] : acc[e + 32];
-        const double kp = h4 ? acc[e + 32] : acc[e];
-        acc[e] = kp + __shfl_xor_sync(0xffffffffu, snd, 4);
+        for (int e = 0; e < 32; e++) v[e] = (e < 25 && stay_slot(40 + e) >= 0) ? sa[stay_slot(40 + (e < 25 ? e : 0)) >= 0 ? stay_slot(40 + (e < 25 ? e : 0)) : 0] : 0.0;
+        for (int k = l8; k - l8 < nqm; k += 8) {
+          if (k < qn) {
+            MoverW w;
+            mover_weights(myq + k * 3, w);
+            const double third = 1.0 / 3.0;
+            const double tx0 = 0.5 * w.dsx0, tx1 = fma(0.5, w.dsx1, w.sxm), tx2 = fma(0.5, w.dsx2, w.sx0), tx3 = fma(0.5, w.dsx3, w.sxp),
+                         tx4 = 0.5 * w.dsx4;
+            const double hx0 = third * w.dsx0, hx1 = fma(third, w.dsx1, 0.5 * w.sxm), hx2 = fma(third, w.dsx2, 0.5 * w.sx0),
+                         hx3 = fma(third, w.dsx3, 0.5 * w.sxp), hx4 = third * w.dsx4;
+            const double uy1 = w.qvz * w.sym, uy2 = w.qvz * w.sy0, uy3 = w.qvz * w.syp;
+            const double vy0 = w.qvz * w.dsy0, vy1 = w.qvz * w.dsy1, vy2 = w.qvz * w.dsy2, vy3 = w.qvz * w.dsy3, vy4 = w.qvz * w.dsy4;
+            v[0] = fma(hx0, vy0, v[0]); v[1] = fma(hx1, vy0, v[1]); v[2] = fma(hx2, vy0, v[2]); v[3] = fma(hx3, vy0, v[3]); v[4] = fma(hx4, vy0, v[4]);
+            v[5] = fma(hx0, vy1, fma(tx0, uy1, v[5])); v[6] = fma(hx1, vy1, fma(tx1, uy1, v[6])); v[7] = fma(hx2, vy1, fma(tx2, uy1, v[7]));
+            v[8] = fma(hx3, vy1, fma(tx3, uy1, v[8])); v[9] = fma(hx4, vy1, fma(tx4, uy1, v[9]));
+            v[10] = fma(hx0, vy2, fma(tx0, uy2, v[10])); v[11] = fma(hx1, vy2, fma(tx1, uy2, v[11])); v[12] = fma(hx2, vy2, fma(tx2, uy2, v[12]));
+            v[13] = fma(hx3, vy2, fma(tx3, uy2, v[13])); v[14] = fma(hx4, vy2, fma(tx4, uy2, v[14]));
+            v[15] = fma(hx0, vy3, fma(tx0, uy3, v[15])); v[16] = fma(hx1, vy3, fma(tx1, uy3, v[16])); v[17] = fma(hx2, vy3, fma(tx2, uy3, v[17]));
+            v[18] = fma(hx3, vy3, fma(tx3, uy3, v[18])); v[19] = fma(hx4, vy3, fma(tx4, uy3, v[19]));
+            v[20] = fma(hx0, vy4, v[20]); v[21] = fma(hx1, vy4, v[21]); v[22] = fma(hx2, vy4, v[22]); v[23] = fma(hx3, vy4, v[23]); v[24] = fma(hx4, vy4, v[24]);
+          }
+        }
+        rs_add<32>(v, l8, valid, sj0, 40, 25);
       }
+      {  // Jx block = Cx (x) Ty     acc[b*4 + q],  C = running sum of -q*dx/dt*DSx
+        double v[24];
 #pragma unroll
-      for (int e = 0; e < 16; e++) {
-        const double snd = h2 ? acc[e] : acc[e + 16];
-        const double kp = h2 ? acc[e + 16] : acc[e];
-        acc[e] = kp + __shfl_xor_sync(0xffffffffu, snd, 2);
+        for (int e = 0; e < 24; e++) v[e] = (e < 20 && stay_slot(e < 20 ? e : 0) >= 0) ? sa[stay_slot(e < 20 ? e : 0) >= 0 ? stay_slot(e < 20 ? e : 0) : 0] : 0.0;
+        for (int k = l8; k - l8 < nqm; k += 8) {
+          if (k < qn) {
+            MoverW w;
+            mover_weights(myq + k * 3, w);
+            const double ty0 = 0.5 * w.dsy0, ty1 = fma(0.5, w.dsy1, w.sym), ty2 = fma(0.5, w.dsy2, w.sy0), ty3 = fma(0.5, w.dsy3, w.syp),
+                         ty4 = 0.5 * w.dsy4;
+            const double c0 = -w.qf * w.dsx0, c1 = fma(-w.qf, w.dsx1, c0), c2 = fma(-w.qf, w.dsx2, c1), c3 = w.qf * w.dsx4;
+            v[0] = fma(c0, ty0, v[0]);   v[1] = fma(c1, ty0, v[1]);   v[2] = fma(c2, ty0, v[2]);   v[3] = fma(c3, ty0, v[3]);
+            v[4] = fma(c0, ty1, v[4]);   v[5] = fma(c1, ty1, v[5]);   v[6] = fma(c2, ty1, v[6]);   v[7] = fma(c3, ty1, v[7]);
+            v[8] = fma(c0, ty2, v[8]);   v[9] = fma(c1, ty2, v[9]);   v[10] = fma(c2, ty2, v[10]); v[11] = fma(c3, ty2, v[11]);
+            v[12] = fma(c0, ty3, v[12]); v[13] = fma(c1, ty3, v[13]); v[14] = fma(c2, ty3, v[14]); v[15] = fma(c3, ty3, v[15]);
+            v[16] = fma(c0, ty4, v[16]); v[17] = fma(c1, ty4, v[17]); v[18] = fma(c2, ty4, v[18]); v[19] = fma(c3, ty4, v[19]);
+          }
+        }
+        rs_add<24>(v, l8, valid, sj0, 0, 20);
       }
+      {  // Jy block = Tx (x) Cy     acc[20 + b*5 + q]
+        double v[24];
 #pragma unroll
-      for (int e = 0; e < 8; e++) {
-        const double snd = h1 ? acc[e] : acc[e + 8];
-        const double kp = h1 ? acc[e + 8] : acc[e];
-        acc[e] = kp + __shfl_xor_sync(0xffffffffu, snd, 1);
+        for (int e = 0; e < 24; e++) v[e] = (e < 20 && stay_slot(20 + (e < 20 ? e : 0)) >= 0) ? sa[stay_slot(20 + (e < 20 ? e : 0)) >= 0 ? stay_slot(20 + (e < 20 ? e : 0)) : 0] : 0.0;
+        for (int k = l8; k - l8 < nqm; k += 8) {
+          if (k < qn) {
+            MoverW w;
+            mover_weights(myq + k * 3, w);
+            const double tx0 = 0.5 * w.dsx0, tx1 = fma(0.5, w.dsx1, w.sxm), tx2 = fma(0.5, w.dsx2, w.sx0), tx3 = fma(0.5, w.dsx3, w.sxp),
+                         tx4 = 0.5 * w.dsx4;
+            const double c0 = -w.qf * w.dsy0, c1 = fma(-w.qf, w.dsy1, c0), c2 = fma(-w.qf, w.dsy2, c1), c3 = w.qf * w.dsy4;
+            v[0] = fma(tx0, c0, v[0]);   v[1] = fma(tx1, c0, v[1]);   v[2] = fma(tx2, c0, v[2]);   v[3] = fma(tx3, c0, v[3]);   v[4] = fma(tx4, c0, v[4]);
+            v[5] = fma(tx0, c1, v[5]);   v[6] = fma(tx1, c1, v[6]);   v[7] = fma(tx2, c1, v[7]);   v[8] = fma(tx3, c1, v[8]);   v[9] = fma(tx4, c1, v[9]);
+            v[10] = fma(tx0, c2, v[10]); v[11] = fma(tx1, c2, v[11]); v[12] = fma(tx2, c2, v[12]); v[13] = fma(tx3, c2, v[13]); v[14] = fma(tx4, c2, v[14]);
+            v[15] = fma(tx0, c3, v[15]); v[16] = fma(tx1, c3, v[16]); v[17] = fma(tx2, c3, v[17]); v[18] = fma(tx3, c3, v[18]); v[19] = fma(tx4, c3, v[19]);
+          }
+        }
+        rs_add<24>(v, l8, valid, sj0, 20, 20);
       }
-      if (valid) {
-        const int ebase = (h4 ? 32 : 0) + (h2 ? 16 : 0) + (h1 ? 8 : 0);
-#pragma unroll
-        for (int e = 0; e < 8; e++)
-          if (acc[e] != 0.0) atomicAdd(sj0 + c_joff5.v[ebase + e], acc[e]);
-        if (l8 == 0 && t64 != 0.0) atomicAdd(sj0 + c_joff5.v[64], t64);
-      }
+      __syncwarp();
     }
+    } while (isp < P.nsp);
   }
   __syncthreads();
 
