@@ -134,6 +134,15 @@ __device__ __forceinline__ void ds5(double dn, double sm, double s0, double sp, 
   d4 = r ? t3 : 0.0;
 }
 
+// Opaque copies: after pin(v) the compiler can no longer rematerialise v from its defining expression, so the
+// value stays in a register across the particle loop instead of being recomputed every iteration.
+__device__ __forceinline__ void pin(double &v) { asm volatile("" : "+d"(v)); }
+__device__ __forceinline__ void pin(int &v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void pin(unsigned &v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void pin(size_t &v) { asm volatile("" : "+l"(v)); }
+template <typename T>
+__device__ __forceinline__ void pin(T *&v) { asm volatile("" : "+l"(v)); }
+
 // weights of a queued mover: old shape function, DS of both directions, q*vz, q*dx/dt
 struct MoverW {
   double sxm, sx0, sxp, sym, sy0, syp;
@@ -185,7 +194,7 @@ __device__ __forceinline__ void rs_add(double (&v)[NP], int l8, bool valid, doub
 
 // MINB resident CTAs per SM: 3 -> at most 168 registers.  DRAIN = false drops the movers' current (wrong physics:
 // only for timing the particle loop in isolation).
-template <int MINB, bool DRAIN>
+template <int MINB, bool DRAIN, bool WALL, int PFD>
 __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const Pass1Args a) {
   __shared__ __align__(128) double s_f[WINY * WINX * 6];
   __shared__ __align__(16) double s_j[3 * JY * JX];
@@ -218,12 +227,18 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
 
   const int wid = tid >> 5, lane = tid & 31;
   const int grp = lane >> 3, l8 = lane & 7;
-  const unsigned below = (1u << l8) - 1u;
-  const size_t cstride = (size_t)P.cap * P.nsp;  // elements between component arrays (carved SoA)
+  unsigned below = (1u << l8) - 1u;
+  int gsh = grp * 8;
+  size_t cstride = (size_t)P.cap * P.nsp;  // elements between component arrays (carved SoA)
+  pin(below);
+  pin(gsh);
+  pin(cstride);
   double *const px = a.src.x;
   const double qf_base = P.delx / P.delt;
   const double delt = P.delt, inv_cc = P.inv_cc, cc = P.cc;
-  double2 *const myq = &s_q[(wid * 4 + grp) * (QCAP * 3)];
+  int myqi = (wid * 4 + grp) * (QCAP * 3);
+  pin(myqi);
+  double2 *const myq = &s_q[myqi];
 
   int nb0 = 0, nc0 = 0, nb1 = 0, nc1 = 0;
   {
@@ -244,9 +259,13 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
     const bool valid = (cx < tw) && (cy < th);
     const int cell = (lj0 + cy) * P.nx + (li0 + cx);
     const int gi = P.nxgs + li0 + cx, gj = P.nys + lj0 + cy;
-    const double cxh = (double)gi + 0.5, cyh = (double)gj + 0.5;
-    const double *sf0 = &s_f[(cy * WINX + cx) * 6];
+    double cxh = (double)gi + 0.5, cyh = (double)gj + 0.5;
+    int sfi = (cy * WINX + cx) * 6;
     double *const sj0 = &s_j[cy * JX + cx];
+    pin(cxh);
+    pin(cyh);
+    pin(sfi);
+    const double *const sf0 = &s_f[sfi];
 
 
     // segment bounds of both species: loaded one quad ahead (nb*), so that the first particles of the next
@@ -285,12 +304,15 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
       nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));
       nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
       const size_t so = (size_t)isp * P.cap;
-      const double qs = P.q[isp];
+      double qs = P.q[isp];
       // particle.f90:90-92
-      const double fac1 = qs / P.r[isp] * 0.5 * delt;
+      double fac1 = qs / P.r[isp] * 0.5 * delt;
       const double txxx = fac1 * fac1;
       const double fac2 = qs * delt / P.r[isp];
-      const double qf = qs * qf_base;  // q*delx*d_delt, field.f90:278
+      double qf = qs * qf_base;  // q*delx*d_delt, field.f90:278
+      pin(qs);
+      pin(fac1);
+      pin(qf);
 
       long long qrec = 0;
       int qcap = 0;
@@ -300,16 +322,20 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         stage_region(so_slots(P, isp) + cs[c0], so_slots(P, isp) + cs[min(c0 + 4, (lj0 + cy + 1) * P.nx)], &qrec, &qcap);
       }
       int p = beg + l8 + k0;
+      double *pbase = px + (size_t)isp * P.cap;  // slot 0 of this species, component x
+      pin(pbase);
+      __builtin_assume(__isGlobal(pbase));
+      const double *pl = pbase + p;                    // the lane's current particle, component x
+      const int w0 = isp * WIN + (cy + 1) * WINX + (cx + 1);  // this cell in the window of arrival counters
       // the lane's current particle; the next one is loaded into the same registers as soon as the push is done
       double x = 0.0, y = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0, idv = 0.0;
       if (p < end) {
-        const double *b = px + so + p;
-        x = b[0];
-        y = b[cstride];
-        u1 = b[2 * cstride];
-        u2 = b[3 * cstride];
-        u3 = b[4 * cstride];
-        idv = b[5 * cstride];
+        x = pl[0];
+        y = pl[cstride];
+        u1 = pl[2 * cstride];
+        u2 = pl[3 * cstride];
+        u3 = pl[4 * cstride];
+        idv = pl[5 * cstride];
       }
       {
         // first particle of what this lane works on next: the other species of this cell, then species 0 of the
@@ -317,7 +343,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         const bool last = isp + 1 == P.nsp;
         const int pb = last ? nb0 : beg1, pn = last ? nc0 : cnt1;
         if (l8 < pn) {
-          const double *b = px + (last ? (size_t)0 : P.cap) + pb + l8;
+          const double *b = px + (last ? (size_t)0 : (size_t)P.cap) + pb + l8;
 #pragma unroll
           for (int cpt = 0; cpt < 6; cpt++) asm volatile("prefetch.global.L1 [%0];" ::"l"(b + cpt * cstride));
         }
@@ -326,9 +352,6 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
       for (; k < nmax; k += 8) {
         const int pc = p;
         const bool active = pc < end;
-        bool stay = false;   // stays in its cell for the sort (after the particle boundary)
-        bool dmove = false;  // changes cell for the deposit (before the particle boundary)
-        int incx, incy;
         double xn, yn, un1, un2, un3;
         double hx, hy, dxn, dyn, qvz;
         double sxm, sx0, sxp, sym, sy0, syp;
@@ -383,26 +406,30 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
           //      int(gp*d_delx) of field.f90:238 makes (positions > 0: truncation == floor)
           dxn = xn - cxh;
           dyn = yn - cyh;
-          const bool xl = dxn < -0.5, xr = dxn >= 0.5, yl = dyn < -0.5, yr = dyn >= 0.5;
-          stay = !(xl | xr | yl | yr);
-          dmove = !stay;
-          incx = (int)xr - (int)xl;
-          incy = (int)yr - (int)yl;
           qvz = qs * (un3 * wmove);  // q*gvz, field.f90:270-272,295
         }
         // ---- the record is consumed: fetch the lane's next particle into the same registers (the id moves with
-        //      the record, bit pattern).  Its latency is covered by the deposit and the sort bookkeeping.
+        //      the record, bit pattern).  Its latency is covered by the deposit and the sort bookkeeping; the line
+        //      after that one is pulled into L1 by a prefetch hint (no register cost).
         const double idc = idv;
         p += 8;
+        pl += 8;
         if (p < end) {
-          const double *b = px + so + p;
-          x = b[0];
-          y = b[cstride];
-          u1 = b[2 * cstride];
-          u2 = b[3 * cstride];
-          u3 = b[4 * cstride];
-          idv = b[5 * cstride];
+          x = pl[0];
+          y = pl[cstride];
+          u1 = pl[2 * cstride];
+          u2 = pl[3 * cstride];
+          u3 = pl[4 * cstride];
+          idv = pl[5 * cstride];
+          if (PFD > 0) {
+#pragma unroll
+            for (int cpt = 0; cpt < 6; cpt++) asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + cpt * cstride + 8 * PFD));
+          }
         }
+        // stays in its cell as far as the deposit is concerned (before the particle boundary): the comparisons
+        // int(gp*d_delx) of field.f90:238 makes (positions > 0: truncation == floor; xn - cxh is exact)
+        const bool stay = active && dxn >= -0.5 && dxn < 0.5 && dyn >= -0.5 && dyn < 0.5;
+        const bool dmove = active && !stay;
         {
           if (stay) {
             // ---- Esirkepov density decomposition of a stayer (inc = 0)     field.f90:224-298
@@ -438,7 +465,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         // ---- movers: queue the deposit for the drain at the end of the cell
         {
           const unsigned bald = __ballot_sync(0xffffffffu, dmove);
-          const unsigned d8 = (bald >> (grp * 8)) & 0xffu;
+          const unsigned d8 = (bald >> gsh) & 0xffu;
           if (dmove) {
             double2 *r = myq + (qn + __popc(d8 & below)) * 3;  // qn <= QCAP - 8 here
             r[0] = make_double2(hx, hy);
@@ -449,32 +476,34 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         }
         // ---- reflecting x walls (after the deposit, which uses the position before the boundary)
         //      proj/reconnection/boundary_reconnection.f90:61-99
-        if (P.bc != WM_BC_PERIODIC && active) {
-          bool flip = false;
-          if (xn < P.xwlo) {
-            xn = P.xw2lo - xn;
-            flip = true;
-          } else if (xn >= P.xwhi) {
-            xn = P.xw2hi - xn;
-            flip = true;
-          }
-          if (flip) {
-            un1 = -un1;
-            un2 = -un2;
-            un3 = -un3;
-            const double d = xn - cxh;
-            incx = (int)(d >= 0.5) - (int)(d < -0.5);
-            stay = (incx | incy) == 0;
+        bool sstay = stay;  // stays in its cell as far as the sort is concerned (after the particle boundary)
+        if (WALL) {
+          if (active) {
+            bool flip = false;
+            if (xn < P.xwlo) {
+              xn = P.xw2lo - xn;
+              flip = true;
+            } else if (xn >= P.xwhi) {
+              xn = P.xw2hi - xn;
+              flip = true;
+            }
+            if (flip) {
+              un1 = -un1;
+              un2 = -un2;
+              un3 = -un3;
+              dxn = xn - cxh;
+              sstay = dxn >= -0.5 && dxn < 0.5 && dyn >= -0.5 && dyn < 0.5;
+            }
           }
         }
         // ---- sort bookkeeping                                             sort.f90:57-62
-        const unsigned bal = __ballot_sync(0xffffffffu, stay);
-        const unsigned balm = __ballot_sync(0xffffffffu, active && !stay);  // changers + leavers
-        const unsigned m8 = (bal >> (grp * 8)) & 0xffu;
-        if (stay) {
+        const unsigned bal = __ballot_sync(0xffffffffu, sstay);
+        const unsigned balm = __ballot_sync(0xffffffffu, active && !sstay);  // changers + leavers
+        const unsigned m8 = (bal >> gsh) & 0xffu;
+        if (sstay) {
           // stable compaction inside the segment: slot beg + rank among the stayers <= pc
           const int ns = beg + nst + __popc(m8 & below);
-          double *d = px + so + ns;
+          double *d = pbase + ns;
           d[0] = xn;
           d[cstride] = yn;
           d[2 * cstride] = un1;
@@ -484,7 +513,8 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         } else if (active) {
           // cell changer.  |move| < 1 cell (CFL), so the new cell is (gi + incx, gj + incy); anything else
           // is an error (also catches NaN)
-          if (!(fabs(xn - cxh) < 1.5 && fabs(yn - cyh) < 1.5)) atomicOr(a.err, ERR_MOVED_TOO_FAR);
+          if (!(fabs(dxn) < 1.5 && fabs(dyn) < 1.5)) atomicOr(a.err, ERR_MOVED_TOO_FAR);
+          const int incx = (int)(dxn >= 0.5) - (int)(dxn < -0.5), incy = (int)(dyn >= 0.5) - (int)(dyn < -0.5);
           // periodic wraps with round-toward -inf adds   boundary_periodic.f90:74,82-88,124,147-154
           const int gi2 = gi + incx, j2 = gj + incy;  // unwrapped destination cell
           if (gi2 < P.nxgs)
@@ -513,8 +543,8 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
             }
             tg = TAG_DEAD;
           } else {
-            const int w = (cy + 1 + incy) * WINX + (cx + 1 + incx);
-            tg = TAG_ARRIVAL | ((uint32_t)w << TAG_WSHIFT) | (uint32_t)atomicAdd(&s_arr[isp * WIN + w], 1);
+            const int w = w0 + incy * WINX + incx;
+            tg = TAG_ARRIVAL | ((uint32_t)(w - isp * WIN) << TAG_WSHIFT) | (uint32_t)atomicAdd(&s_arr[w], 1);
           }
           // stage the record (64 B: x y | ux uy | uz id | tag -) in the idle store, in the shadow of
           // this quad; slot order = ballot rank, so the stores of a warp are contiguous
@@ -651,12 +681,18 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
 }
 
 void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaStream_t st) {
+  const bool wall = P.bc != WM_BC_PERIODIC;
+  const int grid = P.ntx * P.nty;
   if (variant == 9)
-    k_fused_sm<3, false><<<P.ntx * P.nty, FT, 0, st>>>(P, a);  // timing experiment: movers' current dropped
+    k_fused_sm<3, false, false, 1><<<grid, FT, 0, st>>>(P, a);  // timing experiment: movers' current dropped
   else if (variant == 2)
-    k_fused_sm<2, true><<<P.ntx * P.nty, FT, 0, st>>>(P, a);
+    k_fused_sm<2, true, false, 1><<<grid, FT, 0, st>>>(P, a);   // 2 CTAs per SM, up to 255 registers
+  else if (variant == 10)
+    k_fused_sm<3, true, false, 0><<<grid, FT, 0, st>>>(P, a);   // without the L1 prefetch hints
+  else if (wall)
+    k_fused_sm<3, true, true, 1><<<grid, FT, 0, st>>>(P, a);
   else
-    k_fused_sm<3, true><<<P.ntx * P.nty, FT, 0, st>>>(P, a);
+    k_fused_sm<3, true, false, 1><<<grid, FT, 0, st>>>(P, a);
 }
 
 }  // namespace wm
