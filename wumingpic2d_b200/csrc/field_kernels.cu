@@ -13,6 +13,7 @@
 // without FMA contraction, so the only difference to the CPU path is the order of the
 // global dot-product sums.
 #include <cstddef>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -185,9 +186,11 @@ __global__ void k_rhs(const DevParams P, const double *__restrict__ uf, const do
 }
 
 // ---------------------------------------------------------------- CG (field.f90:319-461)
-// block partial sums -> red[block*8 + k]; the last block to arrive adds them in block order
+// block partial sums -> red[block*8 + k]; the last block to arrive adds them in a fixed order (thread t takes the
+// blocks t, t + 256, ...; then lanes, then warps), so the result is deterministic run to run.  The final sum is
+// done by the whole block: a serial loop over the partials was a 20 us tail on every reducing kernel.
 template <int NV>
-__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *red, unsigned *ticket, double *out) {
+__device__ __forceinline__ bool block_reduce_store(double (&v)[NV], double *red, unsigned *ticket, double *out) {
   __shared__ double s_w[8][NV];
   __shared__ bool s_last;
 #pragma unroll
@@ -213,13 +216,31 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *red,
   __syncthreads();
   if (s_last) {
     __threadfence();
+    double t[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) t[k] = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+      for (int k = 0; k < NV; k++) t[k] += __ldcg(&red[b * 8 + k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+    }
+    __syncthreads();  // s_w is reused
+    if (lane == 0)
+#pragma unroll
+      for (int k = 0; k < NV; k++) s_w[wid][k] = t[k];
+    __syncthreads();
     if (threadIdx.x < NV) {
-      double t = 0.0;
-      for (unsigned b = 0; b < gridDim.x; b++) t += ((volatile double *)red)[b * 8 + threadIdx.x];
-      out[threadIdx.x] = t;
+      double tt = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) tt += s_w[w][threadIdx.x];
+      out[threadIdx.x] = tt;
     }
     if (threadIdx.x == 0) *ticket = 0;
   }
+  return s_last;
 }
 
 // neighbour rows with periodic wrap when this rank owns the whole ring, columns always wrap
@@ -304,6 +325,7 @@ __global__ void k_cg_begin(CgCtl *ctl) {
       act = ctl->sum_g[l] > ctl->eps[l];
     }
     ctl->active[l] = act;
+    ctl->sum1[l] = 0.0;  // bv of the first fused p update (k_cg_pap): p <- r + 0 p
   }
   if (l == 0) ctl->stop = 0;
 }
@@ -407,6 +429,105 @@ __global__ void __launch_bounds__(256) k_cg_pupdate(const DevParams P, const dou
   if (s_last && threadIdx.x == 0) ctl->ticket[3] = 0;
 }
 
+
+// ---- two-kernel CG iteration (default): the p update of field.f90:446-450 is folded into the next A p.
+// k_cg_pap: pn <- r + bv p (bv = sum1/sumr of the previous iteration, 0 in the first), written to a second
+// buffer because the stencil reads p of the neighbours; ap <- f4 pn - N4 pn with pn of the four neighbours
+// recomputed from r and p (identical expression, so the values are those of the three-kernel form);
+// sums r^2 and pn.ap.  With more than one rank the rows nys-1 and nye+1 of pn are computed here as well, from
+// the exchanged halo rows of r (instead of exchanging p every iteration, set_boundary_phi at field.f90:392).
+__global__ void __launch_bounds__(256) k_cg_pap(const DevParams P, const double *__restrict__ r, const double *__restrict__ p,
+                                                double *__restrict__ pn, double *__restrict__ ap, double *red, CgCtl *ctl) {
+  const int a0 = ctl->active[0], a1 = ctl->active[1], a2 = ctl->active[2];
+  if (!(a0 | a1 | a2)) return;
+  const int act[3] = {a0, a1, a2};
+  double bv[3];
+#pragma unroll
+  for (int l = 0; l < 3; l++) bv[l] = act[l] ? ctl->sum1[l] / ctl->sumr[l] : 0.0;
+  const int n = P.nx * P.nyl;
+  const int nh = (P.nsize > 1) ? 2 * P.nx : 0;  // halo rows of pn
+  double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n + nh; t += gridDim.x * blockDim.x) {
+    if (t >= n) {
+      const int h = t - n, li = h % P.nx, lj = (h < P.nx) ? -1 : P.nyl;
+      const size_t o = pidx(P, li, lj);
+#pragma unroll
+      for (int l = 0; l < 3; l++)
+        if (act[l]) pn[o * 3 + l] = r[o * 3 + l] + bv[l] * p[o * 3 + l];
+      continue;
+    }
+    const int lj = t / P.nx, li = t % P.nx;
+    const size_t o = pidx(P, li, lj);
+    size_t xm, xp, ym, yp;
+    nbr(P, li, lj, xm, xp, ym, yp);
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+      if (!act[l]) continue;
+      const double b = bv[l];
+      const double rr = r[o * 3 + l];
+      const double pc = rr + b * p[o * 3 + l];
+      pn[o * 3 + l] = pc;
+      const double pym = r[ym * 3 + l] + b * p[ym * 3 + l], pyp = r[yp * 3 + l] + b * p[yp * 3 + l];
+      double pxm, pxp;
+      if (P.bc != WM_BC_PERIODIC && li == 0)  // conducting wall: see nb_xm
+        pxm = (l == 0) ? -pc : r[(o + 1) * 3 + l] + b * p[(o + 1) * 3 + l];
+      else
+        pxm = r[xm * 3 + l] + b * p[xm * 3 + l];
+      if (P.bc != WM_BC_PERIODIC && li == P.nx - 1)
+        pxp = 0.0;
+      else
+        pxp = r[xp * 3 + l] + b * p[xp * 3 + l];
+      const double av = -pym - pxm + P.f4 * pc - pxp - pyp;
+      ap[o * 3 + l] = av;
+      s[l] = s[l] + rr * rr;
+      s[3 + l] = s[3 + l] + pc * av;
+    }
+  }
+  block_reduce_store<6>(s, red, &ctl->ticket[1], ctl->sumr);
+}
+
+// phi += av p ; r -= av ap ; sum r^2 ; then the loop control of field.f90:426-430,387 (it only needs sumr, the
+// residual before this update)
+__global__ void __launch_bounds__(256) k_cg_update2(const DevParams P, const double *__restrict__ p,
+                                                    const double *__restrict__ ap, double *__restrict__ phi,
+                                                    double *__restrict__ r, double *red, CgCtl *ctl) {
+  const int a0 = ctl->active[0], a1 = ctl->active[1], a2 = ctl->active[2];
+  if (!(a0 | a1 | a2)) return;
+  const int act[3] = {a0, a1, a2};
+  double av[3];
+#pragma unroll
+  for (int l = 0; l < 3; l++) av[l] = act[l] ? ctl->sumr[l] / ctl->sum2[l] : 0.0;
+  const int n = P.nx * P.nyl;
+  double s[3] = {0.0, 0.0, 0.0};
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int lj = t / P.nx, li = t % P.nx;
+    const size_t o = pidx(P, li, lj);
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+      if (!act[l]) continue;
+      phi[o * 3 + l] = phi[o * 3 + l] + av[l] * p[o * 3 + l];
+      const double rr = r[o * 3 + l] - av[l] * ap[o * 3 + l];
+      r[o * 3 + l] = rr;
+      s[l] = s[l] + rr * rr;
+    }
+  }
+  const bool last = block_reduce_store<3>(s, red, &ctl->ticket[2], ctl->sum1);
+  if (last && threadIdx.x < 3) {
+    // every other block has read ctl (it had written its partial sums before the ticket): advance the loop state
+    const int l = threadIdx.x;
+    if (act[l]) {
+      ctl->ite[l] = ctl->ite[l] + 1;
+      ctl->sum_g[l] = sqrt(ctl->sumr[l]);  // residual *before* this iteration's update (:426)
+      if (ctl->ite[l] >= 100) {            // ite_max (:427)
+        ctl->stop = 1;
+        ctl->active[l] = 0;
+      } else {
+        ctl->active[l] = ctl->sum_g[l] > ctl->eps[l];
+      }
+    }
+  }
+}
+
 // df(l) <- phi on the interior                                               field.f90:455-457
 __global__ void k_cg_finish(const DevParams P, const double *__restrict__ phi, double *__restrict__ df) {
   const int n = P.nx * P.nyl;
@@ -477,6 +598,17 @@ __global__ void __launch_bounds__(256) k_field_energy(const DevParams P, const d
 }
 
 // ---------------------------------------------------------------- launch wrappers
+// grid of the reducing CG kernels: RED_BLOCKS by default (4 per SM); WM_CGBLOCKS overrides it up to the allocated maximum
+static int cg_blocks() {
+  static int nb = 0;
+  if (!nb) {
+    nb = RED_BLOCKS;
+    if (const char *v = getenv("WM_CGBLOCKS")) nb = atoi(v);
+    if (nb < 1) nb = 1;
+    if (nb > RED_BLOCKS_MAX) nb = RED_BLOCKS_MAX;
+  }
+  return nb;
+}
 static inline int gblocks(long long n) { return (int)((n + 255) / 256 < RED_BLOCKS * 2 ? (n + 255) / 256 : RED_BLOCKS * 2); }
 
 size_t cgctl_bytes() { return sizeof(CgCtl); }
@@ -517,22 +649,28 @@ void launch_rhs(const DevParams &P, const FieldBufs &f, cudaStream_t st) {
   k_rhs<<<gblocks((long long)P.ncell), 256, 0, st>>>(P, f.uf, f.uj, f.gkl);
 }
 void launch_cg_init(const DevParams &P, const FieldBufs &f, cudaStream_t st) {
-  k_cg_init<<<RED_BLOCKS, 256, 0, st>>>(P, f.df, f.gkl, f.phi, f.red, (CgCtl *)f.cgstate);
+  k_cg_init<<<cg_blocks(), 256, 0, st>>>(P, f.df, f.gkl, f.phi, f.red, (CgCtl *)f.cgstate);
 }
 void launch_cg_resid0(const DevParams &P, const FieldBufs &f, cudaStream_t st) {
-  k_cg_resid0<<<RED_BLOCKS, 256, 0, st>>>(P, f.gkl, f.phi, f.r, f.p, f.red, (CgCtl *)f.cgstate);
+  k_cg_resid0<<<cg_blocks(), 256, 0, st>>>(P, f.gkl, f.phi, f.r, f.p, f.red, (CgCtl *)f.cgstate);
 }
 void launch_cg_begin(const DevParams &, const FieldBufs &f, int, cudaStream_t st) {
   k_cg_begin<<<1, 32, 0, st>>>((CgCtl *)f.cgstate);
 }
 void launch_cg_ap(const DevParams &P, const FieldBufs &f, cudaStream_t st) {
-  k_cg_ap<<<RED_BLOCKS, 256, 0, st>>>(P, f.p, f.r, f.ap, f.red, (CgCtl *)f.cgstate);
+  k_cg_ap<<<cg_blocks(), 256, 0, st>>>(P, f.p, f.r, f.ap, f.red, (CgCtl *)f.cgstate);
 }
 void launch_cg_update(const DevParams &P, const FieldBufs &f, cudaStream_t st) {
-  k_cg_update<<<RED_BLOCKS, 256, 0, st>>>(P, f.p, f.ap, f.phi, f.r, f.red, (CgCtl *)f.cgstate);
+  k_cg_update<<<cg_blocks(), 256, 0, st>>>(P, f.p, f.ap, f.phi, f.r, f.red, (CgCtl *)f.cgstate);
+}
+void launch_cg_pap(const DevParams &P, const FieldBufs &f, const double *p_in, double *p_out, cudaStream_t st) {
+  k_cg_pap<<<cg_blocks(), 256, 0, st>>>(P, f.r, p_in, p_out, f.ap, f.red, (CgCtl *)f.cgstate);
+}
+void launch_cg_update2(const DevParams &P, const FieldBufs &f, const double *p, cudaStream_t st) {
+  k_cg_update2<<<cg_blocks(), 256, 0, st>>>(P, p, f.ap, f.phi, f.r, f.red, (CgCtl *)f.cgstate);
 }
 void launch_cg_pupdate(const DevParams &P, const FieldBufs &f, cudaStream_t st) {
-  k_cg_pupdate<<<RED_BLOCKS, 256, 0, st>>>(P, f.r, f.p, (CgCtl *)f.cgstate);
+  k_cg_pupdate<<<cg_blocks(), 256, 0, st>>>(P, f.r, f.p, (CgCtl *)f.cgstate);
 }
 void launch_cg_finish(const DevParams &P, const FieldBufs &f, cudaStream_t st) {
   k_cg_finish<<<gblocks((long long)P.ncell), 256, 0, st>>>(P, f.phi, f.df);

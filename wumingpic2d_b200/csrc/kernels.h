@@ -58,10 +58,12 @@ struct FieldBufs {
   double *uf, *df, *tmpf;     // AoS6 padded
   double *uj, *gkl;           // AoS3 padded
   double *phi, *p, *r, *ap;   // CG vectors, AoS3 padded (b lives in gkl, scaled by f5)
+  double *p2;                 // second p buffer of the two-kernel CG iteration
   double *red;                // reduction scratch: see field_kernels.cu
   int *cgstate;               // device CG control block
 };
-constexpr int RED_BLOCKS = 592;  // 148 SMs x 4
+constexpr int RED_BLOCKS = 592;       // 148 SMs x 4
+constexpr int RED_BLOCKS_MAX = 2368;  // size of the partial-sum scratch
 
 void launch_tmpf(const DevParams &P, const double *uf, double *tmpf, cudaStream_t st);
 void launch_fill_x(const DevParams &P, double *a, int ncomp, int ng, cudaStream_t st);           // periodic x ghosts (copy)
@@ -78,6 +80,9 @@ void launch_cg_begin(const DevParams &P, const FieldBufs &f, int nranks_reduced,
 void launch_cg_ap(const DevParams &P, const FieldBufs &f, cudaStream_t st);        // ap, sums
 void launch_cg_update(const DevParams &P, const FieldBufs &f, cudaStream_t st);    // phi, r, sum r^2
 void launch_cg_pupdate(const DevParams &P, const FieldBufs &f, cudaStream_t st);   // p
+// two-kernel iteration: p update folded into A p (p double-buffered), loop control in the update kernel
+void launch_cg_pap(const DevParams &P, const FieldBufs &f, const double *p_in, double *p_out, cudaStream_t st);
+void launch_cg_update2(const DevParams &P, const FieldBufs &f, const double *p, cudaStream_t st);
 void launch_cg_finish(const DevParams &P, const FieldBufs &f, cudaStream_t st);    // df(1:3) <- phi
 void launch_efield(const DevParams &P, const FieldBufs &f, cudaStream_t st);       // df(4:6)
 void launch_update_uf(const DevParams &P, const FieldBufs &f, cudaStream_t st);    // uf += df

@@ -70,6 +70,7 @@ struct wm_ctx {
   int ovfcap = 0;
   float slack = 6.0f;                    // segment slack in std deviations of the count change (WM_SLACK)
   bool inplace = true;                   // WM_INPLACE=0 selects the tag + scatter sort for wm_step
+  bool cg3 = false;                      // WM_CG3=1: three-kernel CG iteration (k_cg_ap, k_cg_update, k_cg_pupdate)
   int sm = 1;                            // stayer/mover split deposit (k_fused_sm); WM_SM=0 selects k_fused<INPLACE>
   bool pipe = false;                     // WM_PIPE=1: software-pipelined deposit (k_fused_pipe)
   bool ws = false;                       // WM_WS=1 selects the warp-specialised k_fused_ws (slower so far: profiles/r01h)
@@ -256,14 +257,28 @@ int cg_solve(wm_ctx *c) {
   const size_t ctl_n = 7 * sizeof(int);
   int it = 0;
   bool done = false;
+  double *p_in = c->f.p, *p_out = c->f.p2;
   for (; it < 101 && !done; it++) {
-    if (P.nsize > 1) WM(halo_copy(c, c->f.p, 3, 1, false));  // set_boundary_phi(p)  field.f90:392
-    launch_cg_ap(P, c->f, c->st);
-    WM(allreduce_ctl(c, 1, 6));
-    launch_cg_update(P, c->f, c->st);
-    WM(allreduce_ctl(c, 3, 3));
-    launch_cg_pupdate(P, c->f, c->st);
-    c->launches += 3;
+    if (c->cg3) {
+      // three-kernel iteration (WM_CG3=1): A p, update, p update, as field.f90:392-450 is written
+      if (P.nsize > 1) WM(halo_copy(c, c->f.p, 3, 1, false));  // set_boundary_phi(p)  field.f90:392
+      launch_cg_ap(P, c->f, c->st);
+      WM(allreduce_ctl(c, 1, 6));
+      launch_cg_update(P, c->f, c->st);
+      WM(allreduce_ctl(c, 3, 3));
+      launch_cg_pupdate(P, c->f, c->st);
+      c->launches += 3;
+    } else {
+      // two-kernel iteration: the p update is folded into the next A p; the neighbours' rows of p follow from the
+      // exchanged rows of r (one exchange per iteration, as set_boundary_phi(p) at field.f90:392)
+      if (P.nsize > 1) WM(halo_copy(c, c->f.r, 3, 1, false));
+      launch_cg_pap(P, c->f, p_in, p_out, c->st);
+      WM(allreduce_ctl(c, 1, 6));
+      launch_cg_update2(P, c->f, p_out, c->st);
+      WM(allreduce_ctl(c, 3, 3));
+      std::swap(p_in, p_out);
+      c->launches += 2;
+    }
     int *h = c->h_cg + (it & 1) * 8;
     CU(cudaMemcpyAsync(h, ctl, ctl_n, cudaMemcpyDeviceToHost, c->st));
     CU(cudaEventRecord(c->ev_cg[it & 1], c->st));
@@ -464,6 +479,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   if (const char *v = getenv("WM_WS")) c->ws = atoi(v) != 0;
   if (const char *v = getenv("WM_PIPE")) c->pipe = atoi(v) != 0;
   if (const char *v = getenv("WM_SM")) c->sm = atoi(v);
+  if (const char *v = getenv("WM_CG3")) c->cg3 = atoi(v) != 0;
   if (g->flags & WM_FLAG_EXACT_PUSH) c->inplace = false;  // the exact path keeps the reference's two-pass structure
   if (g->bc != WM_BC_PERIODIC) c->fused_variant = 1;      // k_fused2 has no wall reflection
   if (g->device >= 0) {
@@ -533,13 +549,14 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   CU(cudaMalloc(&c->f.gkl, ng * 3 * sizeof(double)));
   CU(cudaMalloc(&c->f.phi, ng * 3 * sizeof(double)));
   CU(cudaMalloc(&c->f.p, ng * 3 * sizeof(double)));
+  CU(cudaMalloc(&c->f.p2, ng * 3 * sizeof(double)));
   CU(cudaMalloc(&c->f.r, ng * 3 * sizeof(double)));
   CU(cudaMalloc(&c->f.ap, ng * 3 * sizeof(double)));
-  CU(cudaMalloc(&c->f.red, (size_t)RED_BLOCKS * 8 * sizeof(double)));
+  CU(cudaMalloc(&c->f.red, (size_t)RED_BLOCKS_MAX * 8 * sizeof(double)));
   CU(cudaMalloc(&c->f.cgstate, cgctl_bytes()));
   CU(cudaMemset(c->f.cgstate, 0, cgctl_bytes()));
   for (double *a : {c->f.uf, c->f.df, c->f.tmpf}) CU(cudaMemset(a, 0, ng * 6 * sizeof(double)));  // df=0: field.f90:109-111
-  for (double *a : {c->f.uj, c->f.gkl, c->f.phi, c->f.p, c->f.r, c->f.ap}) CU(cudaMemset(a, 0, ng * 3 * sizeof(double)));
+  for (double *a : {c->f.uj, c->f.gkl, c->f.phi, c->f.p, c->f.p2, c->f.r, c->f.ap}) CU(cudaMemset(a, 0, ng * 3 * sizeof(double)));
   CU(cudaMalloc(&c->rowtmp, (size_t)P.pitch * 2 * 6 * sizeof(double)));
   CU(cudaMalloc(&c->mom, (size_t)7 * (nx + 3) * (nyl + 2) * P.nsp * sizeof(double)));
   CU(cudaMalloc(&c->gcnt, (size_t)P.nsp * P.ncell * sizeof(int)));
@@ -576,7 +593,7 @@ int wm_destroy(wm_ctx *c) {
   }
   for (void *p : {(void *)c->tag, (void *)c->gcnt, (void *)c->tilebase, (void *)c->scan_scratch, (void *)c->sendcnt,
                   (void *)c->recvcnt, (void *)c->in_rank, (void *)c->f.uf, (void *)c->f.df, (void *)c->f.tmpf,
-                  (void *)c->f.uj, (void *)c->f.gkl, (void *)c->f.phi, (void *)c->f.p, (void *)c->f.r, (void *)c->f.ap,
+                  (void *)c->f.uj, (void *)c->f.gkl, (void *)c->f.phi, (void *)c->f.p, (void *)c->f.p2, (void *)c->f.r, (void *)c->f.ap,
                   (void *)c->f.red, (void *)c->f.cgstate, (void *)c->rowtmp, (void *)c->mom, (void *)c->partial,
                   (void *)c->d_err})
     cudaFree(p);
