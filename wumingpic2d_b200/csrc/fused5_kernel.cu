@@ -229,11 +229,9 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
   const int grp = lane >> 3, l8 = lane & 7;
   unsigned below = (1u << l8) - 1u;
   int gsh = grp * 8;
-  size_t cstride = (size_t)P.cap * P.nsp;  // elements between component arrays (carved SoA)
   pin(below);
   pin(gsh);
-  pin(cstride);
-  double *const px = a.src.x;
+  double *const px = a.src.x.p;  // 48-byte records (x y | ux uy | uz id): three 16-byte words each
   const double qf_base = P.delx / P.delt;
   const double delt = P.delt, inv_cc = P.inv_cc, cc = P.cc;
   int myqi = (wid * 4 + grp) * (QCAP * 3);
@@ -322,20 +320,21 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         stage_region(so_slots(P, isp) + cs[c0], so_slots(P, isp) + cs[min(c0 + 4, (lj0 + cy + 1) * P.nx)], &qrec, &qcap);
       }
       int p = beg + l8 + k0;
-      double *pbase = px + (size_t)isp * P.cap;  // slot 0 of this species, component x
+      double2 *pbase = reinterpret_cast<double2 *>(px + 6 * ((size_t)isp * P.cap));  // slot 0 of this species
       pin(pbase);
       __builtin_assume(__isGlobal(pbase));
-      const double *pl = pbase + p;                    // the lane's current particle, component x
+      const double2 *pl = pbase + 3 * (size_t)p;              // the lane's current record
       const int w0 = isp * WIN + (cy + 1) * WINX + (cx + 1);  // this cell in the window of arrival counters
       // the lane's current particle; the next one is loaded into the same registers as soon as the push is done
       double x = 0.0, y = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0, idv = 0.0;
       if (p < end) {
-        x = pl[0];
-        y = pl[cstride];
-        u1 = pl[2 * cstride];
-        u2 = pl[3 * cstride];
-        u3 = pl[4 * cstride];
-        idv = pl[5 * cstride];
+        const double2 r0 = pl[0], r1 = pl[1], r2 = pl[2];
+        x = r0.x;
+        y = r0.y;
+        u1 = r1.x;
+        u2 = r1.y;
+        u3 = r2.x;
+        idv = r2.y;
       }
       {
         // first particle of what this lane works on next: the other species of this cell, then species 0 of the
@@ -343,9 +342,9 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         const bool last = isp + 1 == P.nsp;
         const int pb = last ? nb0 : beg1, pn = last ? nc0 : cnt1;
         if (l8 < pn) {
-          const double *b = px + (last ? (size_t)0 : (size_t)P.cap) + pb + l8;
-#pragma unroll
-          for (int cpt = 0; cpt < 6; cpt++) asm volatile("prefetch.global.L1 [%0];" ::"l"(b + cpt * cstride));
+          const double *b = px + 6 * ((last ? (size_t)0 : (size_t)P.cap) + pb + l8);
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(b));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(b + 5));
         }
       }
       int k = k0;
@@ -413,17 +412,18 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         //      after that one is pulled into L1 by a prefetch hint (no register cost).
         const double idc = idv;
         p += 8;
-        pl += 8;
+        pl += 24;
         if (p < end) {
-          x = pl[0];
-          y = pl[cstride];
-          u1 = pl[2 * cstride];
-          u2 = pl[3 * cstride];
-          u3 = pl[4 * cstride];
-          idv = pl[5 * cstride];
+          const double2 r0 = pl[0], r1 = pl[1], r2 = pl[2];
+          x = r0.x;
+          y = r0.y;
+          u1 = r1.x;
+          u2 = r1.y;
+          u3 = r2.x;
+          idv = r2.y;
           if (PFD > 0) {
-#pragma unroll
-            for (int cpt = 0; cpt < 6; cpt++) asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + cpt * cstride + 8 * PFD));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 * PFD));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 * PFD + 2));
           }
         }
         // stays in its cell as far as the deposit is concerned (before the particle boundary): the comparisons
@@ -503,13 +503,10 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         if (sstay) {
           // stable compaction inside the segment: slot beg + rank among the stayers <= pc
           const int ns = beg + nst + __popc(m8 & below);
-          double *d = pbase + ns;
-          d[0] = xn;
-          d[cstride] = yn;
-          d[2 * cstride] = un1;
-          d[3 * cstride] = un2;
-          d[4 * cstride] = un3;
-          if (ns != pc) d[5 * cstride] = idc;
+          double2 *d = pbase + 3 * (size_t)ns;
+          d[0] = make_double2(xn, yn);
+          d[1] = make_double2(un1, un2);
+          d[2] = make_double2(un3, idc);  // the id moves with the record (bit pattern)
         } else if (active) {
           // cell changer.  |move| < 1 cell (CFL), so the new cell is (gi + incx, gj + incy); anything else
           // is an error (also catches NaN)
@@ -550,7 +547,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
           // this quad; slot order = ballot rank, so the stores of a warp are contiguous
           const int sk = nmv + __popc(balm & ((1u << lane) - 1u));
           if (sk < qcap) {
-            double2 *d = reinterpret_cast<double2 *>(a.dst.x) + (size_t)(qrec + sk) * 4;
+            double2 *d = reinterpret_cast<double2 *>(a.dst.x.p) + (size_t)(qrec + sk) * 4;
             d[0] = make_double2(xn, yn);
             d[1] = make_double2(un1, un2);
             d[2] = make_double2(un3, idc);

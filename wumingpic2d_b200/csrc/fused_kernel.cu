@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
   const int wid = tid >> 5, lane = tid & 31;
   const int grp = lane >> 3, l8 = lane & 7;
   const unsigned below = (1u << l8) - 1u;
-  const size_t cstride = (size_t)P.cap * P.nsp;  // elements between component arrays (carved SoA)
-  double *const px = a.src.x;
+  constexpr size_t cstride = 1;  // components of a record are adjacent (48-byte records)
+  double *const px = a.src.x.p;
   const double qf_base = P.delx / P.delt;
   const double delt = P.delt, inv_cc = P.inv_cc, cc = P.cc;
   const double xlo = (double)P.nxgs, xhi = (double)(P.nxgs + P.nx);
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
       int p = beg + l8;
       double nx_ = 0.0, ny_ = 0.0, nu1 = 0.0, nu2 = 0.0, nu3 = 0.0, nid = 0.0;
       if (p < end) {
-        const double *b = px + so + p;
+        const double *b = px + 6 * (so + p);
         nx_ = b[0];
         ny_ = b[cstride];
         nu1 = b[2 * cstride];
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
         const double x = nx_, y = ny_, u1 = nu1, u2 = nu2, u3 = nu3, idc = nid;
         p += 8;
         if (p < end) {  // prefetch the next particle of this lane
-          const double *b = px + so + p;
+          const double *b = px + 6 * (so + p);
           nx_ = b[0];
           ny_ = b[cstride];
           nu1 = b[2 * cstride];
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
           xn = fma(un1, dtw, x);
           yn = fma(un2, dtw, y);
           if (!INPLACE) {
-            double *b = px + so + pc;
+            double *b = px + 6 * (so + pc);
             b[2 * cstride] = un1;
             b[3 * cstride] = un2;
             b[4 * cstride] = un3;
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
             un2 = -un2;
             un3 = -un3;
             if (!INPLACE) {
-              double *b = px + so + pc;
+              double *b = px + 6 * (so + pc);
               b[2 * cstride] = un1;
               b[3 * cstride] = un2;
               b[4 * cstride] = un3;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
           if (stay) {
             // stable compaction inside the segment: slot beg + rank among the stayers <= pc
             const int ns = beg + nst + __popc(m8 & below);
-            double *d = px + so + ns;
+            double *d = px + 6 * (so + ns);
             d[0] = xn;
             d[cstride] = yn;
             d[2 * cstride] = un1;
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
             // this quad; slot order = ballot rank, so the stores of a warp are contiguous
             const int sk = nmv + __popc(balm & ((1u << lane) - 1u));
             if (sk < qcap) {
-              double2 *d = reinterpret_cast<double2 *>(a.dst.x) + (size_t)(qrec + sk) * 4;
+              double2 *d = reinterpret_cast<double2 *>(a.dst.x.p) + (size_t)(qrec + sk) * 4;
               d[0] = make_double2(xn, yn);
               d[1] = make_double2(un1, un2);
               d[2] = make_double2(un3, idc);
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
               tg = ((uint32_t)((cy + 1) * WINX + (cx + 1)) << TAG_WSHIFT) | (uint32_t)srank;
               if (INPLACE) {
                 // stable compaction inside the segment: slot beg + srank <= pc
-                double *d = px + so + beg + srank;
+                double *d = px + 6 * (so + beg + srank);
                 d[0] = xn;
                 d[cstride] = yn;
                 d[2 * cstride] = un1;
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
               else if (yn >= yhi)
                 yn = __dadd_rd(yn, -P.ylen);
               const bool leaves = (P.nsize > 1) && (j2 < P.nys || j2 >= P.nys + P.nyl);
-              const double idv = INPLACE ? idc : (leaves ? px[so + pc + 5 * cstride] : 0.0);  // id, bit pattern
+              const double idv = INPLACE ? idc : (leaves ? px[6 * (so + pc) + 5] : 0.0);  // id, bit pattern
               if (leaves) {
                 // record goes to the neighbour's edge row        boundary_periodic.f90:156-161,174-189
                 const int dir = (j2 < P.nys) ? 0 : 1;
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
                 // this quad; slot order = ballot rank, so the stores of a warp are contiguous
                 const int sk = nmv + __popc(balm & ((1u << lane) - 1u));
                 if (sk < qcap) {
-                  double2 *d = reinterpret_cast<double2 *>(a.dst.x) + (size_t)(qrec + sk) * 4;
+                  double2 *d = reinterpret_cast<double2 *>(a.dst.x.p) + (size_t)(qrec + sk) * 4;
                   d[0] = make_double2(xn, yn);
                   d[1] = make_double2(un1, un2);
                   d[2] = make_double2(un3, idv);
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
               }
             }
             if (!INPLACE) {
-              double *b = px + so + pc;
+              double *b = px + 6 * (so + pc);
               b[0] = xn;
               b[cstride] = yn;
               a.tag[so + pc] = tg;

@@ -10,10 +10,8 @@ enum { M_PUSH = 1, M_DEPOSIT = 2, M_BOUND = 4, M_EXACT = 8, M_NOMOVE = 16 };
 void launch_pass1(int mode, const DevParams &P, const Pass1Args &a, cudaStream_t st);
 // fused push + deposit + particle boundaries + histogram, FMA arithmetic (fused_kernel.cu)
 void launch_fused(const DevParams &P, const Pass1Args &a, cudaStream_t st);
-// second generation: accumulators split over the 8 lanes of a cell (fused2_kernel.cu)
-void launch_fused2(const DevParams &P, const Pass1Args &a, cudaStream_t st);
 void launch_pass2(const DevParams &P, const PartSoA &src, const PartSoA &dst, const int *cstart_old,
-                  const int *cstart_new, const int *tilebase, const uint32_t *tag, const double *keyx, unsigned *err,
+                  const int *cstart_new, const int *tilebase, const uint32_t *tag, PView<double> keyx, unsigned *err,
                   cudaStream_t st);
 int scan_scratch_ints(int n);
 // exclusive scan of cell_capacity(in[c], sl): sl = 0 gives the tight offsets (cumcnt), sl > 0 the segment offsets
@@ -39,18 +37,14 @@ void launch_incoming_append(const DevParams &P, const double *rec, int n, int is
 // in-place sort: append the records staged by k_fused<INPLACE> to their new segments, retire vacated slots
 void launch_place(const DevParams &P, const double *stage, const PartSoA &dst, const int *cstart, int *cnt_new,
                   const int *tilebase, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err, cudaStream_t st);
-void launch_mark_dead(const DevParams &P, double *x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st);
+void launch_mark_dead(const DevParams &P, PView<double> x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st);
 // fused push + deposit + boundaries that moves cell changers itself (no tags, no scatter pass)
 void launch_fused_inplace(const DevParams &P, const Pass1Args &a, cudaStream_t st);
-// the same, warp-specialised: push warps and deposit warps with different register budgets (fused3_kernel.cu)
-void launch_fused_ws(const DevParams &P, const Pass1Args &a, cudaStream_t st);
-// k_fused<INPLACE> with the deposit of particle k interleaved with the push of particle k+1 (fused4_kernel.cu)
-void launch_fused_pipe(const DevParams &P, const Pass1Args &a, cudaStream_t st);
 // k_fused<INPLACE> with the deposit split into stayers (21 sums, in the loop) and movers (queued, drained per cell) (fused5_kernel.cu)
 void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaStream_t st);
 void launch_kinetic(const DevParams &P, const PartSoA &src, const int *cstart, int isp, double *partial, int nblocks,
                     cudaStream_t st);
-void launch_moments(const DevParams &P, const PartSoA &src, const double *keyx, const int *cstart, double *mom,
+void launch_moments(const DevParams &P, const PartSoA &src, PView<double> keyx, const int *cstart, double *mom,
                     cudaStream_t st);
 
 // ---- fields

@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) k_pass1(const DevParams P, cons
             a.dst.ux[so + p] = un1;
             a.dst.uy[so + p] = un2;
             a.dst.uz[so + p] = un3;
-            if (a.dst.id != a.src.id) a.dst.id[so + p] = a.src.id[so + p];  // particle.f90:171-175
+            if (a.dst.id.p != a.src.id.p) a.dst.id[so + p] = a.src.id[so + p];  // particle.f90:171-175
           } else if (BOUND) {
             a.dst.x[so + p] = xn;
             a.dst.y[so + p] = yn;
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(P1_THREADS, 1) k_pass1(const DevParams P, cons
 __global__ void __launch_bounds__(256) k_pass2(const DevParams P, const PartSoA src, const PartSoA dst,
                                                const int *__restrict__ cstart_old, const int *__restrict__ cstart_new,
                                                const int *__restrict__ tilebase, const uint32_t *__restrict__ tag,
-                                               const double *__restrict__ keyx, unsigned *err) {
+                                               const PView<double> keyx, unsigned *err) {
   __shared__ int s_base[WM_NSP_MAX * 512];  // [isp][kind][256]: indexed by the top 9 bits of a tag
   const int tid = threadIdx.x, tile = blockIdx.x;
   const int li0 = (tile % P.ntx) * TX, lj0 = (tile / P.ntx) * TY;
@@ -610,7 +610,7 @@ __global__ void k_soa2aos(const PartSoA src, size_t so, long long n, double *__r
 
 // stand-alone x wrap (stage mode)                                  boundary_periodic.f90:61-96
 __global__ void k_bcx(const DevParams P, const PartSoA g, const int *__restrict__ cstart) {
-  double *x = g.x;
+  const PView<double> x = g.x;
   for (int isp = 0; isp < P.nsp; isp++) {
     const int n = cstart[(size_t)isp * (P.ncell + 1) + P.ncell];
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(256) k_kinetic(const DevParams P, const PartSo
 }
 
 // moments with bilinear weights (mom_calc.f90:167-249): mom (7, nx+3, nyl+2, nsp), RED.ADD.F64
-__global__ void k_moments(const DevParams P, const PartSoA src, const double *__restrict__ keyx,
+__global__ void k_moments(const DevParams P, const PartSoA src, const PView<double> keyx,
                           const int *__restrict__ cstart, double *mom) {
   for (int isp = 0; isp < P.nsp; isp++) {
     const int n = cstart[(size_t)isp * (P.ncell + 1) + P.ncell];
@@ -921,7 +921,6 @@ __global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const d
   }
   __syncthreads();
   const int total = s_pref[nwin], nstaged = s_off[nreg];
-  const size_t cstride = (size_t)P.cap * P.nsp;
   for (int j0 = 0; j0 < total; j0 += PL_MAX) {
     // where does every staged record go in destination order?  (window cell, rank) -> position
     for (int k = tid; k < nstaged; k += PL_THREADS) {
@@ -953,13 +952,10 @@ __global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const d
       if (s_base[e] < 0) continue;
       const int d = s_base[e] + (int)(t & TAG_RANK_MASK);
       if (d < s_end[e]) {
-        double *o = dst.x + (size_t)isp * P.cap + d;
-        o[0] = r0.x;
-        o[cstride] = r0.y;
-        o[2 * cstride] = r1.x;
-        o[3 * cstride] = r1.y;
-        o[4 * cstride] = r2.x;
-        o[5 * cstride] = r2.y;
+        double2 *o = reinterpret_cast<double2 *>(dst.rec((size_t)isp * P.cap + d));  // 48-byte record, 16-byte aligned
+        o[0] = r0;
+        o[1] = r1;
+        o[2] = r2;
       } else {  // segment full: park the record; the host rebuilds the layout after this step
         const int kk = atomicAdd(ovfcnt, 1);
         if (kk < ovfcap) {
@@ -977,7 +973,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const d
 
 // in-place sort, last step: clamp the new counts to the segment capacity (the surplus is in the
 // overflow list) and retire the slots between the new and the old count
-__global__ void k_mark_dead(const DevParams P, double *x, const int *__restrict__ cstart, const int *__restrict__ cnt_old,
+__global__ void k_mark_dead(const DevParams P, const PView<double> x, const int *__restrict__ cstart, const int *__restrict__ cnt_old,
                             int *cnt_new) {
   const long long n = (long long)P.nsp * P.ncell;
   for (long long wk = (long long)blockIdx.x * blockDim.x + threadIdx.x; wk < n; wk += (long long)gridDim.x * blockDim.x) {
@@ -989,8 +985,8 @@ __global__ void k_mark_dead(const DevParams P, double *x, const int *__restrict_
       nn = capc;
       cnt_new[wk] = nn;
     }
-    double *xs = x + (size_t)isp * P.cap + cs[cell];
-    for (int p = nn; p < cnt_old[wk]; p++) xs[p] = dead_x();
+    const size_t xs = (size_t)isp * P.cap + cs[cell];
+    for (int p = nn; p < cnt_old[wk]; p++) x[xs + p] = dead_x();
   }
 }
 
@@ -1015,7 +1011,7 @@ void launch_pass1(int mode, const DevParams &P, const Pass1Args &a, cudaStream_t
 }
 
 void launch_pass2(const DevParams &P, const PartSoA &src, const PartSoA &dst, const int *cstart_old,
-                  const int *cstart_new, const int *tilebase, const uint32_t *tag, const double *keyx, unsigned *err,
+                  const int *cstart_new, const int *tilebase, const uint32_t *tag, PView<double> keyx, unsigned *err,
                   cudaStream_t st) {
   k_pass2<<<P.ntx * P.nty, 256, 0, st>>>(P, src, dst, cstart_old, cstart_new, tilebase, tag, keyx, err);
 }
@@ -1068,7 +1064,7 @@ void launch_place(const DevParams &P, const double *stage, const PartSoA &dst, c
   k_place<<<P.ntx * P.nty, PL_THREADS, 0, st>>>(P, reinterpret_cast<const double2 *>(stage), dst, cstart, cnt_new, tilebase, ovf,
                                                ovfsp, ovfcnt, ovfcap, err);
 }
-void launch_mark_dead(const DevParams &P, double *x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st) {
+void launch_mark_dead(const DevParams &P, PView<double> x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st) {
   k_mark_dead<<<148 * 16, 256, 0, st>>>(P, x, cstart, cnt_old, cnt_new);
 }
 void launch_bcx(const DevParams &P, const PartSoA &g, const int *cstart, cudaStream_t st) {
@@ -1082,7 +1078,7 @@ void launch_kinetic(const DevParams &P, const PartSoA &src, const int *cstart, i
                     cudaStream_t st) {
   k_kinetic<<<nblocks, 256, 0, st>>>(P, src, cstart, isp, partial);
 }
-void launch_moments(const DevParams &P, const PartSoA &src, const double *keyx, const int *cstart, double *mom,
+void launch_moments(const DevParams &P, const PartSoA &src, PView<double> keyx, const int *cstart, double *mom,
                     cudaStream_t st) {
   k_moments<<<148 * 8, 256, 0, st>>>(P, src, keyx, cstart, mom);
 }

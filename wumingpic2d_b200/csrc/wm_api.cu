@@ -72,8 +72,6 @@ struct wm_ctx {
   bool inplace = true;                   // WM_INPLACE=0 selects the tag + scatter sort for wm_step
   bool cg3 = false;                      // WM_CG3=1: three-kernel CG iteration (k_cg_ap, k_cg_update, k_cg_pupdate)
   int sm = 1;                            // stayer/mover split deposit (k_fused_sm); WM_SM=0 selects k_fused<INPLACE>
-  bool pipe = false;                     // WM_PIPE=1: software-pipelined deposit (k_fused_pipe)
-  bool ws = false;                       // WM_WS=1 selects the warp-specialised k_fused_ws (slower so far: profiles/r01h)
   long long rebuilds = 0;
   int cur = 0;
   int *gcnt = nullptr, *tilebase = nullptr, *scan_scratch = nullptr;
@@ -104,20 +102,18 @@ struct wm_ctx {
   double ms[5] = {0, 0, 0, 0, 0};
   long long launches = 0;
   bool timing = true;
-  int fused_variant = 1;     // WM_FUSED=2 selects k_fused2 (lane-split accumulators; slower so far: profiles/r01c)
   bool accl_valid = false;   // the idle store holds mom_calc__accl's half-step momenta
 };
 
 namespace {
 
-void carve(PartSoA &s, double *base, long long cap, int nsp) {
-  const size_t n = (size_t)cap * nsp;
-  s.x = base;
-  s.y = base + n;
-  s.ux = base + 2 * n;
-  s.uy = base + 3 * n;
-  s.uz = base + 4 * n;
-  s.id = reinterpret_cast<long long *>(base + 5 * n);
+void carve(PartSoA &s, double *base, long long, int) {
+  s.x.p = base;
+  s.y.p = base + 1;
+  s.ux.p = base + 2;
+  s.uy.p = base + 3;
+  s.uz.p = base + 4;
+  s.id.p = reinterpret_cast<long long *>(base + 5);
 }
 
 int alloc_particles(wm_ctx *c, long long need) {
@@ -141,7 +137,7 @@ int alloc_particles(wm_ctx *c, long long need) {
     carve(c->soa[b], c->pbuf[b], cap, nsp);
     CU(cudaMalloc(&c->cstart[b], (size_t)nsp * (c->P.ncell + 1) * sizeof(int)));
     CU(cudaMalloc(&c->cnt[b], (size_t)nsp * c->P.ncell * sizeof(int)));
-    CU(cudaMemset(c->pbuf[b], 0xFF, (size_t)cap * nsp * sizeof(double)));  // x: every slot dead
+    CU(cudaMemset(c->pbuf[b], 0xFF, (size_t)cap * nsp * 6 * sizeof(double)));  // every slot dead (x = all-ones NaN)
   }
   CU(cudaMalloc(&c->cnt_tail, (size_t)nsp * c->P.ncell * sizeof(int)));
   CU(cudaMalloc(&c->tight, (size_t)nsp * (c->P.ncell + 1) * sizeof(int)));
@@ -429,7 +425,7 @@ int scan_tight(wm_ctx *c) {
 }
 
 int fill_dead(wm_ctx *c, int buf) {
-  CU(cudaMemsetAsync(c->soa[buf].x, 0xFF, (size_t)c->P.cap * c->P.nsp * sizeof(double), c->st));
+  CU(cudaMemsetAsync(c->pbuf[buf], 0xFF, (size_t)c->P.cap * c->P.nsp * 6 * sizeof(double), c->st));
   return 0;
 }
 
@@ -473,15 +469,11 @@ int wm_create(const wm_config *g, wm_ctx **out) {
     return fail("wm_create: no CUDA device available (this library has no CPU fallback)");
   wm_ctx *c = new wm_ctx();
   c->cfg = *g;
-  if (const char *v = getenv("WM_FUSED")) c->fused_variant = atoi(v);
   if (const char *v = getenv("WM_SLACK")) c->slack = (float)atof(v);
   if (const char *v = getenv("WM_INPLACE")) c->inplace = atoi(v) != 0;
-  if (const char *v = getenv("WM_WS")) c->ws = atoi(v) != 0;
-  if (const char *v = getenv("WM_PIPE")) c->pipe = atoi(v) != 0;
   if (const char *v = getenv("WM_SM")) c->sm = atoi(v);
   if (const char *v = getenv("WM_CG3")) c->cg3 = atoi(v) != 0;
   if (g->flags & WM_FLAG_EXACT_PUSH) c->inplace = false;  // the exact path keeps the reference's two-pass structure
-  if (g->bc != WM_BC_PERIODIC) c->fused_variant = 1;      // k_fused2 has no wall reflection
   if (g->device >= 0) {
     c->dev = g->device;
   } else {
@@ -982,7 +974,7 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
   const DevParams &P = c->P;
   const size_t ng = (size_t)P.pitch * (P.nyl + 4);
   const int mode = M_PUSH | M_DEPOSIT | M_BOUND | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
-  const bool inplace = c->inplace && !(c->cfg.flags & WM_FLAG_EXACT_PUSH) && c->fused_variant == 1;
+  const bool inplace = c->inplace && !(c->cfg.flags & WM_FLAG_EXACT_PUSH);
   CU(cudaEventRecord(c->ev_call[0], c->st));
   for (int it = 0; it < nsteps; it++) {
     if (c->timing) CU(cudaEventRecord(c->ev[0], c->st));
@@ -995,18 +987,12 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
     if (c->timing) CU(cudaEventRecord(c->ev[1], c->st));
     if (c->cfg.flags & WM_FLAG_EXACT_PUSH)
       launch_pass1(mode, P, p1args(c, a, a, P.delt), c->st);
-    else if (inplace && c->ws)
-      launch_fused_ws(P, p1args(c, a, c->soa[c->cur ^ 1], P.delt), c->st);       // idle store = staging of the cell changers
     else if (inplace && c->sm)
       launch_fused_sm(P, p1args(c, a, c->soa[c->cur ^ 1], P.delt), c->sm, c->st);
-    else if (inplace && c->pipe)
-      launch_fused_pipe(P, p1args(c, a, c->soa[c->cur ^ 1], P.delt), c->st);
     else if (inplace)
       launch_fused_inplace(P, p1args(c, a, c->soa[c->cur ^ 1], P.delt), c->st);
-    else if (c->fused_variant == 1)
-      launch_fused(P, p1args(c, a, a, P.delt), c->st);
     else
-      launch_fused2(P, p1args(c, a, a, P.delt), c->st);
+      launch_fused(P, p1args(c, a, a, P.delt), c->st);
     c->launches += 2;
     if (c->timing) CU(cudaEventRecord(c->ev[2], c->st));
     // rest of field__fdtd_i

@@ -1,7 +1,7 @@
 // wm_internal.h -- device data model shared by the kernels and the C-ABI host layer.
 //
 // Data layout in HBM (one context = one y-slab, rows nys..nye, full x extent):
-//  * particles: SoA per component (x, y, ux, uy, uz, id), species s at offset s*cap,
+//  * particles: 48-byte records (x, y, ux, uy, uz, id), species s at slot offset s*cap,
 //    globally cell-sorted: cell = (j-nys)*nx + (i-nxgs); cell c of species s owns slots
 //    [cstart[s][c], cstart[s][c] + cnt[s][c]); cstart[s][c+1] - cstart[s][c] is the segment's
 //    CAPACITY (count + slack, so that a step only has to move the ~15 % of particles that change
@@ -35,9 +35,18 @@ constexpr int TAG_WSHIFT = 23;
 constexpr uint32_t TAG_ARRIVAL = 0x80000000u;
 constexpr uint32_t TAG_RANK_MASK = (1u << TAG_WSHIFT) - 1u;
 
-struct PartSoA {
-  double *x, *y, *ux, *uy, *uz;
-  long long *id;
+// Particle store: one 48-byte record (x, y, ux, uy, uz, id) per slot, the reference's own record (up(1:6,ii,j,isp),
+// proj/weibel/app.f90:75-76).  A record is three 16-byte words, so the hot kernels move it with three 128-bit loads
+// or stores and one address; PView gives the other kernels component-wise access (element i of one component).
+template <typename T>
+struct PView {
+  T *p;
+  __host__ __device__ __forceinline__ T &operator[](size_t i) const { return p[6 * i]; }
+};
+struct PartSoA {  // (the name predates the record layout)
+  PView<double> x, y, ux, uy, uz;
+  PView<long long> id;
+  __host__ __device__ __forceinline__ double *rec(size_t i) const { return x.p + 6 * i; }
 };
 
 struct DevParams {
