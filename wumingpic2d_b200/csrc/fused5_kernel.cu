@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
   int gsh = grp * 8;
   pin(below);
   pin(gsh);
-  double *const px = a.src.x.p;  // 48-byte records (x y | ux uy | uz id): three 16-byte words each
+  double *const px = a.src.x.p;  // blocks of 8 slots x three 16-byte words (x y | ux uy | uz id), wm_internal.h
   const double qf_base = P.delx / P.delt;
   const double delt = P.delt, inv_cc = P.inv_cc, cc = P.cc;
   int myqi = (wid * 4 + grp) * (QCAP * 3);
@@ -320,21 +320,18 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         stage_region(so_slots(P, isp) + cs[c0], so_slots(P, isp) + cs[min(c0 + 4, (lj0 + cy + 1) * P.nx)], &qrec, &qcap);
       }
       int p = beg + l8 + k0;
-      double2 *pbase = reinterpret_cast<double2 *>(px + 6 * ((size_t)isp * P.cap));  // slot 0 of this species
+      double2 *pbase = reinterpret_cast<double2 *>(px + 6 * ((size_t)isp * P.cap));  // slot 0 of this species (cap % 8 == 0)
       pin(pbase);
       __builtin_assume(__isGlobal(pbase));
-      const double2 *pl = pbase + 3 * (size_t)p;              // the lane's current record
+      const double2 *pl = pbase + pslot_w((size_t)p);        // word 0 of the lane's current slot; + 8, + 16: words 1, 2
       const int w0 = isp * WIN + (cy + 1) * WINX + (cx + 1);  // this cell in the window of arrival counters
-      // the lane's current particle; the next one is loaded into the same registers as soon as the push is done
-      double x = 0.0, y = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0, idv = 0.0;
-      if (p < end) {
-        const double2 r0 = pl[0], r1 = pl[1], r2 = pl[2];
-        x = r0.x;
-        y = r0.y;
-        u1 = r1.x;
-        u2 = r1.y;
-        u3 = r2.x;
-        idv = r2.y;
+      // Latency hiding without registers: the lines of the iterations k + 1 and k + 2 are pulled into L1 by prefetch
+      // hints (PFD iterations ahead in steady state); the loads at the top of iteration k are L1 hits.  Hints for
+      // iteration k0 were issued while the previous species / quad was being worked on.
+      if (p + 8 < end) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 + 8));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 + 16));
       }
       {
         // first particle of what this lane works on next: the other species of this cell, then species 0 of the
@@ -342,9 +339,10 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         const bool last = isp + 1 == P.nsp;
         const int pb = last ? nb0 : beg1, pn = last ? nc0 : cnt1;
         if (l8 < pn) {
-          const double *b = px + 6 * ((last ? (size_t)0 : (size_t)P.cap) + pb + l8);
+          const double2 *b = reinterpret_cast<const double2 *>(px) + pslot_w((last ? (size_t)0 : (size_t)P.cap) + pb + l8);
           asm volatile("prefetch.global.L1 [%0];" ::"l"(b));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(b + 5));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(b + 8));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(b + 16));
         }
       }
       int k = k0;
@@ -354,7 +352,16 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         double xn, yn, un1, un2, un3;
         double hx, hy, dxn, dyn, qvz;
         double sxm, sx0, sxp, sym, sy0, syp;
+        double idc;  // the id moves with the record (bit pattern)
+        if (p + 8 * PFD < end) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 * PFD));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 * PFD + 8));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 * PFD + 16));
+        }
         if (active) {
+          const double2 r0 = pl[0], r1 = pl[8], r2 = pl[16];
+          const double x = r0.x, y = r0.y, u1 = r1.x, u2 = r1.y, u3 = r2.x;
+          idc = r2.y;
           // ---- second order shape function about the sorted cell       particle.f90:97-105
           hx = x - cxh;
           hy = y - cyh;
@@ -407,25 +414,8 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
           dyn = yn - cyh;
           qvz = qs * (un3 * wmove);  // q*gvz, field.f90:270-272,295
         }
-        // ---- the record is consumed: fetch the lane's next particle into the same registers (the id moves with
-        //      the record, bit pattern).  Its latency is covered by the deposit and the sort bookkeeping; the line
-        //      after that one is pulled into L1 by a prefetch hint (no register cost).
-        const double idc = idv;
         p += 8;
         pl += 24;
-        if (p < end) {
-          const double2 r0 = pl[0], r1 = pl[1], r2 = pl[2];
-          x = r0.x;
-          y = r0.y;
-          u1 = r1.x;
-          u2 = r1.y;
-          u3 = r2.x;
-          idv = r2.y;
-          if (PFD > 0) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 * PFD));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 * PFD + 2));
-          }
-        }
         // stays in its cell as far as the deposit is concerned (before the particle boundary): the comparisons
         // int(gp*d_delx) of field.f90:238 makes (positions > 0: truncation == floor; xn - cxh is exact)
         const bool stay = active && dxn >= -0.5 && dxn < 0.5 && dyn >= -0.5 && dyn < 0.5;
@@ -503,10 +493,10 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         if (sstay) {
           // stable compaction inside the segment: slot beg + rank among the stayers <= pc
           const int ns = beg + nst + __popc(m8 & below);
-          double2 *d = pbase + 3 * (size_t)ns;
+          double2 *d = pbase + pslot_w((size_t)ns);
           d[0] = make_double2(xn, yn);
-          d[1] = make_double2(un1, un2);
-          d[2] = make_double2(un3, idc);  // the id moves with the record (bit pattern)
+          d[8] = make_double2(un1, un2);
+          d[16] = make_double2(un3, idc);  // the id moves with the record (bit pattern)
         } else if (active) {
           // cell changer.  |move| < 1 cell (CFL), so the new cell is (gi + incx, gj + incy); anything else
           // is an error (also catches NaN)
@@ -681,15 +671,15 @@ void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaSt
   const bool wall = P.bc != WM_BC_PERIODIC;
   const int grid = P.ntx * P.nty;
   if (variant == 9)
-    k_fused_sm<3, false, false, 1><<<grid, FT, 0, st>>>(P, a);  // timing experiment: movers' current dropped
+    k_fused_sm<3, false, false, 2><<<grid, FT, 0, st>>>(P, a);  // timing experiment: movers' current dropped
   else if (variant == 2)
-    k_fused_sm<2, true, false, 1><<<grid, FT, 0, st>>>(P, a);   // 2 CTAs per SM, up to 255 registers
+    k_fused_sm<2, true, false, 2><<<grid, FT, 0, st>>>(P, a);   // 2 CTAs per SM, up to 255 registers
   else if (variant == 10)
-    k_fused_sm<3, true, false, 0><<<grid, FT, 0, st>>>(P, a);   // without the L1 prefetch hints
+    k_fused_sm<3, true, false, 3><<<grid, FT, 0, st>>>(P, a);   // hints three iterations ahead
   else if (wall)
-    k_fused_sm<3, true, true, 1><<<grid, FT, 0, st>>>(P, a);
+    k_fused_sm<3, true, true, 2><<<grid, FT, 0, st>>>(P, a);
   else
-    k_fused_sm<3, true, false, 1><<<grid, FT, 0, st>>>(P, a);
+    k_fused_sm<3, true, false, 2><<<grid, FT, 0, st>>>(P, a);
 }
 
 }  // namespace wm

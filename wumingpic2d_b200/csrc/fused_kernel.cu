@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
   const int wid = tid >> 5, lane = tid & 31;
   const int grp = lane >> 3, l8 = lane & 7;
   const unsigned below = (1u << l8) - 1u;
-  constexpr size_t cstride = 1;  // components of a record are adjacent (48-byte records)
+  // component offsets of a slot in doubles: x 0, y 1, ux 16, uy 17, uz 32, id 33 (wm_internal.h, PView)
   double *const px = a.src.x.p;
   const double qf_base = P.delx / P.delt;
   const double delt = P.delt, inv_cc = P.inv_cc, cc = P.cc;
@@ -210,13 +210,13 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
       int p = beg + l8;
       double nx_ = 0.0, ny_ = 0.0, nu1 = 0.0, nu2 = 0.0, nu3 = 0.0, nid = 0.0;
       if (p < end) {
-        const double *b = px + 6 * (so + p);
+        const double *b = px + 2 * pslot_w(so + p);
         nx_ = b[0];
-        ny_ = b[cstride];
-        nu1 = b[2 * cstride];
-        nu2 = b[3 * cstride];
-        nu3 = b[4 * cstride];
-        if (INPLACE) nid = b[5 * cstride];
+        ny_ = b[1];
+        nu1 = b[16];
+        nu2 = b[17];
+        nu3 = b[32];
+        if (INPLACE) nid = b[33];
       }
       for (int k = 0; k < nmax; k += 8) {
         const int pc = p;
@@ -224,13 +224,13 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
         const double x = nx_, y = ny_, u1 = nu1, u2 = nu2, u3 = nu3, idc = nid;
         p += 8;
         if (p < end) {  // prefetch the next particle of this lane
-          const double *b = px + 6 * (so + p);
+          const double *b = px + 2 * pslot_w(so + p);
           nx_ = b[0];
-          ny_ = b[cstride];
-          nu1 = b[2 * cstride];
-          nu2 = b[3 * cstride];
-          nu3 = b[4 * cstride];
-          if (INPLACE) nid = b[5 * cstride];  // the id moves with the record (bit pattern)
+          ny_ = b[1];
+          nu1 = b[16];
+          nu2 = b[17];
+          nu3 = b[32];
+          if (INPLACE) nid = b[33];  // the id moves with the record (bit pattern)
         }
         bool stay = false;
         int incx = 0, incy = 0;  // new cell - old cell, from the same comparisons the deposit uses
@@ -284,10 +284,10 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
           xn = fma(un1, dtw, x);
           yn = fma(un2, dtw, y);
           if (!INPLACE) {
-            double *b = px + 6 * (so + pc);
-            b[2 * cstride] = un1;
-            b[3 * cstride] = un2;
-            b[4 * cstride] = un3;
+            double *b = px + 2 * pslot_w(so + pc);
+            b[16] = un1;
+            b[17] = un2;
+            b[32] = un3;
           }
           // ---- new cell relative to the old one (int() truncation == floor: positions > 0)
           const bool xl = xn < di, xr = xn >= di1, yl = yn < dj, yr = yn >= dj1;
@@ -373,10 +373,10 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
             un2 = -un2;
             un3 = -un3;
             if (!INPLACE) {
-              double *b = px + 6 * (so + pc);
-              b[2 * cstride] = un1;
-              b[3 * cstride] = un2;
-              b[4 * cstride] = un3;
+              double *b = px + 2 * pslot_w(so + pc);
+              b[16] = un1;
+              b[17] = un2;
+              b[32] = un3;
             }
             incx = (int)(xn >= di1) - (int)(xn < di);
             stay = (incx | incy) == 0;
@@ -390,13 +390,13 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
           if (stay) {
             // stable compaction inside the segment: slot beg + rank among the stayers <= pc
             const int ns = beg + nst + __popc(m8 & below);
-            double *d = px + 6 * (so + ns);
+            double *d = px + 2 * pslot_w(so + ns);
             d[0] = xn;
-            d[cstride] = yn;
-            d[2 * cstride] = un1;
-            d[3 * cstride] = un2;
-            d[4 * cstride] = un3;
-            if (ns != pc) d[5 * cstride] = idc;
+            d[1] = yn;
+            d[16] = un1;
+            d[17] = un2;
+            d[32] = un3;
+            if (ns != pc) d[33] = idc;
           } else if (active) {
             // cell changer.  |move| < 1 cell (CFL), so the new cell is (gi + incx, gj + incy); anything else
             // is an error (also catches NaN)
@@ -458,13 +458,13 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
               tg = ((uint32_t)((cy + 1) * WINX + (cx + 1)) << TAG_WSHIFT) | (uint32_t)srank;
               if (INPLACE) {
                 // stable compaction inside the segment: slot beg + srank <= pc
-                double *d = px + 6 * (so + beg + srank);
+                double *d = px + 2 * pslot_w(so + beg + srank);
                 d[0] = xn;
-                d[cstride] = yn;
-                d[2 * cstride] = un1;
-                d[3 * cstride] = un2;
-                d[4 * cstride] = un3;
-                if (beg + srank != pc) d[5 * cstride] = idc;
+                d[1] = yn;
+                d[16] = un1;
+                d[17] = un2;
+                d[32] = un3;
+                if (beg + srank != pc) d[33] = idc;
               }
             } else {
               // cell changers: periodic wraps with round-toward -inf adds  boundary_periodic.f90:74,82-88,124,147-154
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
               else if (yn >= yhi)
                 yn = __dadd_rd(yn, -P.ylen);
               const bool leaves = (P.nsize > 1) && (j2 < P.nys || j2 >= P.nys + P.nyl);
-              const double idv = INPLACE ? idc : (leaves ? px[6 * (so + pc) + 5] : 0.0);  // id, bit pattern
+              const double idv = INPLACE ? idc : (leaves ? px[2 * pslot_w(so + pc) + 33] : 0.0);  // id, bit pattern
               if (leaves) {
                 // record goes to the neighbour's edge row        boundary_periodic.f90:156-161,174-189
                 const int dir = (j2 < P.nys) ? 0 : 1;
@@ -522,9 +522,9 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
               }
             }
             if (!INPLACE) {
-              double *b = px + 6 * (so + pc);
+              double *b = px + 2 * pslot_w(so + pc);
               b[0] = xn;
-              b[cstride] = yn;
+              b[1] = yn;
               a.tag[so + pc] = tg;
             }
             nst += __popc(m8);

@@ -952,10 +952,10 @@ __global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const d
       if (s_base[e] < 0) continue;
       const int d = s_base[e] + (int)(t & TAG_RANK_MASK);
       if (d < s_end[e]) {
-        double2 *o = reinterpret_cast<double2 *>(dst.rec((size_t)isp * P.cap + d));  // 48-byte record, 16-byte aligned
+        double2 *o = dst.word((size_t)isp * P.cap + d);  // three 16-byte words of the record, one per 128-byte row
         o[0] = r0;
-        o[1] = r1;
-        o[2] = r2;
+        o[8] = r1;
+        o[16] = r2;
       } else {  // segment full: park the record; the host rebuilds the layout after this step
         const int kk = atomicAdd(ovfcnt, 1);
         if (kk < ovfcap) {

@@ -108,12 +108,13 @@ struct wm_ctx {
 namespace {
 
 void carve(PartSoA &s, double *base, long long, int) {
+  // component offsets inside a block: w0 = (x, y) at 0, w1 = (ux, uy) at 8 words, w2 = (uz, id) at 16 words
   s.x.p = base;
   s.y.p = base + 1;
-  s.ux.p = base + 2;
-  s.uy.p = base + 3;
-  s.uz.p = base + 4;
-  s.id.p = reinterpret_cast<long long *>(base + 5);
+  s.ux.p = base + 16;
+  s.uy.p = base + 17;
+  s.uz.p = base + 32;
+  s.id.p = reinterpret_cast<long long *>(base + 33);
 }
 
 int alloc_particles(wm_ctx *c, long long need) {
@@ -128,7 +129,7 @@ int alloc_particles(wm_ctx *c, long long need) {
   if (cap < need) return fail("wm_config.capacity %lld < particles per species %lld", cap, need);
   while (c->slack > 0.f && bound(c->slack) > (double)cap) c->slack = (c->slack > 0.5f) ? c->slack * 0.5f : 0.f;
   if (c->slack <= 0.f) c->inplace = false;
-  cap = (cap + 3) & ~3LL;
+  cap = (cap + 7) & ~7LL;  // species offsets are whole blocks of the particle store
   if (cap >= (1LL << 31) - 1) return fail("more than 2^31 particles per species per GPU are not supported");
   c->P.cap = cap;
   const int nsp = c->P.nsp;

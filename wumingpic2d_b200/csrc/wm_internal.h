@@ -1,7 +1,7 @@
 // wm_internal.h -- device data model shared by the kernels and the C-ABI host layer.
 //
 // Data layout in HBM (one context = one y-slab, rows nys..nye, full x extent):
-//  * particles: 48-byte records (x, y, ux, uy, uz, id), species s at slot offset s*cap,
+//  * particles: 48-byte records (x, y, ux, uy, uz, id) blocked by 8 slots (see PView), species s at slot offset s*cap,
 //    globally cell-sorted: cell = (j-nys)*nx + (i-nxgs); cell c of species s owns slots
 //    [cstart[s][c], cstart[s][c] + cnt[s][c]); cstart[s][c+1] - cstart[s][c] is the segment's
 //    CAPACITY (count + slack, so that a step only has to move the ~15 % of particles that change
@@ -35,18 +35,24 @@ constexpr int TAG_WSHIFT = 23;
 constexpr uint32_t TAG_ARRIVAL = 0x80000000u;
 constexpr uint32_t TAG_RANK_MASK = (1u << TAG_WSHIFT) - 1u;
 
-// Particle store: one 48-byte record (x, y, ux, uy, uz, id) per slot, the reference's own record (up(1:6,ii,j,isp),
-// proj/weibel/app.f90:75-76).  A record is three 16-byte words, so the hot kernels move it with three 128-bit loads
-// or stores and one address; PView gives the other kernels component-wise access (element i of one component).
+// Particle store: the reference's 48-byte record (x, y, ux, uy, uz, id) = up(1:6,ii,j,isp) (proj/weibel/app.f90:75-76),
+// kept as three 16-byte words w0 = (x, y), w1 = (ux, uy), w2 = (uz, id) and blocked by 8 slots:
+//     block b = slot >> 3 (384 bytes) = [w0 of its 8 slots | w1 of its 8 slots | w2 of its 8 slots]   (3 x 128 bytes)
+// The 8 lanes that work on a cell read 8 consecutive slots with three 128-bit loads, each a full 128-byte line
+// at an immediate offset from one running pointer; consecutive destination slots of the sort are consecutive
+// 16-byte pieces of a line.  PView gives the other kernels component-wise access (element i of one component).
+constexpr int PBLK = 8;  // slots per block
+__host__ __device__ __forceinline__ size_t pslot_w(size_t i) { return (i >> 3) * 24 + (i & 7); }  // in 16-byte words, word 0
 template <typename T>
 struct PView {
-  T *p;
-  __host__ __device__ __forceinline__ T &operator[](size_t i) const { return p[6 * i]; }
+  T *p;  // base + offset of the component inside block 0, slot 0
+  __host__ __device__ __forceinline__ T &operator[](size_t i) const { return p[2 * pslot_w(i)]; }
 };
-struct PartSoA {  // (the name predates the record layout)
+struct PartSoA {  // (the name predates the blocked record layout)
   PView<double> x, y, ux, uy, uz;
   PView<long long> id;
-  __host__ __device__ __forceinline__ double *rec(size_t i) const { return x.p + 6 * i; }
+  // word w (0..2) of slot i as a 16-byte pointer: word(i)[8 * w]
+  __host__ __device__ __forceinline__ double2 *word(size_t i) const { return reinterpret_cast<double2 *>(x.p) + pslot_w(i); }
 };
 
 struct DevParams {
@@ -82,7 +88,7 @@ enum : unsigned {
 // change of a Poisson count between two layout rebuilds; sl = 0 -> tight
 __host__ __device__ inline int cell_capacity(int n, float sl) {
   if (sl <= 0.f) return n;
-  return (n + 4 + (int)ceilf(sl * sqrtf(2.0f * (float)n)) + 3) & ~3;
+  return (n + 4 + (int)ceilf(sl * sqrtf(2.0f * (float)n)) + 7) & ~7;  // whole blocks: a cell's 8 lanes read one 128-byte line per word
 }
 
 struct Pass1Args {
