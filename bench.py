@@ -252,14 +252,20 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     achieved = ALG_BYTES_PASS1 * n_local / (ms_pass1 * 1e-3) / 1e9
-    traffic = None
+    # dram__bytes_read.sum + dram__bytes_write.sum and the FP64 pipe utilisation of the same kernel, from the committed
+    # `ncu --set full` capture of this workload (profiles/pass1_traffic.json names the report it was read from)
+    traffic, fp64_pipe = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "pass1_traffic.json"))).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "pass1_traffic.json")))
+        if (nx, rows, ppc) == (tj.get("nx"), tj.get("rows"), tj.get("ppc")) and not args.exact:
+            traffic = tj.get("dram_bytes_per_launch")
+        fp64_pipe = tj.get("fp64_pipe_pct_of_peak")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_pass1<PUSH|DEPOSIT|BOUND> (exact)" if args.exact else "k_fused<INPLACE> (push + Esirkepov deposit + particle boundaries + in-place cell sort of the stayers, one pass)",
+    roofline = {"bound": "hbm", "kernel": "k_pass1<PUSH|DEPOSIT|BOUND> (exact)" if args.exact else ("k_fused_sm (push + Esirkepov deposit split into stayers/movers + particle boundaries + in-place cell sort of the stayers, one pass)" if os.environ.get("WM_SM", "1") != "0" else "k_fused<INPLACE>"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_kind, "alg_bytes_per_particle": ALG_BYTES_PASS1, "ms_per_launch": ms_pass1,
+                "fp64_pipe_pct_of_peak_ncu": fp64_pipe,
                 "whole_step": {"alg_bytes_per_particle_step": ALG_BYTES_STEP,
                                "achieved": ALG_BYTES_STEP * n_local / (allmax(ms[4]) / args.steps * 1e-3) / 1e9,
                                "frac": ALG_BYTES_STEP * n_local / (allmax(ms[4]) / args.steps * 1e-3) / 1e9 / peak}}

@@ -92,6 +92,8 @@ struct wm_ctx {
   unsigned *d_err = nullptr, *h_err = nullptr;
   int *h_cg = nullptr;       // pinned copies of CgCtl {active[3], ite[3], stop} x 2
   cudaEvent_t ev_cg[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_b[2] = {nullptr, nullptr};  // sort on st2 beside the field solve
+  bool overlap = true;                   // WM_OVERLAP=0: everything on one stream
   int cg_ite[3] = {0, 0, 0};
   // comm
   ncclComm_t comm = nullptr;
@@ -474,6 +476,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   if (const char *v = getenv("WM_INPLACE")) c->inplace = atoi(v) != 0;
   if (const char *v = getenv("WM_SM")) c->sm = atoi(v);
   if (const char *v = getenv("WM_CG3")) c->cg3 = atoi(v) != 0;
+  if (const char *v = getenv("WM_OVERLAP")) c->overlap = atoi(v) != 0;
   if (g->flags & WM_FLAG_EXACT_PUSH) c->inplace = false;  // the exact path keeps the reference's two-pass structure
   if (g->device >= 0) {
     c->dev = g->device;
@@ -532,8 +535,14 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   c->nup = (g->nrank == g->nsize - 1) ? 0 : g->nrank + 1;   // mpi_set.f90:44-47
   c->ndown = (g->nrank == 0) ? g->nsize - 1 : g->nrank - 1;
 
-  CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+  {
+    // the main stream outranks the second one: when the sort tail (k_place, thousands of CTAs) runs beside the
+    // field solve (many small kernels), the field kernels get their SM slots first and k_place fills the rest
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, hi));
+    CU(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, lo));
+  }
   const size_t ng = (size_t)P.pitch * (nyl + 4);
   CU(cudaMalloc(&c->f.uf, ng * 6 * sizeof(double)));
   CU(cudaMalloc(&c->f.df, ng * 6 * sizeof(double)));
@@ -567,6 +576,9 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   CU(cudaMemset(c->sendcnt, 0, 2 * WM_NSP_MAX * sizeof(int)));
   for (auto &e : c->ev_cg) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : c->ev) CU(cudaEventCreate(&e));
+  for (auto &e : c->ev_b) CU(cudaEventCreate(&e));
+  CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (auto &e : c->ev_call) CU(cudaEventCreate(&e));
   *out = c;
   return 0;
@@ -996,10 +1008,30 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
       launch_fused(P, p1args(c, a, a, P.delt), c->st);
     c->launches += 2;
     if (c->timing) CU(cudaEventRecord(c->ev[2], c->st));
-    // rest of field__fdtd_i
-    WM(field_solve(c));
-    if (c->timing) CU(cudaEventRecord(c->ev[3], c->st));
-    if (inplace) {
+    if (inplace && c->overlap) {
+      // The rest of the sort (migration, k_place, k_mark_dead) only needs what the fused pass left behind, the rest
+      // of field__fdtd_i only needs uj: the two run side by side, the sort on the second stream.  (NCCL calls stay
+      // on the main stream, in program order.)
+      WM(migrate(c, true));  // ring exchange of the leavers; arrivals are appended to their segments
+      CU(cudaEventRecord(c->ev_fork, c->st));
+      CU(cudaStreamWaitEvent(c->st2, c->ev_fork, 0));
+      if (c->timing) CU(cudaEventRecord(c->ev_b[0], c->st2));
+      launch_place(P, c->pbuf[c->cur ^ 1], a, c->cstart[c->cur], c->cnt_tail, c->tilebase, c->ovf, c->ovfsp, c->ovfcnt,
+                   c->ovfcap, c->d_err, c->st2);
+      launch_mark_dead(P, a.x, c->cstart[c->cur], c->cnt[c->cur], c->cnt_tail, c->st2);
+      c->launches += 2;
+      std::swap(c->cnt[c->cur], c->cnt_tail);  // cnt_tail held the new counts
+      CU(cudaMemcpyAsync(c->h_ovf, c->ovfcnt, sizeof(int), cudaMemcpyDeviceToHost, c->st2));
+      if (c->timing) CU(cudaEventRecord(c->ev_b[1], c->st2));
+      CU(cudaEventRecord(c->ev_join, c->st2));
+      if (c->timing) CU(cudaEventRecord(c->ev[3], c->st));  // (ev[2], ev[3]) = migration
+      WM(field_solve(c));
+      if (c->timing) CU(cudaEventRecord(c->ev[4], c->st));  // (ev[3], ev[4]) = field solve, k_place running beside it
+      CU(cudaStreamWaitEvent(c->st, c->ev_join, 0));
+    } else if (inplace) {
+      // rest of field__fdtd_i
+      WM(field_solve(c));
+      if (c->timing) CU(cudaEventRecord(c->ev[3], c->st));
       // ring exchange of the leavers; arrivals are appended to their segments
       WM(migrate(c, true));
       if (c->timing) CU(cudaEventRecord(c->ev[4], c->st));
@@ -1011,6 +1043,9 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
       std::swap(c->cnt[c->cur], c->cnt_tail);  // cnt_tail held the new counts
       CU(cudaMemcpyAsync(c->h_ovf, c->ovfcnt, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     } else {
+      // rest of field__fdtd_i
+      WM(field_solve(c));
+      if (c->timing) CU(cudaEventRecord(c->ev[3], c->st));
       // migration, prefix scan
       WM(migrate(c));
       const int dst = c->cur ^ 1;
@@ -1029,9 +1064,17 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
       float t[5];
       for (int k = 0; k < 5; k++) CU(cudaEventElapsedTime(&t[k], c->ev[k], c->ev[k + 1]));
       c->ms[0] += t[1];
-      c->ms[1] += t[2];
-      c->ms[2] += t[0] + t[3];
-      c->ms[3] += t[4];
+      if (inplace && c->overlap) {
+        float tb;
+        CU(cudaEventElapsedTime(&tb, c->ev_b[0], c->ev_b[1]));
+        c->ms[1] += t[3];         // field solve
+        c->ms[2] += t[0] + t[2];  // prep + migration
+        c->ms[3] += tb;           // k_place + k_mark_dead, overlapped with the field solve
+      } else {
+        c->ms[1] += t[2];
+        c->ms[2] += t[0] + t[3];
+        c->ms[3] += t[4];
+      }
     }
     if (inplace && *c->h_ovf > 0) WM(rebuild_layout(c, *c->h_ovf));
   }
