@@ -277,11 +277,13 @@ def test_call_order_is_enforced(warm):
     c.close()
 
 
-@pytest.mark.parametrize("env", [{"WM_INPLACE": "0"}, {"WM_SLACK": "0.4"}, {"WM_SLACK": "12"}, {"WM_FUSED": "2"}])
+@pytest.mark.parametrize("env", [{"WM_INPLACE": "0"}, {"WM_SLACK": "0.4"}, {"WM_SLACK": "12"}, {"WM_SM": "0"},
+                                 {"WM_CG3": "1"}, {"WM_OVERLAP": "0"}])
 def test_sort_variants_match_oracle(env, monkeypatch):
     """wm_step with (a) the tag + scatter sort, (b) the in-place sort with so little segment slack that
-    segments overflow and the layout is rebuilt nearly every step, (c) generous slack, (d) k_fused2:
-    per-cell counts bit-exact and particles/fields within tolerance in every case."""
+    segments overflow and the layout is rebuilt nearly every step, (c) generous slack, (d) k_fused<INPLACE> (65
+    register sums per lane) instead of k_fused_sm, (e) the three-kernel CG iteration, (f) everything on one
+    stream: per-cell counts bit-exact and particles/fields within tolerance in every case."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     prm, w = make_world(40, 24, 16)
@@ -301,6 +303,32 @@ def test_sort_variants_match_oracle(env, monkeypatch):
         assert rel_to_max(c.download_field(), w.array(0, O.UF)).max() <= 1e-9
     if env.get("WM_SLACK") == "0.4":
         assert c.rebuilds() > 0, "the overflow -> rebuild path was not exercised"
+    c.close()
+
+
+def test_dense_cells_drain_early():
+    """k_fused_sm queues the movers of a cell (40 slots per cell) and drains the queue when the cell is done.  With
+    200 particles per cell per species about 60 particles per cell change cell in a step, so the queue is drained
+    early and the particle loop re-entered several times per cell: J (hence E, B) and the particles must still
+    match the oracle, and the discrete Gauss law must hold."""
+    prm, w = make_world(24, 16, 200)
+    s = oracle_state(w)
+    c = ctx_for(prm)
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    c.upload_field(s["uf"])
+    for it in range(3):
+        w.step(1)
+        c.step(1)
+        assert c.cg_iters() == w.cg_iters()
+        tol = TOL if it == 0 else 1e-10
+        assert rel_to_max(c.download_current(), w.array(0, O.UJ)).max() <= tol
+        assert rel_to_max(c.download_field(), w.array(0, O.UF)).max() <= tol
+        up, np2, cum = c.download_particles()
+        assert np.array_equal(cum, w.array(0, O.CUMCNT)), "per-cell counts must be bit-exact"
+        a, b = flatten_by_id(up, np2), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
+        assert np.array_equal(a[0], b[0])
+        ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+        assert ex <= tol and eu <= tol
     c.close()
 
 
