@@ -21,7 +21,7 @@ module wm_cabi
   public
 
   integer(c_int), parameter :: WM_NSP_MAX = 2
-  integer(c_int), parameter :: WM_BC_PERIODIC = 0, WM_BC_RECONNECTION = 1
+  integer(c_int), parameter :: WM_BC_PERIODIC = 0, WM_BC_RECONNECTION = 1, WM_BC_SHOCK = 2
   integer(c_int), parameter :: WM_FLAG_EXACT_PUSH = 1
 
   !> mirrors `struct wm_config` of include/wumingpic2d.h member by member
@@ -119,6 +119,18 @@ module wm_cabi
        type(c_ptr), value :: ctx
        integer(c_int) :: ierr
      end function wm_boundary__particle_x
+     function wm_boundary__injection(ctx, u0) bind(C, name='wm_boundary__injection') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value    :: ctx
+       real(c_double), value :: u0
+       integer(c_int)        :: ierr
+     end function wm_boundary__injection
+     function wm_set_u_inject(ctx, u0) bind(C, name='wm_set_u_inject') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value    :: ctx
+       real(c_double), value :: u0
+       integer(c_int)        :: ierr
+     end function wm_set_u_inject
      function wm_boundary__particle_y(ctx) bind(C, name='wm_boundary__particle_y') result(ierr)
        import :: c_int, c_ptr
        type(c_ptr), value :: ctx

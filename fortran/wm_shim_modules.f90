@@ -302,3 +302,89 @@ contains
   end subroutine boundary_reconnection__mom
 
 end module boundary_reconnection
+
+
+!> proj/shock/boundary_shock.f90 (reflecting wall on the left, injection wall on the right, periodic y).
+!! The app selects it by `use boundary_shock, bc__init => boundary_shock__init, bc__injection => ...`
+!! (proj/shock/app.f90:6-14).  The device library implements the fixed box nxs = nxgs, nxe = nxge: the driver's
+!! `relocate` (proj/shock/app.f90:611-680), which moves nxe and appends particles to the host arrays, is not
+!! supported yet (DESIGN.md section 7).
+module boundary_shock
+  use wm_cabi
+  implicit none
+  private
+  public :: boundary_shock__init
+  public :: boundary_shock__dfield, boundary_shock__particle_x, boundary_shock__particle_y
+  public :: boundary_shock__injection
+  public :: boundary_shock__curre, boundary_shock__phi, boundary_shock__mom
+contains
+
+  subroutine boundary_shock__init(ndim_in,np_in,nsp_in,nxgs_in,nxge_in,nygs_in,nyge_in,nys_in,nye_in, &
+                            nup_in,ndown_in,mnpi_in,mnpr_in,ncomw_in,nerr_in,nstat_in,          &
+                            delx_in,delt_in,c_in)
+    use mpi
+    integer, intent(in) :: ndim_in, np_in, nsp_in
+    integer, intent(in) :: nxgs_in, nxge_in, nygs_in, nyge_in, nys_in, nye_in
+    integer, intent(in) :: nup_in, ndown_in, mnpi_in, mnpr_in, ncomw_in, nerr_in, nstat_in(:)
+    real(8), intent(in) :: delx_in, delt_in, c_in
+    integer :: nerr, nrank, nsize
+    call MPI_COMM_RANK(ncomw_in, nrank, nerr)
+    call MPI_COMM_SIZE(ncomw_in, nsize, nerr)
+    cfg%nrank = nrank; cfg%nsize = nsize
+    comm_world = ncomw_in
+    bc_kind = WM_BC_SHOCK
+    have_ring = .true.
+    call wm_shim__try_create()
+  end subroutine boundary_shock__init
+
+  subroutine boundary_shock__particle_x(up,np2,nxs,nxe)
+    integer, intent(in)    :: nxs, nxe
+    integer, intent(in)    :: np2(cfg%nys:cfg%nye,cfg%nsp)
+    real(8), intent(inout) :: up(cfg%ndim,cfg%np,cfg%nys:cfg%nye,cfg%nsp)
+    if (nxs /= cfg%nxgs .or. nxe /= cfg%nxge) then
+       write(6,*) 'boundary_shock__particle_x: nxs/nxe must equal nxgs/nxge'
+       stop
+    end if
+    call wm_check(wm_boundary__particle_x(ctx), 'boundary_shock__particle_x')
+  end subroutine boundary_shock__particle_x
+
+  subroutine boundary_shock__particle_y(up,np2)
+    integer, intent(inout) :: np2(cfg%nys:cfg%nye,cfg%nsp)
+    real(8), intent(inout) :: up(cfg%ndim,cfg%np,cfg%nys:cfg%nye,cfg%nsp)
+    call wm_check(wm_boundary__particle_y(ctx), 'boundary_shock__particle_y')
+  end subroutine boundary_shock__particle_y
+
+  !> bc__injection(gp,np2,nxs,nxe,u0), called between particle__solv and field__fdtd_i (proj/shock/app.f90:112-113)
+  subroutine boundary_shock__injection(up,np2,nxs,nxe,u0)
+    integer, intent(in)    :: nxs, nxe
+    integer, intent(in)    :: np2(cfg%nys:cfg%nye,cfg%nsp)
+    real(8), intent(inout) :: up(cfg%ndim,cfg%np,cfg%nys:cfg%nye,cfg%nsp)
+    real(8), intent(in)    :: u0
+    if (nxs /= cfg%nxgs .or. nxe /= cfg%nxge) then
+       write(6,*) 'boundary_shock__injection: a moving nxe (relocate) is not supported by the device library yet'
+       stop
+    end if
+    call wm_check(wm_boundary__injection(ctx, u0), 'boundary_shock__injection')
+  end subroutine boundary_shock__injection
+
+  subroutine boundary_shock__dfield(df,nxs,nxe,nys,nye,nxgs,nxge)
+    integer, intent(in)    :: nxs, nxe, nys, nye, nxgs, nxge
+    real(8), intent(inout) :: df(6,nxgs-2:nxge+2,nys-2:nye+2)
+  end subroutine boundary_shock__dfield
+
+  subroutine boundary_shock__curre(uj,nxs,nxe,nys,nye,nxgs,nxge)
+    integer, intent(in)    :: nxs, nxe, nys, nye, nxgs, nxge
+    real(8), intent(inout) :: uj(3,nxgs-2:nxge+2,nys-2:nye+2)
+  end subroutine boundary_shock__curre
+
+  subroutine boundary_shock__phi(phi,nxs,nxe,nys,nye,l)
+    integer, intent(in)    :: nxs, nxe, nys, nye, l
+    real(8), intent(inout) :: phi(nxs-1:nxe+1,nys-1:nye+1)
+  end subroutine boundary_shock__phi
+
+  subroutine boundary_shock__mom(mom)
+    real(8), intent(inout) :: mom(7,cfg%nxgs-1:cfg%nxge+1,cfg%nys-1:cfg%nye+1,cfg%nsp)
+    call wm_check(wm_boundary__mom(ctx, mom), 'boundary_shock__mom')
+  end subroutine boundary_shock__mom
+
+end module boundary_shock

@@ -40,9 +40,13 @@ extern "C" {
 /* boundary plugin (the module chosen by `use ... => bc__*` in proj/<problem>/app.f90:6-13) */
 enum {
   WM_BC_PERIODIC = 0,      /* common/boundary_periodic.f90 (proj/weibel)                                         */
-  WM_BC_RECONNECTION = 1   /* proj/reconnection/boundary_reconnection.f90: reflecting particles / conducting     */
+  WM_BC_RECONNECTION = 1,  /* proj/reconnection/boundary_reconnection.f90: reflecting particles / conducting     */
                            /* fields at the x walls nxs+1, nxe-1; periodic y                                     */
-  /* proj/shock/boundary_shock.f90 (moving injection wall, nxe changes in time) is not implemented yet          */
+  WM_BC_SHOCK = 2          /* proj/shock/boundary_shock.f90: reflecting left wall, injection wall at             */
+                           /* xend = nxe*delx + v0*delt on the right (bc__injection, applied BEFORE the field    */
+                           /* solve: proj/shock/app.f90:112-113), df = 0 in the right ghost column; periodic y.   */
+                           /* The box is the full range nxgs..nxge (the driver's `relocate`, which moves nxe,    */
+                           /* is not supported yet).  wm_step needs wm_set_u_inject first.                       */
 };
 
 /* flags */
@@ -113,6 +117,10 @@ int wm_boundary__curre(wm_ctx *ctx);       /* bc__curre       common/boundary_pe
 int wm_field__fdtd_i(wm_ctx *ctx);         /* field__fdtd_i   common/field.f90:66 (incl. ele_cur, bc__curre, cgm, bc__dfield) */
 int wm_boundary__particle_x(wm_ctx *ctx);  /* bc__particle_x  common/boundary_periodic.f90:61 */
 int wm_boundary__particle_y(wm_ctx *ctx);  /* bc__particle_y  common/boundary_periodic.f90:99 */
+/* bc__injection(gp,np2,nxs,nxe,u0)  proj/shock/boundary_shock.f90:255 (WM_BC_SHOCK; on the pushed store, before
+ * wm_field__fdtd_i).  Also records u0 for wm_step, like wm_set_u_inject. */
+int wm_boundary__injection(wm_ctx *ctx, double u0);
+int wm_set_u_inject(wm_ctx *ctx, double u0);
 int wm_sort__bucket(wm_ctx *ctx);          /* sort__bucket    common/sort.f90:36             */
 /* the five calls above fused: push + deposit + particle boundaries in one kernel,
  * then the field solve, then the scatter pass (proj/weibel/app.f90:100-107) */

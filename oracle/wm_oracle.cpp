@@ -62,6 +62,7 @@ struct orc_world {
   std::vector<Rank> R;
   int cg_ite[3];
   double t_stage[5];
+  double u_inject = 0.0;  // u0 of bc__injection (proj/shock/app.f90:113)
 };
 
 namespace {
@@ -421,6 +422,19 @@ void bc_dfield(orc_world *w) {
       }
     }
   }
+  if (w->c.bc == ORC_BC_SHOCK) {
+    // conducting wall on the left, zero on the right  (proj/shock/boundary_shock.f90:396-405)
+    for (Rank &k : w->R) {
+      V v{w, &k};
+      for (int j = k.nys - 2; j <= k.nye + 2; j++) {
+        k.df[v.F6(1, nxs - 1, j)] = -k.df[v.F6(1, nxs, j)];
+        for (int cidx = 2; cidx <= 4; cidx++) k.df[v.F6(cidx, nxs - 1, j)] = k.df[v.F6(cidx, nxs + 1, j)];
+        for (int cidx = 5; cidx <= 6; cidx++) k.df[v.F6(cidx, nxs - 1, j)] = -k.df[v.F6(cidx, nxs, j)];
+        for (int cidx = 1; cidx <= 6; cidx++) k.df[v.F6(cidx, nxe + 1, j)] = 0.0;
+      }
+    }
+    return;
+  }
   if (w->c.bc == ORC_BC_RECONNECTION) {
     // conducting walls: odd / even mirror  (proj/reconnection/boundary_reconnection.f90:349-359)
     for (Rank &k : w->R) {
@@ -475,9 +489,9 @@ void bc_phi(orc_world *w, int which, int l) {
     V v{w, &k};
     for (int i = nxs; i <= nxe; i++) arr(k)[v.PH(i, k.nys - 1)] = snd[k.ndown][i - nxs];
   }
-  if (w->c.bc == ORC_BC_RECONNECTION) {
+  if (w->c.bc != ORC_BC_PERIODIC) {
     // l = 1 (Bx) odd, l = 2,3 even at the left wall; zero at the right wall
-    // (proj/reconnection/boundary_reconnection.f90:557-577)
+    // (proj/reconnection/boundary_reconnection.f90:557-577, proj/shock/boundary_shock.f90:603-623)
     for (Rank &k : w->R) {
       V v{w, &k};
       for (int j = k.nys - 1; j <= k.nye + 1; j++) {
@@ -500,8 +514,9 @@ void bc_phi(orc_world *w, int which, int l) {
 void bc_particle_x(orc_world *w) {
   const int nxgs = w->nxgs, nxge = w->nxge;
   const double delx = w->delx;
-  if (w->c.bc == ORC_BC_RECONNECTION) {
-    // reflecting walls at nxs+1 and nxe-1  (proj/reconnection/boundary_reconnection.f90:61-99)
+  if (w->c.bc != ORC_BC_PERIODIC) {
+    // reflecting walls at nxs+1 and nxe-1  (proj/reconnection/boundary_reconnection.f90:61-99,
+    // proj/shock/boundary_shock.f90:62-100)
     const int nxs = w->nxs, nxe = w->nxe;
     for (Rank &k : w->R) {
       V v{w, &k};
@@ -987,7 +1002,7 @@ extern "C" {
 
 orc_world *orc_create(const orc_config *cfg) {
   if (cfg->nsp < 1 || cfg->nsp > ORC_NSP_MAX || cfg->nranks < 1 || cfg->ny < cfg->nranks) return nullptr;
-  if (cfg->bc != ORC_BC_PERIODIC && cfg->bc != ORC_BC_RECONNECTION) return nullptr;
+  if (cfg->bc != ORC_BC_PERIODIC && cfg->bc != ORC_BC_RECONNECTION && cfg->bc != ORC_BC_SHOCK) return nullptr;
   orc_world *w = new orc_world();
   w->c = *cfg;
   w->nx = cfg->nx;
@@ -1088,6 +1103,44 @@ void orc_ele_cur(orc_world *w) {
 void orc_bc_curre(orc_world *w) { bc_curre(w); }
 int orc_field_fdtd_i(orc_world *w) { return field_fdtd_i(w); }
 void orc_bc_particle_x(orc_world *w) { bc_particle_x(w); }
+
+// boundary_shock__injection, on gp                          proj/shock/boundary_shock.f90:255-297
+void orc_bc_injection(orc_world *w, double u0) {
+  const int nxs = w->nxs, nxe = w->nxe;
+  const double delx = w->delx, c = std::sqrt(w->cc);
+  w->u_inject = u0;
+  const double xend = nxe * delx + u0 / std::sqrt(1 + (u0 * u0) / (c * c)) * w->delt;
+  for (Rank &k : w->R) {
+    V v{w, &k};
+    for (int isp = 1; isp <= w->nsp; isp++) {
+#pragma omp parallel for
+      for (int j = k.nys; j <= k.nye; j++)
+        for (int ii = 1; ii <= k.np2[v.NP2(j, isp)]; ii++) {
+          double *r = &k.gp[v.UP(1, ii, j, isp)];
+          const int ipos = (int)(r[0] / delx);
+          if (ipos < nxs + 1) {
+            r[0] = +2. * (nxs + 1) * delx - r[0];
+            r[2] = -r[2];
+            r[3] = -r[3];
+            r[4] = -r[4];
+          } else if (r[0] > xend) {
+            r[0] = +2. * xend - r[0];
+            r[2] = +2. * u0 - r[2];
+            r[3] = -r[3];
+            r[4] = -r[4];
+          }
+        }
+    }
+  }
+}
+void orc_set_u_inject(orc_world *w, double u0) { w->u_inject = u0; }
+// the active x range [nxs, nxe] of the shock app (proj/shock/app.f90:611-621 `relocate` moves nxe)
+int orc_set_xrange(orc_world *w, int nxs, int nxe) {
+  if (nxs < w->nxgs || nxe > w->nxge || nxe - nxs < 4) return 1;
+  w->nxs = nxs;
+  w->nxe = nxe;
+  return 0;
+}
 int orc_bc_particle_y(orc_world *w) { return bc_particle_y(w); }
 void orc_sort_bucket(orc_world *w) { sort_bucket(w); }
 
@@ -1096,9 +1149,10 @@ int orc_step(orc_world *w, int nsteps) {
     double t0 = now();
     orc_particle_solv(w);
     double t1 = now();
+    if (w->c.bc == ORC_BC_SHOCK) orc_bc_injection(w, w->u_inject);  // proj/shock/app.f90:112-113: before the field solve
     if (field_fdtd_i(w)) return 1;
     double t2 = now();
-    bc_particle_x(w);
+    if (w->c.bc != ORC_BC_SHOCK) bc_particle_x(w);
     double t3 = now();
     const int e = bc_particle_y(w);
     if (e) return 10 + e;

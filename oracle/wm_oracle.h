@@ -37,8 +37,10 @@ extern "C" {
 /* boundary kinds (the "plugin" chosen by use-renaming in proj/<problem>/app.f90:6-13) */
 enum {
   ORC_BC_PERIODIC = 0,      /* common/boundary_periodic.f90 (weibel)                                        */
-  ORC_BC_RECONNECTION = 1   /* proj/reconnection/boundary_reconnection.f90: conducting/reflecting x walls,   */
+  ORC_BC_RECONNECTION = 1,  /* proj/reconnection/boundary_reconnection.f90: conducting/reflecting x walls,   */
                             /* periodic y                                                                     */
+  ORC_BC_SHOCK = 2          /* proj/shock/boundary_shock.f90: reflecting left wall, injection wall on the    */
+                            /* right (bc__injection before the field solve), active x range [nxs, nxe]       */
 };
 
 typedef struct orc_config {
@@ -72,6 +74,9 @@ void orc_ele_cur(orc_world *w);         /* uj <- deposit(up, gp)        common/f
 void orc_bc_curre(orc_world *w);        /* uj fold + halo               boundary_periodic.f90:357  */
 int  orc_field_fdtd_i(orc_world *w);    /* full field solve; 0 ok, 1 = CG hit ite_max (field.f90:427) */
 void orc_bc_particle_x(orc_world *w);   /* on gp                        boundary_periodic.f90:61   */
+void orc_bc_injection(orc_world *w, double u0); /* on gp            proj/shock/boundary_shock.f90:255  */
+void orc_set_u_inject(orc_world *w, double u0); /* u0 used by orc_step (proj/shock/app.f90:113)           */
+int  orc_set_xrange(orc_world *w, int nxs, int nxe); /* active x range of the shock app; 0 = ok         */
 int  orc_bc_particle_y(orc_world *w);   /* on gp; 1 = row overflow      boundary_periodic.f90:99   */
 void orc_sort_bucket(orc_world *w);     /* up <- sort(gp), cumcnt       common/sort.f90:36         */
 int  orc_step(orc_world *w, int nsteps);/* the 5 calls above in order                               */

@@ -86,3 +86,41 @@ def make_wall_world(nx, ny, ppc, nranks=1, steps=0, seed=7, b0=0.02, **kw):
     if steps:
         w.step(steps)
     return prm, w
+
+
+def make_shock_world(nx, ny, ppc, u0=-0.3, nranks=1, seed=11, b0=0.02, **kw):
+    """A shock-type world (proj/shock: reflecting wall on the left, injection wall at xend on the right, periodic
+    y): a neutral plasma that drifts toward the left wall with four-velocity u0 < 0 in a uniform By, Ez = v0 By
+    (the upstream state of proj/shock/app.f90:400-470, without the driver's per-step injection of new
+    particles).  The IC is written into gp and bucket-sorted by the oracle."""
+    prm = O.weibel_params(nx, ny, ppc, nranks=nranks, **kw)
+    prm["bc"] = O.BC_SHOCK
+    prm["u0"] = u0
+    w = O.World(prm)
+    w.set_u_inject(u0)
+    nxgs, nygs = prm["nxgs"], prm["nygs"]
+    v0 = u0 / np.sqrt(1 + u0 * u0 / prm["c"] ** 2)
+    xlo, xhi = nxgs + 1, nxgs + nx - 2          # particles live in cells nxs+1 .. nxe-1 (nxe = nxgs+nx-1)
+    npr = ppc * (xhi - xlo + 1)
+    for rk in range(nranks):
+        nys, nye = w.bounds(rk)
+        gp, np2 = w.array(rk, O.GP), w.array(rk, O.NP2)
+        uf = w.array(rk, O.UF)
+        uf[:, :, 1] = b0                          # By
+        uf[:, :, 5] = -v0 * b0 / prm["c"]         # Ez = -v0 By / c   (proj/shock/app.f90: uf(6) = -v0*uf(2)/c)
+        for jl in range(nye - nys + 1):
+            r = np.random.default_rng([seed, nys + jl])
+            x = r.uniform(xlo, xhi + 1, npr)
+            y = (nys + jl) + r.uniform(0, 1, npr)
+            for isp in range(2):
+                u = r.normal(0.0, prm["vte"], (npr, 3))
+                gam = np.sqrt(1 + (u ** 2).sum(axis=1) / prm["c"] ** 2)
+                u[:, 0] = (u[:, 0] + v0 * gam) / np.sqrt(1 - v0 * v0 / prm["c"] ** 2)   # Lorentz boost, app.f90:452
+                gp[isp, jl, :npr, 0], gp[isp, jl, :npr, 1] = x, y
+                gp[isp, jl, :npr, 2:5] = u
+                gp[isp, jl, :npr, 5].view(np.int64)[:] = -(np.arange(npr) + 1 + (nys - nygs + jl) * npr)
+                np2[isp, jl] = npr
+    w.sort_bucket()
+    for rk in range(nranks):
+        w.array(rk, O.GP)[...] = w.array(rk, O.UP)
+    return prm, w

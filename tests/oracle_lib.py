@@ -16,7 +16,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 NSP_MAX = 4
 UP, GP, UF, DF, UJ, GKL, MOM = range(7)
 NP2, CUMCNT = 16, 17
-BC_PERIODIC, BC_RECONNECTION = 0, 1
+BC_PERIODIC, BC_RECONNECTION, BC_SHOCK = 0, 1, 2
 
 
 class OrcConfig(C.Structure):
@@ -61,6 +61,12 @@ def load(fast=False):
     for name in ("orc_field_fdtd_i", "orc_bc_particle_y"):
         getattr(lib, name).argtypes = [P]
         getattr(lib, name).restype = C.c_int
+    lib.orc_bc_injection.argtypes = [P, C.c_double]
+    lib.orc_bc_injection.restype = None
+    lib.orc_set_u_inject.argtypes = [P, C.c_double]
+    lib.orc_set_u_inject.restype = None
+    lib.orc_set_xrange.argtypes = [P, C.c_int, C.c_int]
+    lib.orc_set_xrange.restype = C.c_int
     lib.orc_step.argtypes = [P, C.c_int]
     lib.orc_step.restype = C.c_int
     lib.orc_stage_times.argtypes = [P, C.POINTER(C.c_double), C.c_int]
@@ -162,6 +168,8 @@ class World:
     def field_fdtd_i(self): return self.lib.orc_field_fdtd_i(self.h)
     def bc_particle_x(self): self.lib.orc_bc_particle_x(self.h)
     def bc_particle_y(self): return self.lib.orc_bc_particle_y(self.h)
+    def bc_injection(self, u0): self.lib.orc_bc_injection(self.h, u0)
+    def set_u_inject(self, u0): self.lib.orc_set_u_inject(self.h, u0)
     def sort_bucket(self): self.lib.orc_sort_bucket(self.h)
     def mom_accl(self): self.lib.orc_mom_accl(self.h)
     def mom_nvt(self): self.lib.orc_mom_nvt(self.h)

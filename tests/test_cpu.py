@@ -120,3 +120,45 @@ def test_oracle_reconnection_walls(nranks):
     assert np.abs(w.global_field() - w1.global_field()).max() <= 1e-13
     assert w.cg_iters() == w1.cg_iters()
     w.close(); w1.close()
+
+
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_oracle_shock_injection(nranks):
+    """proj/shock boundary module in the oracle.  Known answers for bc__injection (boundary_shock.f90:255-297): a
+    particle left of nxs+1 is mirrored there with u -> -u; a particle beyond xend = nxe*delx + v0*delt is mirrored
+    at xend with ux -> 2 u0 - ux, uy, uz -> -uy, -uz; everything else is untouched.  Then a run: particles stay
+    between the walls, their number is conserved, the discrete Gauss law residual stays at roundoff although
+    particles are reflected (the injection precedes the deposit, proj/shock/app.f90:112-113), and the slab
+    decomposition does not change the answer."""
+    from helpers import make_shock_world
+    u0 = -0.3
+    prm, w = make_shock_world(32, 16, 6, u0=u0, nranks=nranks)
+    nxgs, nx = prm["nxgs"], prm["nx"]
+    nxs, nxe = nxgs, nxgs + nx - 1
+    v0 = u0 / np.sqrt(1 + u0 * u0)
+    xend = nxe * 1.0 + v0 * prm["delt"]
+    # ---- known answers on three hand-placed records of rank 0, row 0, species 0
+    gp = w.array(0, O.GP)
+    keep = gp[0, 0, :3].copy()
+    gp[0, 0, 0, :5] = (nxs + 0.75, gp[0, 0, 0, 1], -0.4, 0.1, -0.2)       # left of the wall at nxs+1
+    gp[0, 0, 1, :5] = (xend + 0.125, gp[0, 0, 1, 1], 0.05, 0.1, -0.2)     # beyond the injection wall
+    gp[0, 0, 2, :5] = (xend - 0.125, gp[0, 0, 2, 1], 0.05, 0.1, -0.2)     # inside
+    w.bc_injection(u0)
+    assert np.array_equal(gp[0, 0, 0, :5], (2. * (nxs + 1) - (nxs + 0.75), keep[0, 1], 0.4, -0.1, 0.2))
+    assert np.array_equal(gp[0, 0, 1, :5], (2. * xend - (xend + 0.125), keep[1, 1], 2. * u0 - 0.05, -0.1, 0.2))
+    assert np.array_equal(gp[0, 0, 2, :5], (xend - 0.125, keep[2, 1], 0.05, 0.1, -0.2))
+    gp[0, 0, :3] = keep
+    # ---- a run
+    _, w1 = make_shock_world(32, 16, 6, u0=u0, nranks=1)
+    r0, s0 = w.gauss_residual()
+    w.step(12)
+    w1.step(12)
+    ids, sp, rec = w.particles_by_id()
+    assert len(ids) == 2 * 6 * (32 - 2) * 16
+    assert rec[:, 0].min() >= nxs + 1 and rec[:, 0].max() <= xend
+    r, s = w.gauss_residual()
+    assert abs(r - r0) <= 1e-11 * max(s, 1.0)
+    i1, s1, r1 = w1.particles_by_id()
+    assert np.array_equal(ids, i1) and np.abs(rec - r1).max() <= 1e-12
+    assert np.abs(w.global_field() - w1.global_field()).max() <= 1e-13
+    w.close(); w1.close()

@@ -367,3 +367,40 @@ def test_reconnection_walls_match_oracle(env, monkeypatch):
         mom = c.moments()
         assert rel_to_max(mom[:, 1:-1, 1:-1], w.array(0, O.MOM)[:, 1:-1, 1:-1]).max() <= 1e-10
         c.close(); w.close()
+
+
+def test_shock_injection_matches_oracle():
+    """WM_BC_SHOCK (proj/shock/boundary_shock.f90): reflecting left wall, injection wall at xend with ux -> 2 u0 - ux,
+    applied BEFORE the deposit (proj/shock/app.f90:112-113), df = 0 in the right ghost column; fused step (FMA and
+    exact push) and the stage calls against the oracle's restatement."""
+    import wumingpic2d_b200 as wm
+    from helpers import make_shock_world
+    u0 = -0.3
+    prm, w0 = make_shock_world(40, 20, 10, u0=u0)
+    s = oracle_state(w0)
+    for flags in (0, wm.WM_FLAG_EXACT_PUSH):
+        _, w = make_shock_world(40, 20, 10, u0=u0)
+        c = ctx_for(prm, flags=flags, bc=wm.WM_BC_SHOCK)
+        c.set_u_inject(u0)
+        c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+        c.upload_field(s["uf"])
+        nref = 0
+        for it in range(8):
+            w.step(1)
+            if it == 5:   # one step through the stage calls of proj/shock/app.f90:111-116
+                c.particle__solv(); c.bc__injection(u0); c.field__fdtd_i(); c.bc__particle_y(); c.sort__bucket()
+            else:
+                c.step(1)
+            assert c.cg_iters() == w.cg_iters()
+            up, np2, cum = c.download_particles()
+            assert np.array_equal(cum, w.array(0, O.CUMCNT)), "per-cell counts must be bit-exact (step %d)" % it
+            a, b = flatten_by_id(up, np2), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+            ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+            tol = 1e-12 if it == 0 else 1e-10
+            assert ex <= tol and eu <= tol
+            assert rel_to_max(c.download_field(), w.array(0, O.UF)).max() <= tol
+            assert rel_to_max(c.download_current(), w.array(0, O.UJ)).max() <= tol
+        # the walls were actually hit: some particles have ux > 0 although the plasma drifts to the left at -0.3
+        assert (b[2][:, 2] > 0.2).sum() > 0
+        c.close(); w.close()

@@ -5,4 +5,4 @@ There is no CPU fallback: loading fails loudly if the library has not been built
 call fails if no B200-class device is present.
 """
 from .api import (Context, WmConfig, WmError, load_library, library_path,  # noqa: F401
-                  WM_BC_PERIODIC, WM_BC_RECONNECTION, WM_FLAG_EXACT_PUSH)
+                  WM_BC_PERIODIC, WM_BC_RECONNECTION, WM_BC_SHOCK, WM_FLAG_EXACT_PUSH)

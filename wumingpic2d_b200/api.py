@@ -17,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 WM_NSP_MAX = 2
 WM_BC_PERIODIC = 0
 WM_BC_RECONNECTION = 1
+WM_BC_SHOCK = 2
 WM_FLAG_EXACT_PUSH = 1
 
 
@@ -47,7 +48,8 @@ EXPORTS = [
     "wm_upload_particles", "wm_upload_particles_sorted", "wm_upload_field", "wm_download_particles",
     "wm_download_gp", "wm_download_field", "wm_download_current", "wm_download_dfield",
     "wm_particle_counts", "wm_particle__solv", "wm_field__ele_cur", "wm_boundary__curre",
-    "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_sort__bucket",
+    "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_boundary__injection",
+    "wm_set_u_inject", "wm_sort__bucket",
     "wm_step", "wm_host_step", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
     "wm_energy", "wm_moments", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_ic_weibel", "wm_timing", "wm_synchronize", "wm_layout_rebuilds",
 ]
@@ -100,6 +102,8 @@ def load_library():
               "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_sort__bucket", "wm_synchronize"):
         getattr(lib, n).argtypes = [P]
     lib.wm_step.argtypes = [P, C.c_int32]
+    lib.wm_boundary__injection.argtypes = [P, C.c_double]
+    lib.wm_set_u_inject.argtypes = [P, C.c_double]
     lib.wm_host_step.argtypes = [P, D, D, I32, I32]
     lib.wm_host_particle__solv.argtypes = [P, D, D, D, I32, I32]
     lib.wm_host_sort__bucket.argtypes = [P, D, D, I32, I32]
@@ -239,6 +243,8 @@ class Context:
     def field__fdtd_i(self): self._ck(self.lib.wm_field__fdtd_i(self.h))
     def bc__particle_x(self): self._ck(self.lib.wm_boundary__particle_x(self.h))
     def bc__particle_y(self): self._ck(self.lib.wm_boundary__particle_y(self.h))
+    def bc__injection(self, u0): self._ck(self.lib.wm_boundary__injection(self.h, u0))
+    def set_u_inject(self, u0): self._ck(self.lib.wm_set_u_inject(self.h, u0))
     def sort__bucket(self): self._ck(self.lib.wm_sort__bucket(self.h))
     def step(self, n=1): self._ck(self.lib.wm_step(self.h, n))
 

@@ -90,9 +90,13 @@ __global__ void k_wall_x_dfield(const DevParams P, double *df) {
     row[6 * (-1) + 0] = -row[6 * 0 + 0];
     for (int c = 1; c <= 3; c++) row[6 * (-1) + c] = row[6 * 1 + c];
     for (int c = 4; c <= 5; c++) row[6 * (-1) + c] = -row[6 * 0 + c];
-    row[6 * e + 0] = -row[6 * (e - 1) + 0];
-    for (int c = 1; c <= 3; c++) row[6 * (e + 1) + c] = row[6 * (e - 1) + c];
-    for (int c = 4; c <= 5; c++) row[6 * e + c] = -row[6 * (e - 1) + c];
+    if (P.bc == WM_BC_SHOCK) {  // proj/shock/boundary_shock.f90:401-403
+      for (int c = 0; c <= 5; c++) row[6 * (e + 1) + c] = 0.0;
+    } else {                    // proj/reconnection/boundary_reconnection.f90:355-357
+      row[6 * e + 0] = -row[6 * (e - 1) + 0];
+      for (int c = 1; c <= 3; c++) row[6 * (e + 1) + c] = row[6 * (e - 1) + c];
+      for (int c = 4; c <= 5; c++) row[6 * e + c] = -row[6 * (e - 1) + c];
+    }
   }
 }
 

@@ -194,7 +194,7 @@ __device__ __forceinline__ void rs_add(double (&v)[NP], int l8, bool valid, doub
 
 // MINB resident CTAs per SM: 3 -> at most 168 registers.  DRAIN = false drops the movers' current (wrong physics:
 // only for timing the particle loop in isolation).
-template <int MINB, bool DRAIN, bool WALL, int PFD>
+template <int MINB, bool DRAIN, int WALL, int PFD>
 __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const Pass1Args a) {
   __shared__ __align__(128) double s_f[WINY * WINX * 6];
   __shared__ __align__(16) double s_j[3 * JY * JX];
@@ -404,12 +404,29 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
           un3 = fma(fac1, f5, uvm3);
           // ---- move                                                      particle.f90:156-161
           const double uu = fma(un3, un3, fma(un2, un2, un1 * un1));
-          const double wmove = rsqrt_fast(fma(uu, inv_cc, 1.0));
+          double wmove = rsqrt_fast(fma(uu, inv_cc, 1.0));
           const double dtw = delt * wmove;
           xn = fma(un1, dtw, x);
           yn = fma(un2, dtw, y);
           // ---- new cell relative to the old one: xn - cxh is exact, so these are the comparisons
           //      int(gp*d_delx) of field.f90:238 makes (positions > 0: truncation == floor)
+          if (WALL == 2) {
+            // bc__injection, before the deposit (proj/shock/app.f90:112-113, boundary_shock.f90:280-291): reflecting
+            // wall at nxs+1, injection wall at xend (mirror in the frame that moves with u0)
+            if (xn < P.xwlo) {
+              xn = P.xw2lo - xn;
+              un1 = -un1;
+              un2 = -un2;
+              un3 = -un3;
+            } else if (xn > P.xwhi) {
+              xn = P.xw2hi - xn;
+              un1 = P.u0x2 - un1;
+              un2 = -un2;
+              un3 = -un3;
+              // ele_cur takes vz = uz/gamma from the momentum it finds in gp (field.f90:270-272): the new one
+              wmove = rsqrt_fast(fma(fma(un3, un3, fma(un2, un2, un1 * un1)), inv_cc, 1.0));
+            }
+          }
           dxn = xn - cxh;
           dyn = yn - cyh;
           qvz = qs * (un3 * wmove);  // q*gvz, field.f90:270-272,295
@@ -467,7 +484,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         // ---- reflecting x walls (after the deposit, which uses the position before the boundary)
         //      proj/reconnection/boundary_reconnection.f90:61-99
         bool sstay = stay;  // stays in its cell as far as the sort is concerned (after the particle boundary)
-        if (WALL) {
+        if (WALL == 1) {
           if (active) {
             bool flip = false;
             if (xn < P.xwlo) {
@@ -668,18 +685,19 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
 }
 
 void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaStream_t st) {
-  const bool wall = P.bc != WM_BC_PERIODIC;
   const int grid = P.ntx * P.nty;
-  if (variant == 9)
-    k_fused_sm<3, false, false, 2><<<grid, FT, 0, st>>>(P, a);  // timing experiment: movers' current dropped
+  if (P.bc == WM_BC_SHOCK)
+    k_fused_sm<3, true, 2, 2><<<grid, FT, 0, st>>>(P, a);
+  else if (P.bc == WM_BC_RECONNECTION)
+    k_fused_sm<3, true, 1, 2><<<grid, FT, 0, st>>>(P, a);
+  else if (variant == 9)
+    k_fused_sm<3, false, 0, 2><<<grid, FT, 0, st>>>(P, a);  // timing experiment: movers' current dropped
   else if (variant == 2)
-    k_fused_sm<2, true, false, 2><<<grid, FT, 0, st>>>(P, a);   // 2 CTAs per SM, up to 255 registers
+    k_fused_sm<2, true, 0, 2><<<grid, FT, 0, st>>>(P, a);   // 2 CTAs per SM, up to 255 registers
   else if (variant == 10)
-    k_fused_sm<3, true, false, 3><<<grid, FT, 0, st>>>(P, a);   // hints three iterations ahead
-  else if (wall)
-    k_fused_sm<3, true, true, 2><<<grid, FT, 0, st>>>(P, a);
+    k_fused_sm<3, true, 0, 3><<<grid, FT, 0, st>>>(P, a);   // hints three iterations ahead
   else
-    k_fused_sm<3, true, false, 2><<<grid, FT, 0, st>>>(P, a);
+    k_fused_sm<3, true, 0, 2><<<grid, FT, 0, st>>>(P, a);
 }
 
 }  // namespace wm

@@ -22,7 +22,7 @@ void launch_incoming_scatter(const DevParams &P, const double *rec, int n, int i
                              const int *rank, const PartSoA &dst, unsigned *err, cudaStream_t st);
 void launch_aos2soa(const double *rec, long long n, size_t so, const PartSoA &dst, cudaStream_t st);
 void launch_soa2aos(const PartSoA &src, size_t so, long long n, double *rec, cudaStream_t st);
-void launch_bcx(const DevParams &P, const PartSoA &g, const int *cstart, cudaStream_t st);
+void launch_bcx(const DevParams &P, const PartSoA &g, const int *cstart, bool injection, cudaStream_t st);
 void launch_ic_weibel(const DevParams &P, const PartSoA &dst, int *cstart, int *cnt, uint64_t seed, int n0, double vti,
                       double vte, double t_ani, float sl, cudaStream_t st);
 void launch_relayout_from_aos(const DevParams &P, const double *rec, long long n, const int *tight, const int *cstart_dst,

@@ -179,6 +179,22 @@ __global__ void __launch_bounds__(P1_THREADS, 1) k_pass1(const DevParams P, cons
                 wmove = rsqrt(1.0 + uu * P.inv_cc);
               xn = A::add(x, A::mul(A::mul(un1, P.delt), wmove));
               yn = A::add(y, A::mul(A::mul(un2, P.delt), wmove));
+              if (P.bc == WM_BC_SHOCK && BOUND) {
+                // fused step: bc__injection comes before the deposit (proj/shock/app.f90:112-113)
+                if (xn < P.xwlo) {
+                  xn = A::sub(P.xw2lo, xn);
+                  un1 = -un1; un2 = -un2; un3 = -un3;
+                } else if (xn > P.xwhi) {
+                  xn = A::sub(P.xw2hi, xn);
+                  un1 = A::sub(P.u0x2, un1); un2 = -un2; un3 = -un3;
+                  // ele_cur takes vz = uz/gamma from the momentum it finds in gp (field.f90:270-272): the new one
+                  const double uu2 = A::add(A::add(A::mul(un1, un1), A::mul(un2, un2)), A::mul(un3, un3));
+                  if (EX)
+                    wmove = A::div(1.0, A::sqrt_(A::add(1.0, A::div(uu2, P.cc))));
+                  else
+                    wmove = rsqrt(1.0 + uu2 * P.inv_cc);
+                }
+              }
             }
           } else {
             xn = a.dst.x[so + p];
@@ -291,7 +307,9 @@ __global__ void __launch_bounds__(P1_THREADS, 1) k_pass1(const DevParams P, cons
             // periodic wraps with round-toward -inf adds      boundary_periodic.f90:74,82-88,124,147-154
             const int j2 = gj + incy;  // unwrapped destination row
             const int ic = __double2int_rz(xn), jc = __double2int_rz(yn);
-            if (P.bc != WM_BC_PERIODIC) {
+            if (P.bc == WM_BC_SHOCK) {
+              // the shock app applies bc__injection before the field solve and has no bc__particle_x in its step
+            } else if (P.bc != WM_BC_PERIODIC) {
               // reflecting walls                     proj/reconnection/boundary_reconnection.f90:82-92
               bool flip = false;
               if (xn < P.xwlo) {
@@ -609,7 +627,7 @@ __global__ void k_soa2aos(const PartSoA src, size_t so, long long n, double *__r
 }
 
 // stand-alone x wrap (stage mode)                                  boundary_periodic.f90:61-96
-__global__ void k_bcx(const DevParams P, const PartSoA g, const int *__restrict__ cstart) {
+__global__ void k_bcx(const DevParams P, const PartSoA g, const int *__restrict__ cstart, const bool injection) {
   const PView<double> x = g.x;
   for (int isp = 0; isp < P.nsp; isp++) {
     const int n = cstart[(size_t)isp * (P.ncell + 1) + P.ncell];
@@ -619,8 +637,25 @@ __global__ void k_bcx(const DevParams P, const PartSoA g, const int *__restrict_
       const int ipos = __double2int_rz(v);
       if (P.bc != WM_BC_PERIODIC) {  // reflecting walls   proj/reconnection/boundary_reconnection.f90:82-92
         const size_t o = (size_t)isp * P.cap + s;
-        if (v < P.xwlo || v >= P.xwhi) {
-          x[o] = (v < P.xwlo ? P.xw2lo : P.xw2hi) - v;
+        if (injection) {  // bc__injection   proj/shock/boundary_shock.f90:280-291
+          if (v < P.xwlo) {
+            x[o] = P.xw2lo - v;
+            g.ux[o] = -g.ux[o];
+            g.uy[o] = -g.uy[o];
+            g.uz[o] = -g.uz[o];
+          } else if (v > P.xwhi) {
+            x[o] = P.xw2hi - v;
+            g.ux[o] = P.u0x2 - g.ux[o];
+            g.uy[o] = -g.uy[o];
+            g.uz[o] = -g.uz[o];
+          }
+          continue;
+        }
+        // bc__particle_x of the wall modules: walls at nxs+1 and nxe-1 (in WM_BC_SHOCK xwhi/xw2hi hold xend)
+        const double whi = (P.bc == WM_BC_SHOCK) ? (double)(P.nxgs + P.nx - 2) * P.delx : P.xwhi;
+        const double w2hi = (P.bc == WM_BC_SHOCK) ? 2. * (P.nxgs + P.nx - 2) * P.delx : P.xw2hi;
+        if (v < P.xwlo || v >= whi) {
+          x[o] = (v < P.xwlo ? P.xw2lo : w2hi) - v;
           g.ux[o] = -g.ux[o];
           g.uy[o] = -g.uy[o];
           g.uz[o] = -g.uz[o];
@@ -1067,8 +1102,8 @@ void launch_place(const DevParams &P, const double *stage, const PartSoA &dst, c
 void launch_mark_dead(const DevParams &P, PView<double> x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st) {
   k_mark_dead<<<148 * 16, 256, 0, st>>>(P, x, cstart, cnt_old, cnt_new);
 }
-void launch_bcx(const DevParams &P, const PartSoA &g, const int *cstart, cudaStream_t st) {
-  k_bcx<<<148 * 8, 256, 0, st>>>(P, g, cstart);
+void launch_bcx(const DevParams &P, const PartSoA &g, const int *cstart, bool injection, cudaStream_t st) {
+  k_bcx<<<148 * 8, 256, 0, st>>>(P, g, cstart, injection);
 }
 void launch_ic_weibel(const DevParams &P, const PartSoA &dst, int *cstart, int *cnt, uint64_t seed, int n0, double vti,
                       double vte, double t_ani, float sl, cudaStream_t st) {

@@ -94,6 +94,7 @@ struct wm_ctx {
   cudaEvent_t ev_cg[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_b[2] = {nullptr, nullptr};  // sort on st2 beside the field solve
   bool overlap = true;                   // WM_OVERLAP=0: everything on one stream
+  bool u_inject_set = false;             // WM_BC_SHOCK: wm_set_u_inject / wm_boundary__injection has been called
   int cg_ite[3] = {0, 0, 0};
   // comm
   ncclComm_t comm = nullptr;
@@ -459,8 +460,8 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   *out = nullptr;
   if (g->ndim != 6) return fail("wm_create: ndim must be 6 (x,y,ux,uy,uz,id)");
   if (g->nsp < 1 || g->nsp > WM_NSP_MAX) return fail("wm_create: nsp must be 1..%d", WM_NSP_MAX);
-  if (g->bc != WM_BC_PERIODIC && g->bc != WM_BC_RECONNECTION)
-    return fail("wm_create: boundary kind %d not implemented (periodic and reconnection walls are)", g->bc);
+  if (g->bc != WM_BC_PERIODIC && g->bc != WM_BC_RECONNECTION && g->bc != WM_BC_SHOCK)
+    return fail("wm_create: boundary kind %d not implemented (periodic, reconnection walls and shock injection are)", g->bc);
   if (g->delx != 1.0) return fail("wm_create: delx must be 1 (common/sort.f90:60 keys on int(x) without /delx; all apps use delx=1)");
   const int nx = g->nxge - g->nxgs + 1, ny = g->nyge - g->nygs + 1, nyl = g->nye - g->nys + 1;
   if (nx < 4 || nyl < 2 || ny < nyl) return fail("wm_create: grid too small (nx>=4, rows per rank>=2)");
@@ -518,6 +519,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   P.xwhi = (g->nxge - 1) * g->delx;
   P.xw2lo = 2. * (g->nxgs + 1) * g->delx;
   P.xw2hi = 2. * (g->nxge - 1) * g->delx;
+  P.u0x2 = 0.0;  // WM_BC_SHOCK: wm_set_u_inject replaces xwhi, xw2hi by xend, 2.*xend
   for (int s = 0; s < g->nsp; s++) {
     P.q[s] = g->q[s];
     P.r[s] = g->r[s];
@@ -907,10 +909,33 @@ int wm_field__fdtd_i(wm_ctx *c) {
   return 0;
 }
 
+// u0 of bc__injection: xend = nxe*delx + u0/sqrt(1 + (u0*u0)/(c*c))*delt   proj/shock/boundary_shock.f90:272
+int wm_set_u_inject(wm_ctx *c, double u0) {
+  if (!c) return fail("wm_set_u_inject: null context");
+  if (c->P.bc != WM_BC_SHOCK) return fail("wm_set_u_inject: the context was not created with WM_BC_SHOCK");
+  const double cl = c->cfg.c, delx = c->cfg.delx;
+  const double xend = c->cfg.nxge * delx + u0 / std::sqrt(1 + (u0 * u0) / (cl * cl)) * c->cfg.delt;
+  c->P.xwhi = xend;
+  c->P.xw2hi = +2. * xend;
+  c->P.u0x2 = +2. * u0;
+  c->u_inject_set = true;
+  return 0;
+}
+
+int wm_boundary__injection(wm_ctx *c, double u0) {
+  WM(wm_set_u_inject(c, u0));
+  WM(need_state(c, ST_PUSHED, "wm_boundary__injection"));
+  WM(set_device(c));
+  launch_bcx(c->P, c->soa[c->cur ^ 1], c->cstart[c->cur], true, c->st);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 int wm_boundary__particle_x(wm_ctx *c) {
   WM(need_state(c, ST_PUSHED, "wm_boundary__particle_x"));
   WM(set_device(c));
-  launch_bcx(c->P, c->soa[c->cur ^ 1], c->cstart[c->cur], c->st);
+  launch_bcx(c->P, c->soa[c->cur ^ 1], c->cstart[c->cur], false, c->st);
   c->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -988,6 +1013,11 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
   const size_t ng = (size_t)P.pitch * (P.nyl + 4);
   const int mode = M_PUSH | M_DEPOSIT | M_BOUND | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
   const bool inplace = c->inplace && !(c->cfg.flags & WM_FLAG_EXACT_PUSH);
+  if (P.bc == WM_BC_SHOCK) {
+    if (!c->u_inject_set) return fail("wm_step: WM_BC_SHOCK needs wm_set_u_inject(u0) first (bc__injection, proj/shock/app.f90:113)");
+    if (!(c->cfg.flags & WM_FLAG_EXACT_PUSH) && !(inplace && c->sm))
+      return fail("wm_step: WM_BC_SHOCK is implemented by k_fused_sm and the exact path only (unset WM_SM=0 / WM_INPLACE=0)");
+  }
   CU(cudaEventRecord(c->ev_call[0], c->st));
   for (int it = 0; it < nsteps; it++) {
     if (c->timing) CU(cudaEventRecord(c->ev[0], c->st));

@@ -70,6 +70,8 @@ struct DevParams {
   double xlen, ylen;            // nx*delx, ny*delx
   double xwlo, xwhi;            // reflecting walls at (nxs+1)*delx, (nxe-1)*delx (wall kinds)
   double xw2lo, xw2hi;          // 2.*(nxs+1)*delx, 2.*(nxe-1)*delx as the reference computes them
+  double u0x2;                  // WM_BC_SHOCK: 2.*u0 of bc__injection; then xwhi = xend, xw2hi = 2.*xend
+                                // (proj/shock/boundary_shock.f90:272,287-290)
   double q[WM_NSP_MAX], r[WM_NSP_MAX];
   double f1, f2, f3, f4, f5, gfac, pi4dt;  // field.f90:53-57, 4*pi*delt
 };
