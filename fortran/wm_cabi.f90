@@ -125,6 +125,20 @@ module wm_cabi
        real(c_double), value :: u0
        integer(c_int)        :: ierr
      end function wm_boundary__injection
+     function wm_set_xrange(ctx, nxs, nxe) bind(C, name='wm_set_xrange') result(ierr)
+       import :: c_ptr, c_int, c_int32_t
+       type(c_ptr), value       :: ctx
+       integer(c_int32_t), value :: nxs, nxe
+       integer(c_int)           :: ierr
+     end function wm_set_xrange
+     function wm_append_particles(ctx, isp, n, rec) bind(C, name='wm_append_particles') result(ierr)
+       import :: c_ptr, c_int, c_int32_t, c_int64_t, c_double
+       type(c_ptr), value        :: ctx
+       integer(c_int32_t), value :: isp
+       integer(c_int64_t), value :: n
+       real(c_double), intent(in) :: rec(*)
+       integer(c_int)            :: ierr
+     end function wm_append_particles
      function wm_set_u_inject(ctx, u0) bind(C, name='wm_set_u_inject') result(ierr)
        import :: c_ptr, c_int, c_double
        type(c_ptr), value    :: ctx

@@ -306,9 +306,10 @@ end module boundary_reconnection
 
 !> proj/shock/boundary_shock.f90 (reflecting wall on the left, injection wall on the right, periodic y).
 !! The app selects it by `use boundary_shock, bc__init => boundary_shock__init, bc__injection => ...`
-!! (proj/shock/app.f90:6-14).  The device library implements the fixed box nxs = nxgs, nxe = nxge: the driver's
-!! `relocate` (proj/shock/app.f90:611-680), which moves nxe and appends particles to the host arrays, is not
-!! supported yet (DESIGN.md section 7).
+!! (proj/shock/app.f90:6-14).  The active range nxs..nxe of the step is forwarded with wm_set_xrange.  The driver's
+!! `inject` and `relocate` (proj/shock/app.f90:611-850) write new particles and upstream fields straight into the
+!! host arrays: with device-resident state they have to hand the new records to wm_append_particles and the
+!! changed field columns to wm_upload_field instead (INTEGRATION.md).
 module boundary_shock
   use wm_cabi
   implicit none
@@ -360,10 +361,8 @@ contains
     integer, intent(in)    :: np2(cfg%nys:cfg%nye,cfg%nsp)
     real(8), intent(inout) :: up(cfg%ndim,cfg%np,cfg%nys:cfg%nye,cfg%nsp)
     real(8), intent(in)    :: u0
-    if (nxs /= cfg%nxgs .or. nxe /= cfg%nxge) then
-       write(6,*) 'boundary_shock__injection: a moving nxe (relocate) is not supported by the device library yet'
-       stop
-    end if
+    ! the shock app moves nxe (relocate): tell the library the active range of this step's calls
+    call wm_check(wm_set_xrange(ctx, nxs, nxe), 'boundary_shock__injection (wm_set_xrange)')
     call wm_check(wm_boundary__injection(ctx, u0), 'boundary_shock__injection')
   end subroutine boundary_shock__injection
 

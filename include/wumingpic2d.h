@@ -45,8 +45,7 @@ enum {
   WM_BC_SHOCK = 2          /* proj/shock/boundary_shock.f90: reflecting left wall, injection wall at             */
                            /* xend = nxe*delx + v0*delt on the right (bc__injection, applied BEFORE the field    */
                            /* solve: proj/shock/app.f90:112-113), df = 0 in the right ghost column; periodic y.   */
-                           /* The box is the full range nxgs..nxge (the driver's `relocate`, which moves nxe,    */
-                           /* is not supported yet).  wm_step needs wm_set_u_inject first.                       */
+                           /* Active range nxs..nxe: wm_set_xrange.  wm_step needs wm_set_u_inject first.       */
 };
 
 /* flags */
@@ -121,6 +120,13 @@ int wm_boundary__particle_y(wm_ctx *ctx);  /* bc__particle_y  common/boundary_pe
  * wm_field__fdtd_i).  Also records u0 for wm_step, like wm_set_u_inject. */
 int wm_boundary__injection(wm_ctx *ctx, double u0);
 int wm_set_u_inject(wm_ctx *ctx, double u0);
+/* The active x range [nxs, nxe] that the following calls work on: the nxs, nxe arguments of particle__solv,
+ * field__fdtd_i, sort__bucket, bc__injection ... (proj/shock/app.f90:111-116; `relocate` moves nxe, :611-621).
+ * nxs must be nxgs; cells beyond nxe must hold no particles.  Default: nxgs..nxge. */
+int wm_set_xrange(wm_ctx *ctx, int32_t nxs, int32_t nxe);
+/* Particles the driver adds between two steps (`inject` / `relocate` of proj/shock/app.f90:611-850 append them to
+ * the rows of `up`): n records (x,y,ux,uy,uz,id) of species isp (0-based), any order, inside this rank's slab. */
+int wm_append_particles(wm_ctx *ctx, int32_t isp, int64_t n, const double *rec);
 int wm_sort__bucket(wm_ctx *ctx);          /* sort__bucket    common/sort.f90:36             */
 /* the five calls above fused: push + deposit + particle boundaries in one kernel,
  * then the field solve, then the scatter pass (proj/weibel/app.f90:100-107) */

@@ -88,7 +88,7 @@ def make_wall_world(nx, ny, ppc, nranks=1, steps=0, seed=7, b0=0.02, **kw):
     return prm, w
 
 
-def make_shock_world(nx, ny, ppc, u0=-0.3, nranks=1, seed=11, b0=0.02, **kw):
+def make_shock_world(nx, ny, ppc, u0=-0.3, nranks=1, seed=11, b0=0.02, nxe=None, **kw):
     """A shock-type world (proj/shock: reflecting wall on the left, injection wall at xend on the right, periodic
     y): a neutral plasma that drifts toward the left wall with four-velocity u0 < 0 in a uniform By, Ez = v0 By
     (the upstream state of proj/shock/app.f90:400-470, without the driver's per-step injection of new
@@ -99,8 +99,12 @@ def make_shock_world(nx, ny, ppc, u0=-0.3, nranks=1, seed=11, b0=0.02, **kw):
     w = O.World(prm)
     w.set_u_inject(u0)
     nxgs, nygs = prm["nxgs"], prm["nygs"]
+    if nxe is None:
+        nxe = nxgs + nx - 1
+    else:                                       # the box of proj/shock starts short and grows (relocate)
+        assert w.lib.orc_set_xrange(w.h, nxgs, nxe) == 0
     v0 = u0 / np.sqrt(1 + u0 * u0 / prm["c"] ** 2)
-    xlo, xhi = nxgs + 1, nxgs + nx - 2          # particles live in cells nxs+1 .. nxe-1 (nxe = nxgs+nx-1)
+    xlo, xhi = nxgs + 1, nxe - 1                # particles live in cells nxs+1 .. nxe-1
     npr = ppc * (xhi - xlo + 1)
     for rk in range(nranks):
         nys, nye = w.bounds(rk)
@@ -124,3 +128,32 @@ def make_shock_world(nx, ny, ppc, u0=-0.3, nranks=1, seed=11, b0=0.02, **kw):
     for rk in range(nranks):
         w.array(rk, O.GP)[...] = w.array(rk, O.UP)
     return prm, w
+
+
+def shock_relocate(prm, up, np2, uf, nxe_new, n0, u0, b0, seed):
+    """The state changes of `relocate` (proj/shock/app.f90:611-680) on host arrays of one rank holding all rows:
+    n0 new particles per row and species in the cell nxe_new-1 (evenly spaced in x, drifting Maxwellian; ions and
+    electrons at the same positions), upstream By / Ez in the new columns.  Deterministic stand-in for the
+    driver's RNG; returns the appended records per species (for wm_append_particles)."""
+    nxgs, nygs = prm["nxgs"], prm["nygs"]
+    v0 = u0 / np.sqrt(1 + u0 * u0 / prm["c"] ** 2)
+    nsp, nyl = np2.shape
+    added = [[] for _ in range(nsp)]
+    for jl in range(nyl):
+        r = np.random.default_rng([seed, nxe_new, jl])
+        x = (nxe_new - 1) + (np.arange(n0) + 0.5) / n0
+        y = (nygs + jl) + r.uniform(0, 1, n0)
+        for isp in range(nsp):
+            u = r.normal(0.0, prm["vte"], (n0, 3))
+            gam = np.sqrt(1 + (u ** 2).sum(axis=1) / prm["c"] ** 2)
+            u[:, 0] = (u[:, 0] + v0 * gam) / np.sqrt(1 - v0 * v0 / prm["c"] ** 2)
+            k = np2[isp, jl]
+            up[isp, jl, k:k + n0, 0], up[isp, jl, k:k + n0, 1] = x, y
+            up[isp, jl, k:k + n0, 2:5] = u
+            up[isp, jl, k:k + n0, 5].view(np.int64)[:] = -(10 ** 7 * nxe_new + jl * n0 + np.arange(n0) + 1)
+            np2[isp, jl] = k + n0
+            added[isp].append(up[isp, jl, k:k + n0].copy())
+    for i in (nxe_new - 1, nxe_new):              # uf(2,...) = By, uf(6,...) = Ez in the columns that became active
+        uf[:, i - (nxgs - 2), 1] = b0
+    uf[:, (nxe_new - 1) - (nxgs - 2), 5] = -v0 * b0 / prm["c"]
+    return [np.concatenate(a) for a in added]

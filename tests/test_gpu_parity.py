@@ -404,3 +404,62 @@ def test_shock_injection_matches_oracle():
         # the walls were actually hit: some particles have ux > 0 although the plasma drifts to the left at -0.3
         assert (b[2][:, 2] > 0.2).sum() > 0
         c.close(); w.close()
+
+
+def test_shock_moving_box_matches_oracle():
+    """The shock app works on the active range nxs..nxe and moves nxe (`relocate`, proj/shock/app.f90:611-680): the nxs,
+    nxe arguments of particle__solv, bc__injection, field__fdtd_i, sort__bucket vary in time.  Start with a short box,
+    run, grow the box twice the way relocate does (new particles in the cell nxe-1, upstream fields in the new
+    columns; applied to the oracle's arrays and to downloaded device arrays alike), and compare after every step."""
+    import wumingpic2d_b200 as wm
+    from helpers import make_shock_world, shock_relocate
+    u0, b0, n0 = -0.3, 0.02, 10
+    nx, ny = 40, 16
+    prm, w = make_shock_world(nx, ny, n0, u0=u0, b0=b0, nxe=2 + 30)
+    nxgs = prm["nxgs"]
+    nxe = nxgs + 30
+    s = oracle_state(w)
+    c = ctx_for(prm, bc=wm.WM_BC_SHOCK)
+    c.set_xrange(nxgs, nxe)
+    c.set_u_inject(u0)
+    c.upload_particles(s["up"], s["np2"])
+    c.upload_field(s["uf"])
+
+    def compare(tol):
+        na = nxe - nxgs + 1
+        assert c.cg_iters() == w.cg_iters()
+        up, np2, cum = c.download_particles()
+        assert np.array_equal(np2, w.array(0, O.NP2))
+        assert np.array_equal(cum[:, :, :na + 1], w.array(0, O.CUMCNT)[:, :, :na + 1]), "per-cell counts must be bit-exact"
+        a, b = flatten_by_id(up, np2), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
+        assert np.array_equal(a[0], b[0])
+        ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+        assert ex <= tol and eu <= tol
+        assert rel_to_max(c.download_field(), w.array(0, O.UF)).max() <= tol
+        assert rel_to_max(c.download_current(), w.array(0, O.UJ)).max() <= tol
+
+    for it in range(3):
+        w.step(1); c.step(1)
+        compare(1e-12 if it == 0 else 1e-10)
+    for grow in range(2):
+        nxe += 1
+        # oracle side: edit its arrays in place, as the driver does
+        shock_relocate(prm, w.array(0, O.UP), w.array(0, O.NP2), w.array(0, O.UF), nxe, n0, u0, b0, seed=5)
+        cum = w.array(0, O.CUMCNT)
+        cum[:, :, nxe - nxgs] = cum[:, :, nxe - 1 - nxgs] + n0      # cumcnt(nxe,j,isp) = cumcnt(nxe-1,j,isp) + n0
+        assert w.lib.orc_set_xrange(w.h, nxgs, nxe) == 0
+        # device side: first growth through downloaded arrays + upload, second through wm_append_particles
+        up, np2, _ = c.download_particles()
+        uf = c.download_field()
+        added = shock_relocate(prm, up, np2, uf, nxe, n0, u0, b0, seed=5)
+        c.set_xrange(nxgs, nxe)
+        if grow == 0:
+            c.upload_particles(up, np2)
+        else:
+            for isp in range(2):
+                c.append_particles(isp, added[isp])
+        c.upload_field(uf)
+        for it in range(3):
+            w.step(1); c.step(1)
+            compare(1e-10)
+    c.close(); w.close()

@@ -49,7 +49,7 @@ EXPORTS = [
     "wm_download_gp", "wm_download_field", "wm_download_current", "wm_download_dfield",
     "wm_particle_counts", "wm_particle__solv", "wm_field__ele_cur", "wm_boundary__curre",
     "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_boundary__injection",
-    "wm_set_u_inject", "wm_sort__bucket",
+    "wm_set_u_inject", "wm_set_xrange", "wm_append_particles", "wm_sort__bucket",
     "wm_step", "wm_host_step", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
     "wm_energy", "wm_moments", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_ic_weibel", "wm_timing", "wm_synchronize", "wm_layout_rebuilds",
 ]
@@ -104,6 +104,8 @@ def load_library():
     lib.wm_step.argtypes = [P, C.c_int32]
     lib.wm_boundary__injection.argtypes = [P, C.c_double]
     lib.wm_set_u_inject.argtypes = [P, C.c_double]
+    lib.wm_set_xrange.argtypes = [P, C.c_int32, C.c_int32]
+    lib.wm_append_particles.argtypes = [P, C.c_int32, C.c_int64, D]
     lib.wm_host_step.argtypes = [P, D, D, I32, I32]
     lib.wm_host_particle__solv.argtypes = [P, D, D, D, I32, I32]
     lib.wm_host_sort__bucket.argtypes = [P, D, D, I32, I32]
@@ -245,6 +247,11 @@ class Context:
     def bc__particle_y(self): self._ck(self.lib.wm_boundary__particle_y(self.h))
     def bc__injection(self, u0): self._ck(self.lib.wm_boundary__injection(self.h, u0))
     def set_u_inject(self, u0): self._ck(self.lib.wm_set_u_inject(self.h, u0))
+    def set_xrange(self, nxs, nxe): self._ck(self.lib.wm_set_xrange(self.h, nxs, nxe))
+
+    def append_particles(self, isp, rec):
+        rec = np.ascontiguousarray(rec, dtype=np.float64).reshape(-1, 6)
+        self._ck(self.lib.wm_append_particles(self.h, isp, rec.shape[0], _d(rec)))
     def sort__bucket(self): self._ck(self.lib.wm_sort__bucket(self.h))
     def step(self, n=1): self._ck(self.lib.wm_step(self.h, n))
 

@@ -1025,6 +1025,20 @@ __global__ void k_mark_dead(const DevParams P, const PView<double> x, const int 
   }
 }
 
+// counts that ran past their segment's capacity (the surplus went to the overflow list): clamp
+__global__ void k_clamp_counts(const DevParams P, const int *__restrict__ cstart, int *cnt) {
+  const long long n = (long long)P.nsp * P.ncell;
+  for (long long wk = (long long)blockIdx.x * blockDim.x + threadIdx.x; wk < n; wk += (long long)gridDim.x * blockDim.x) {
+    const int isp = (int)(wk / P.ncell), cell = (int)(wk - (long long)isp * P.ncell);
+    const int *cs = cstart + (size_t)isp * (P.ncell + 1);
+    const int capc = cs[cell + 1] - cs[cell];
+    if (cnt[wk] > capc) cnt[wk] = capc;
+  }
+}
+void launch_clamp_counts(const DevParams &P, const int *cstart, int *cnt, cudaStream_t st) {
+  k_clamp_counts<<<148 * 8, 256, 0, st>>>(P, cstart, cnt);
+}
+
 // ---------------------------------------------------------------- launch wrappers
 template <int MODE>
 static void launch_p1(const DevParams &P, const Pass1Args &a, cudaStream_t st) {

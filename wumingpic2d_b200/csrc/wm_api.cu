@@ -94,6 +94,8 @@ struct wm_ctx {
   cudaEvent_t ev_cg[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_b[2] = {nullptr, nullptr};  // sort on st2 beside the field solve
   bool overlap = true;                   // WM_OVERLAP=0: everything on one stream
+  int nxa = 0;                           // active cells in x: nxe - nxgs + 1 (< nx only while the shock box grows)
+  double u_inject = 0.0;
   bool u_inject_set = false;             // WM_BC_SHOCK: wm_set_u_inject / wm_boundary__injection has been called
   int cg_ite[3] = {0, 0, 0};
   // comm
@@ -161,6 +163,14 @@ inline size_t host_up_index(const wm_config &g, int isp, int jl) {
   return (size_t)6 * ((size_t)g.np * ((size_t)jl + (size_t)nyl * isp));
 }
 
+// Parameters of the grid kernels: the same layout (pitch), x extent = the active range nxs..nxe of the call
+// (field.f90 loops i = nxs..nxe; only the shock app moves nxe, proj/shock/app.f90:611-621).
+inline DevParams fieldp(const wm_ctx *c) {
+  DevParams P = c->P;
+  P.nx = c->nxa;
+  return P;
+}
+
 int check_errors(wm_ctx *c, const char *where) {
   CU(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
   CU(cudaStreamSynchronize(c->st));
@@ -194,7 +204,7 @@ int ring_rows(wm_ctx *c, double *a, int ncomp, int lj_send, int to, int lj_recv,
 int halo_copy(wm_ctx *c, double *a, int ncomp, int ng, bool do_x) {
   const int nyl = c->P.nyl;
   if (c->P.nsize == 1) {
-    launch_fill_y_local(c->P, a, ncomp, ng, c->st);
+    launch_fill_y_local(fieldp(c), a, ncomp, ng, c->st);
     c->launches++;
   } else {
     // my first ng rows -> ndown ; nup's first rows land in my upper ghosts
@@ -203,7 +213,7 @@ int halo_copy(wm_ctx *c, double *a, int ncomp, int ng, bool do_x) {
     WM(ring_rows(c, a, ncomp, nyl - ng, c->nup, -ng, c->ndown, ng));
   }
   if (do_x) {
-    launch_fill_x(c->P, a, ncomp, ng, c->st);
+    launch_fill_x(fieldp(c), a, ncomp, ng, c->st);
     c->launches++;
   }
   return 0;
@@ -245,7 +255,7 @@ int allreduce_ctl(wm_ctx *c, int which, int n) {
 
 // cgm for l = 1..3 together                                                field.f90:319-461
 int cg_solve(wm_ctx *c) {
-  const DevParams &P = c->P;
+  const DevParams P = fieldp(c);
   launch_cg_init(P, c->f, c->st);
   WM(allreduce_ctl(c, 0, 3));
   if (P.nsize > 1) WM(halo_copy(c, c->f.phi, 3, 1, false));  // set_boundary_phi(phi)  field.f90:367
@@ -301,7 +311,7 @@ int cg_solve(wm_ctx *c) {
 
 // everything of field__fdtd_i after ele_cur                                 field.f90:122-184
 int field_solve(wm_ctx *c) {
-  const DevParams &P = c->P;
+  const DevParams P = fieldp(c);
   WM(bc_curre(c));
   launch_rhs(P, c->f, c->st);
   c->launches++;
@@ -520,6 +530,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   P.xw2lo = 2. * (g->nxgs + 1) * g->delx;
   P.xw2hi = 2. * (g->nxge - 1) * g->delx;
   P.u0x2 = 0.0;  // WM_BC_SHOCK: wm_set_u_inject replaces xwhi, xw2hi by xend, 2.*xend
+  c->nxa = nx;
   for (int s = 0; s < g->nsp; s++) {
     P.q[s] = g->q[s];
     P.r[s] = g->r[s];
@@ -868,12 +879,44 @@ int wm_particle_counts(wm_ctx *c, int64_t *n) {
   return 0;
 }
 
+// Particles the driver adds between two steps (proj/shock/app.f90 `inject` :685-850 and `relocate` :611-680 append
+// them to the rows of `up`): records (x, y, ux, uy, uz, id) of species isp, any order, inside this rank's slab.
+// They are appended at the tail of their cells' segments; a segment that is full sends the record to the overflow
+// list and the layout is rebuilt.
+static int rebuild_layout(wm_ctx *c, int novf);
+
+int wm_append_particles(wm_ctx *c, int32_t isp, int64_t n, const double *rec) {
+  WM(need_state(c, ST_SORTED, "wm_append_particles"));
+  if (isp < 0 || isp >= c->P.nsp) return fail("wm_append_particles: species %d out of range", isp);
+  if (n < 0 || (n > 0 && !rec)) return fail("wm_append_particles: bad arguments");
+  if (n == 0) return 0;
+  if (!c->inplace) return fail("wm_append_particles: needs the segment layout with slack (unset WM_INPLACE=0 / WM_SLACK=0)");
+  if (n >= (1LL << 31)) return fail("wm_append_particles: too many records in one call");
+  WM(set_device(c));
+  c->accl_valid = false;
+  const DevParams &P = c->P;
+  double *d_rec = nullptr;
+  CU(cudaMalloc(&d_rec, (size_t)n * 6 * sizeof(double)));
+  CU(cudaMemcpyAsync(d_rec, rec, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  CU(cudaMemsetAsync(c->ovfcnt, 0, sizeof(int), c->st));
+  launch_incoming_append(P, d_rec, (int)n, isp, c->cstart[c->cur], c->cnt[c->cur], c->soa[c->cur], c->ovf, c->ovfsp,
+                         c->ovfcnt, c->ovfcap, c->d_err, c->st);
+  launch_clamp_counts(P, c->cstart[c->cur], c->cnt[c->cur], c->st);
+  c->launches += 2;
+  CU(cudaMemcpyAsync(c->h_ovf, c->ovfcnt, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  CU(cudaFree(d_rec));
+  WM(check_errors(c, "wm_append_particles"));
+  if (*c->h_ovf > 0) WM(rebuild_layout(c, *c->h_ovf));
+  return 0;
+}
+
 // ---------------------------------------------------------------- stage calls
 int wm_particle__solv(wm_ctx *c) {
   WM(need_state(c, ST_SORTED, "wm_particle__solv"));
   c->accl_valid = false;
   WM(set_device(c));
-  launch_tmpf(c->P, c->f.uf, c->f.tmpf, c->st);
+  launch_tmpf(fieldp(c), c->f.uf, c->f.tmpf, c->st);
   WM(fill_dead(c, c->cur ^ 1));  // gp: only live slots are written by the push
   const int mode = M_PUSH | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
   launch_pass1(mode, c->P, p1args(c, c->soa[c->cur], c->soa[c->cur ^ 1], c->P.delt), c->st);
@@ -914,11 +957,26 @@ int wm_set_u_inject(wm_ctx *c, double u0) {
   if (!c) return fail("wm_set_u_inject: null context");
   if (c->P.bc != WM_BC_SHOCK) return fail("wm_set_u_inject: the context was not created with WM_BC_SHOCK");
   const double cl = c->cfg.c, delx = c->cfg.delx;
-  const double xend = c->cfg.nxge * delx + u0 / std::sqrt(1 + (u0 * u0) / (cl * cl)) * c->cfg.delt;
+  const int nxe = c->cfg.nxgs + c->nxa - 1;
+  const double xend = nxe * delx + u0 / std::sqrt(1 + (u0 * u0) / (cl * cl)) * c->cfg.delt;
   c->P.xwhi = xend;
   c->P.xw2hi = +2. * xend;
   c->P.u0x2 = +2. * u0;
+  c->u_inject = u0;
   c->u_inject_set = true;
+  return 0;
+}
+
+// The active x range of the calls that follow (the nxs, nxe arguments of particle__solv, field__fdtd_i, sort__bucket,
+// bc__injection ...).  nxs must be nxgs (no app moves it); nxe <= nxge.  Cells beyond nxe must hold no particles.
+int wm_set_xrange(wm_ctx *c, int32_t nxs, int32_t nxe) {
+  if (!c) return fail("wm_set_xrange: null context");
+  if (nxs != c->cfg.nxgs) return fail("wm_set_xrange: nxs must equal nxgs (%d)", c->cfg.nxgs);
+  if (nxe > c->cfg.nxge || nxe - nxs < 4) return fail("wm_set_xrange: nxe must be in nxs+4..nxge");
+  if (nxe != c->cfg.nxge && c->P.bc != WM_BC_SHOCK)
+    return fail("wm_set_xrange: only the shock boundary module works on a sub-range (proj/shock/app.f90)");
+  c->nxa = nxe - nxs + 1;
+  if (c->P.bc == WM_BC_SHOCK && c->u_inject_set) WM(wm_set_u_inject(c, c->u_inject));
   return 0;
 }
 
@@ -926,7 +984,7 @@ int wm_boundary__injection(wm_ctx *c, double u0) {
   WM(wm_set_u_inject(c, u0));
   WM(need_state(c, ST_PUSHED, "wm_boundary__injection"));
   WM(set_device(c));
-  launch_bcx(c->P, c->soa[c->cur ^ 1], c->cstart[c->cur], true, c->st);
+  launch_bcx(fieldp(c), c->soa[c->cur ^ 1], c->cstart[c->cur], true, c->st);
   c->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -935,7 +993,7 @@ int wm_boundary__injection(wm_ctx *c, double u0) {
 int wm_boundary__particle_x(wm_ctx *c) {
   WM(need_state(c, ST_PUSHED, "wm_boundary__particle_x"));
   WM(set_device(c));
-  launch_bcx(c->P, c->soa[c->cur ^ 1], c->cstart[c->cur], false, c->st);
+  launch_bcx(fieldp(c), c->soa[c->cur ^ 1], c->cstart[c->cur], false, c->st);
   c->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -1022,7 +1080,7 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
   for (int it = 0; it < nsteps; it++) {
     if (c->timing) CU(cudaEventRecord(c->ev[0], c->st));
     // particle__solv + ele_cur + bc__particle_x/y + (histogram | move of the cell changers) in one pass, in place
-    launch_tmpf(P, c->f.uf, c->f.tmpf, c->st);
+    launch_tmpf(fieldp(c), c->f.uf, c->f.tmpf, c->st);
     CU(cudaMemsetAsync(c->f.uj, 0, ng * 3 * sizeof(double), c->st));
     WM(zero_sort_state(c));
     if (inplace) CU(cudaMemsetAsync(c->ovfcnt, 0, sizeof(int), c->st));
@@ -1216,7 +1274,7 @@ int wm_mom_calc__accl(wm_ctx *c) {
   WM(set_device(c));
   const DevParams &P = c->P;
   // half-step acceleration into the idle store, positions copied (mom_calc.f90:34,48-164)
-  launch_tmpf(P, c->f.uf, c->f.tmpf, c->st);
+  launch_tmpf(fieldp(c), c->f.uf, c->f.tmpf, c->st);
   WM(fill_dead(c, c->cur ^ 1));
   const int mode = M_PUSH | M_NOMOVE | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
   launch_pass1(mode, P, p1args(c, c->soa[c->cur], c->soa[c->cur ^ 1], P.delt * 0.5), c->st);
