@@ -1,0 +1,92 @@
+"""Restart snapshots in the reference's NAME.json + NAME.raw format (common/paraio.f90:93-426)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from helpers import flatten_by_id, make_world, oracle_state, particle_err, rel_to_max
+
+
+def _cfg(prm):
+    return dict(nxgs=prm["nxgs"], nxge=prm["nxgs"] + prm["nx"] - 1, nygs=prm["nygs"], nyge=prm["nygs"] + prm["ny"] - 1,
+                delx=prm["delx"], delt=prm["delt"], c=prm["c"], r=prm["r"], q=prm["q"])
+
+
+def test_restart_file_layout_and_roundtrip(tmp_path):
+    """Two ranks' arrays -> files -> back, bit for bit; byte layout and JSON schema as paraio__output writes them:
+    attributes in the reference's order at a running displacement, datasets rank-major with column-major shapes."""
+    from wumingpic2d_b200 import snapshot as S
+    prm, w = make_world(16, 12, 3, nranks=2, steps=2)
+    ups = [w.array(r, O.UP).copy() for r in range(2)]
+    np2s = [w.array(r, O.NP2).copy() for r in range(2)]
+    ufs = [w.array(r, O.UF).copy() for r in range(2)]
+    base = str(tmp_path / "0000002_restart")
+    S.write_restart(base, 2, prm["nxgs"], prm["nxgs"] + 15, _cfg(prm), ups, np2s, ufs)
+    root = json.load(open(base + ".json"))
+    assert list(root) == ["meta", "attribute", "dataset"]
+    assert root["meta"]["rawfile"] == "0000002_restart.raw" and root["meta"]["endian"] in (1, 16777216)
+    names = list(root["attribute"])
+    assert names == ["dummy_attribute", "it", "nxs", "nxe", "ndim", "np", "nxgs", "nxge", "nygs", "nyge", "nsp", "nproc",
+                     "delx", "delt", "c", "r", "q"]
+    for rec in root["attribute"].values():
+        assert set(rec) == {"datatype", "offset", "size", "ndim", "shape", "description", "data"}
+    off = 0
+    for n in names:   # running displacement, no padding
+        assert root["attribute"][n]["offset"] == off
+        off += root["attribute"][n]["size"]
+    assert root["attribute"]["dummy_attribute"]["data"] == 8 and root["attribute"]["nproc"]["data"] == 2
+    nyl, npcap = ups[0].shape[1], ups[0].shape[2]
+    d = root["dataset"]
+    assert d["up"]["shape"] == [6, npcap, nyl, 2, 2] and d["up"]["offset"] == off and d["up"]["size"] == 2 * ups[0].nbytes
+    assert d["np2"]["shape"] == [nyl, 2, 2] and d["np2"]["datatype"] == "i4"
+    assert d["uf"]["shape"] == [6, 16 + 4, nyl + 4, 2]
+    assert os.path.getsize(base + ".raw") == d["uf"]["offset"] + d["uf"]["size"]
+    # the second rank's first particle sits where the Fortran element up(1,1,nys,1) of rank 1 would be
+    raw = np.fromfile(base + ".raw", dtype=np.float64, count=6, offset=d["up"]["offset"] + ups[0].nbytes)
+    assert np.array_equal(raw.view(np.int64), ups[1][0, 0, 0].view(np.int64))   # (the id is a bit pattern: NaN as a double)
+    attrs, up2, np22, uf2 = S.read_restart(base)
+    assert attrs["it"] == 2 and attrs["q"] == list(prm["q"]) and attrs["delt"] == prm["delt"]
+    for r in range(2):
+        assert np.array_equal(up2[r].view(np.int64), ups[r].view(np.int64))
+        assert np.array_equal(np22[r], np2s[r]) and np.array_equal(uf2[r], ufs[r])
+    w.close()
+
+
+@pytest.mark.gpu
+def test_restart_into_fresh_context_matches_oracle(tmp_path):
+    """Save a device state, load it into a fresh Context (rows re-bucketed on upload, CG warm start zero, as in the
+    reference's restart path proj/weibel/app.f90:349-353) and step: same as an oracle world restarted from the file."""
+    import wumingpic2d_b200 as wm
+    from wumingpic2d_b200 import snapshot as S
+    prm, w0 = make_world(40, 24, 8, steps=3)
+    s = oracle_state(w0)
+    a = wm.Context.from_params(prm)
+    a.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    a.upload_field(s["uf"])
+    a.step(2)
+    base = str(tmp_path / "snap")
+    S.save_context(base, a, 5, _cfg(prm))
+    a.close()
+    attrs, up, np2, uf = S.read_restart(base)
+    # oracle restarted from the file: up -> gp, sort__bucket, df = 0
+    w = O.World(prm)
+    w.array(0, O.GP)[...] = up[0]
+    w.array(0, O.NP2)[...] = np2[0]
+    w.array(0, O.UF)[...] = uf[0]
+    w.sort_bucket()
+    b = wm.Context.from_params(prm)
+    S.load_into_context(base, b)
+    for it in range(2):
+        w.step(1); b.step(1)
+        assert b.cg_iters() == w.cg_iters()
+        upb, np2b, cum = b.download_particles()
+        assert np.array_equal(cum, w.array(0, O.CUMCNT))
+        x, y = flatten_by_id(upb, np2b), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
+        assert np.array_equal(x[0], y[0])
+        ex, eu = particle_err(x[2], y[2], prm["nx"], prm["vte"])
+        tol = 1e-12 if it == 0 else 1e-10
+        assert ex <= tol and eu <= tol
+        assert rel_to_max(b.download_field(), w.array(0, O.UF)).max() <= tol
+    b.close(); w.close(); w0.close()

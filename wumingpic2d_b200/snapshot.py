@@ -1,0 +1,111 @@
+"""Restart snapshots in the reference's format: the pair NAME.json + NAME.raw written by
+`paraio__output` (common/paraio.f90:93-228) and read back by `paraio__input` (:233-426).
+
+The raw file is a flat concatenation in native byte order; the JSON gives names, types, byte offsets and column-major
+shapes (utils/iocore/jsonio.f90:128-192).  Attributes, in this order (paraio.f90:143-155, 963-1000):
+    dummy_attribute (i4, = MPI_OFFSET_KIND), it, nxs, nxe, ndim, np, nxgs, nxge, nygs, nyge, nsp, nproc (i4),
+    delx, delt, c (f8), r(nsp), q(nsp) (f8)
+Datasets (paraio.f90:168-213), every rank's whole local array, rank-major:
+    up  f8 [ndim, np, nyl, nsp, nproc]      np2 i4 [nyl, nsp, nproc]      uf  f8 [6, nx+4, nyl+4, nproc]  (with ghosts)
+
+Arrays on the Python side are in C order = reversed Fortran order, like everywhere in this package
+(`up[rank].shape == (nsp, nyl, np, 6)`, `np2[rank].shape == (nsp, nyl)`, `uf[rank].shape == (nyl+4, nx+4, 6)`), so a
+dataset is simply the concatenation of the ranks' buffers.
+
+A snapshot written by a real reference run (built elsewhere) can be loaded as the initial condition of a Context and
+its next snapshot compared: the only route to parity against the actual Fortran binary.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+_DT = {"i4": np.int32, "i8": np.int64, "f4": np.float32, "f8": np.float64}
+_I4_ATTRS = ("dummy_attribute", "it", "nxs", "nxe", "ndim", "np", "nxgs", "nxge", "nygs", "nyge", "nsp", "nproc")
+_F8_ATTRS = ("delx", "delt", "c", "r", "q")
+
+
+def endian_flag():
+    """mpiio_get_endian_flag (utils/iocore/mpiio.f90): the int32 1 as the writer's memory holds it, read big-endian."""
+    return 1 if sys.byteorder == "big" else 16777216
+
+
+def write_restart(base, it, nxs, nxe, cfg, up, np2, uf):
+    """Write `base`.json + `base`.raw.  cfg: dict with ndim, np, nxgs, nxge, nygs, nyge, nsp, delx, delt, c, r, q.
+    up, np2, uf: lists with one array per rank (equal nyl on every rank, as the format requires)."""
+    nproc = len(up)
+    nsp, nyl, npcap, ndim = up[0].shape
+    if any(a.shape != up[0].shape for a in up) or any(a.shape != uf[0].shape for a in uf):
+        raise ValueError("all ranks must hold the same number of rows (common/paraio.f90:168-213)")
+    vals = dict(dummy_attribute=8, it=it, nxs=nxs, nxe=nxe, ndim=ndim, np=npcap, nxgs=cfg["nxgs"], nxge=cfg["nxge"],
+                nygs=cfg["nygs"], nyge=cfg["nyge"], nsp=nsp, nproc=nproc, delx=cfg["delx"], delt=cfg["delt"], c=cfg["c"],
+                r=list(cfg["r"])[:nsp], q=list(cfg["q"])[:nsp])
+    root = {"meta": {"endian": endian_flag(), "rawfile": os.path.basename(base) + ".raw"}, "attribute": {}, "dataset": {}}
+    disp = 0
+    with open(base + ".raw", "wb") as f:
+        for name in _I4_ATTRS + _F8_ATTRS:
+            dt = "i4" if name in _I4_ATTRS else "f8"
+            a = np.atleast_1d(np.asarray(vals[name], dtype=_DT[dt]))
+            root["attribute"][name] = {"datatype": dt, "offset": disp, "size": int(a.nbytes), "ndim": 1, "shape": [int(a.size)],
+                                       "description": "", "data": (a.tolist() if a.size > 1 else a.tolist()[0])}
+            f.write(a.tobytes())
+            disp += a.nbytes
+        nxg = uf[0].shape[1]
+        for name, dt, arrs, shape, desc in (
+                ("up", "f8", up, [ndim, npcap, nyl, nsp, nproc], "particles"),
+                ("np2", "i4", np2, [nyl, nsp, nproc], "number of active particles"),
+                ("uf", "f8", uf, [6, nxg, uf[0].shape[0], nproc], "electromagnetic fields including ghost cells")):
+            size = 0
+            for a in arrs:
+                b = np.ascontiguousarray(a, dtype=_DT[dt])
+                f.write(b.tobytes())
+                size += b.nbytes
+            root["dataset"][name] = {"datatype": dt, "offset": disp, "size": int(size), "ndim": len(shape), "shape": shape,
+                                     "description": desc}
+            disp += size
+    with open(base + ".json", "w") as f:
+        json.dump(root, f, indent=2)
+    return root
+
+
+def read_restart(base):
+    """Read `base`.json + its raw file.  Returns (attrs: dict, up, np2, uf: lists with one array per rank)."""
+    with open(base + ".json") as f:
+        root = json.load(f)
+    swap = root["meta"]["endian"] != endian_flag()
+    raw = os.path.join(os.path.dirname(base), root["meta"]["rawfile"])
+
+    def fetch(rec):
+        dt = np.dtype(_DT[rec["datatype"]])
+        a = np.fromfile(raw, dtype=dt, count=rec["size"] // dt.itemsize, offset=rec["offset"])
+        return a.byteswap() if swap else a
+
+    attrs = {}
+    for name, rec in root["attribute"].items():
+        a = fetch(rec)
+        attrs[name] = a.tolist() if a.size > 1 else a.tolist()[0]
+    ds = root["dataset"]
+    ndim, npcap, nyl, nsp, nproc = ds["up"]["shape"]
+    up = list(fetch(ds["up"]).reshape(nproc, nsp, nyl, npcap, ndim))
+    np2 = list(fetch(ds["np2"]).reshape(nproc, nsp, nyl))
+    six, nxg, nylg, _ = ds["uf"]["shape"]
+    uf = list(fetch(ds["uf"]).reshape(nproc, nylg, nxg, six))
+    return attrs, up, np2, uf
+
+
+def save_context(base, ctx, it, cfg, comm_gather=None):
+    """Snapshot of one Context (one rank; pass lists gathered from all ranks through write_restart for more)."""
+    up, np2, _ = ctx.download_particles()
+    uf = ctx.download_field()
+    return write_restart(base, it, cfg["nxgs"], cfg["nxge"], cfg, [up], [np2], [uf])
+
+
+def load_into_context(base, ctx, rank=0):
+    """paraio__input followed by sort__bucket, as the applications do on restart (proj/weibel/app.f90:349-353): the
+    rows of `up` are re-bucketed on upload, the CG warm start starts from zero (the reference's SAVEd df is not part
+    of a snapshot either, common/field.f90:98)."""
+    attrs, up, np2, uf = read_restart(base)
+    ctx.upload_particles(np.ascontiguousarray(up[rank]), np.ascontiguousarray(np2[rank]))
+    ctx.upload_field(np.ascontiguousarray(uf[rank]))
+    return attrs
