@@ -226,7 +226,11 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
   mbar_wait(&s_bar, 0);
 
   const int wid = tid >> 5, lane = tid & 31;
-  const int grp = lane >> 3, l8 = lane & 7;
+  const int grp = lane >> 3;
+  int l8 = lane & 7;
+  unsigned lanelt = (1u << lane) - 1u;  // lanes below me
+  pin(l8);
+  pin(lanelt);
   unsigned below = (1u << l8) - 1u;
   int gsh = grp * 8;
   pin(below);
@@ -237,6 +241,9 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
   int myqi = (wid * 4 + grp) * (QCAP * 3);
   pin(myqi);
   double2 *const myq = &s_q[myqi];
+  unsigned myq_a = smem_u32(myq), sarr_a = smem_u32(s_arr);  // 32-bit shared addresses for the stores / atomics of the loop
+  pin(myq_a);
+  pin(sarr_a);
 
   int nb0 = 0, nc0 = 0, nb1 = 0, nc1 = 0;
   {
@@ -474,10 +481,10 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
           const unsigned bald = __ballot_sync(0xffffffffu, dmove);
           const unsigned d8 = (bald >> gsh) & 0xffu;
           if (dmove) {
-            double2 *r = myq + (qn + __popc(d8 & below)) * 3;  // qn <= QCAP - 8 here
-            r[0] = make_double2(hx, hy);
-            r[1] = make_double2(dxn, dyn);
-            r[2] = make_double2(qvz, qf);
+            const unsigned r = myq_a + (unsigned)(qn + __popc(d8 & below)) * 48u;  // qn <= QCAP - 8 here
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(r), "d"(hx), "d"(hy) : "memory");
+            asm volatile("st.shared.v2.f64 [%0+16], {%1, %2};" ::"r"(r), "d"(dxn), "d"(dyn) : "memory");
+            asm volatile("st.shared.v2.f64 [%0+32], {%1, %2};" ::"r"(r), "d"(qvz), "d"(qf) : "memory");
           }
           qn += __popc(d8);
         }
@@ -548,11 +555,13 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
             tg = TAG_DEAD;
           } else {
             const int w = w0 + incy * WINX + incx;
-            tg = TAG_ARRIVAL | ((uint32_t)(w - isp * WIN) << TAG_WSHIFT) | (uint32_t)atomicAdd(&s_arr[w], 1);
+            unsigned rk;  // rank among the arrivals of window cell w: one shared-memory integer atomic
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(rk) : "r"(sarr_a + (unsigned)w * 4u) : "memory");
+            tg = TAG_ARRIVAL | ((uint32_t)(w - isp * WIN) << TAG_WSHIFT) | rk;
           }
           // stage the record (64 B: x y | ux uy | uz id | tag -) in the idle store, in the shadow of
           // this quad; slot order = ballot rank, so the stores of a warp are contiguous
-          const int sk = nmv + __popc(balm & ((1u << lane) - 1u));
+          const int sk = nmv + __popc(balm & lanelt);
           if (sk < qcap) {
             double2 *d = reinterpret_cast<double2 *>(a.dst.x.p) + (size_t)(qrec + sk) * 4;
             d[0] = make_double2(xn, yn);
