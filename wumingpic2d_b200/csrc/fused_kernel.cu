@@ -432,15 +432,15 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
               const int w = (cy + 1 + incy) * WINX + (cx + 1 + incx);
               tg = TAG_ARRIVAL | ((uint32_t)w << TAG_WSHIFT) | (uint32_t)atomicAdd(&s_arr[isp * WIN + w], 1);
             }
-            // stage the record (64 B: x y | ux uy | uz id | tag -) in the idle store, in the shadow of
+            // stage the record (48 B: x y | ux uy | uz id) and its tag in the idle store, in the shadow of
             // this quad; slot order = ballot rank, so the stores of a warp are contiguous
             const int sk = nmv + __popc(balm & ((1u << lane) - 1u));
             if (sk < qcap) {
-              double2 *d = reinterpret_cast<double2 *>(a.dst.x.p) + (size_t)(qrec + sk) * 4;
+              double2 *d = reinterpret_cast<double2 *>(a.dst.x.p) + (size_t)(qrec + sk) * 3;
               d[0] = make_double2(xn, yn);
               d[1] = make_double2(un1, un2);
               d[2] = make_double2(un3, idc);
-              d[3] = make_double2(__longlong_as_double((long long)tg), 0.0);
+              a.tag[qrec + sk] = tg;
             } else {
               atomicOr(a.err, ERR_OVERFLOW);
             }
@@ -507,15 +507,15 @@ __global__ void __launch_bounds__(FT, MINB) k_fused(const DevParams P, const Pas
                 tg = TAG_ARRIVAL | ((uint32_t)w << TAG_WSHIFT) | (uint32_t)rk;
               }
               if (INPLACE) {
-                // stage the record (64 B: x y | ux uy | uz id | tag -) in the idle store, in the shadow of
+                // stage the record (48 B: x y | ux uy | uz id) and its tag in the idle store, in the shadow of
                 // this quad; slot order = ballot rank, so the stores of a warp are contiguous
                 const int sk = nmv + __popc(balm & ((1u << lane) - 1u));
                 if (sk < qcap) {
-                  double2 *d = reinterpret_cast<double2 *>(a.dst.x.p) + (size_t)(qrec + sk) * 4;
+                  double2 *d = reinterpret_cast<double2 *>(a.dst.x.p) + (size_t)(qrec + sk) * 3;
                   d[0] = make_double2(xn, yn);
                   d[1] = make_double2(un1, un2);
                   d[2] = make_double2(un3, idv);
-                  d[3] = make_double2(__longlong_as_double((long long)tg), 0.0);
+                  a.tag[qrec + sk] = tg;
                 } else {
                   atomicOr(a.err, ERR_OVERFLOW);
                 }

@@ -35,8 +35,8 @@ void launch_incoming_append(const DevParams &P, const double *rec, int n, int is
                             const PartSoA &dst, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
                             cudaStream_t st);
 // in-place sort: append the records staged by k_fused<INPLACE> to their new segments, retire vacated slots
-void launch_place(const DevParams &P, const double *stage, const PartSoA &dst, const int *cstart, int *cnt_new,
-                  const int *tilebase, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err, cudaStream_t st);
+void launch_place(const DevParams &P, const double *stage, const uint32_t *tag, const PartSoA &dst, const int *cstart,
+                  int *cnt_new, const int *tilebase, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err, cudaStream_t st);
 void launch_clamp_counts(const DevParams &P, const int *cstart, int *cnt, cudaStream_t st);
 void launch_mark_dead(const DevParams &P, PView<double> x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st);
 // fused push + deposit + boundaries that moves cell changers itself (no tags, no scatter pass)

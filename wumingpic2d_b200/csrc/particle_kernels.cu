@@ -900,7 +900,8 @@ __global__ void k_incoming_append(const DevParams P, const double *__restrict__ 
 constexpr int PL_THREADS = 256;
 constexpr int PL_NQ = (TX / 4) * TY;
 constexpr int PL_MAX = 4096;  // records placed per round
-__global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const double2 *__restrict__ stage, const PartSoA dst,
+__global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const double2 *__restrict__ stage,
+                                                      const uint32_t *__restrict__ tag, const PartSoA dst,
                                                       const int *__restrict__ cstart, int *cnt_new,
                                                       const int *__restrict__ tilebase, double *ovf, int *ovfsp, int *ovfcnt,
                                                       int ovfcap, unsigned *err) {
@@ -965,7 +966,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const d
         if (s_off[mid] <= k) lo = mid; else hi = mid;
       }
       const long long ri = s_rec0[lo] + (k - s_off[lo]);
-      const uint32_t t = (uint32_t)__double_as_longlong(stage[ri * 4 + 3].x);
+      const uint32_t t = tag[ri];
       if (t == TAG_DEAD) continue;  // left the slab: already in the send buffer
       const int e = (lo / PL_NQ) * WIN + (int)((t >> TAG_WSHIFT) & 0xff);
       const int j = s_pref[e] + (int)(t & TAG_RANK_MASK) - j0;
@@ -976,8 +977,8 @@ __global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const d
     const int nj = min(PL_MAX, total - j0);
     for (int j = tid; j < nj; j += PL_THREADS) {
       const long long ri = s_rec0[0] + s_inv[j];
-      const double2 r0 = stage[ri * 4], r1 = stage[ri * 4 + 1], r2 = stage[ri * 4 + 2];
-      const uint32_t t = (uint32_t)__double_as_longlong(stage[ri * 4 + 3].x);
+      const double2 r0 = stage[ri * 3], r1 = stage[ri * 3 + 1], r2 = stage[ri * 3 + 2];
+      const uint32_t t = tag[ri];
       int lo = 0, hi = nwin;  // largest e with s_pref[e] <= j0 + j
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -1108,10 +1109,11 @@ void launch_incoming_append(const DevParams &P, const double *rec, int n, int is
   if (n > 0)
     k_incoming_append<<<(n + 255) / 256, 256, 0, st>>>(P, rec, n, isp, cstart, cnt_tail, dst, ovf, ovfsp, ovfcnt, ovfcap, err);
 }
-void launch_place(const DevParams &P, const double *stage, const PartSoA &dst, const int *cstart, int *cnt_new,
-                  const int *tilebase, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err, cudaStream_t st) {
-  k_place<<<P.ntx * P.nty, PL_THREADS, 0, st>>>(P, reinterpret_cast<const double2 *>(stage), dst, cstart, cnt_new, tilebase, ovf,
-                                               ovfsp, ovfcnt, ovfcap, err);
+void launch_place(const DevParams &P, const double *stage, const uint32_t *tag, const PartSoA &dst, const int *cstart,
+                  int *cnt_new, const int *tilebase, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
+                  cudaStream_t st) {
+  k_place<<<P.ntx * P.nty, PL_THREADS, 0, st>>>(P, reinterpret_cast<const double2 *>(stage), tag, dst, cstart, cnt_new, tilebase,
+                                               ovf, ovfsp, ovfcnt, ovfcap, err);
 }
 void launch_mark_dead(const DevParams &P, PView<double> x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st) {
   k_mark_dead<<<148 * 16, 256, 0, st>>>(P, x, cstart, cnt_old, cnt_new);

@@ -1109,7 +1109,7 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
       CU(cudaEventRecord(c->ev_fork, c->st));
       CU(cudaStreamWaitEvent(c->st2, c->ev_fork, 0));
       if (c->timing) CU(cudaEventRecord(c->ev_b[0], c->st2));
-      launch_place(P, c->pbuf[c->cur ^ 1], a, c->cstart[c->cur], c->cnt_tail, c->tilebase, c->ovf, c->ovfsp, c->ovfcnt,
+      launch_place(P, c->pbuf[c->cur ^ 1], c->tag, a, c->cstart[c->cur], c->cnt_tail, c->tilebase, c->ovf, c->ovfsp, c->ovfcnt,
                    c->ovfcap, c->d_err, c->st2);
       launch_mark_dead(P, a.x, c->cstart[c->cur], c->cnt[c->cur], c->cnt_tail, c->st2);
       c->launches += 2;
@@ -1129,7 +1129,7 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
       WM(migrate(c, true));
       if (c->timing) CU(cudaEventRecord(c->ev[4], c->st));
       // sort__bucket, reduced to the cell changers: append them to their new segments
-      launch_place(P, c->pbuf[c->cur ^ 1], a, c->cstart[c->cur], c->cnt_tail, c->tilebase, c->ovf, c->ovfsp, c->ovfcnt,
+      launch_place(P, c->pbuf[c->cur ^ 1], c->tag, a, c->cstart[c->cur], c->cnt_tail, c->tilebase, c->ovf, c->ovfsp, c->ovfcnt,
                    c->ovfcap, c->d_err, c->st);
       launch_mark_dead(P, a.x, c->cstart[c->cur], c->cnt[c->cur], c->cnt_tail, c->st);
       c->launches += 2;

@@ -118,14 +118,14 @@ struct Pass1Args {
 // a slot holds a particle iff x >= 0 (positions are >= nxgs >= 1); dead = all-ones NaN = memset 0xFF
 __device__ __forceinline__ bool slot_live(double x) { return x >= 0.0; }
 __device__ __forceinline__ double dead_x() { return __longlong_as_double(-1LL); }
-// Staging of the cell changers (in-place sort): the idle particle store is reused as an array of
-// 64-byte records; the region of a quad is the image of its slot range [s0, s1) of the SoA store
-// (48 bytes per slot): records [ceil(3 s0 / 4), floor(3 s1 / 4)).  Regions of different quads are disjoint.
+// Staging of the cell changers (in-place sort): the idle particle store is reused as an array of 48-byte records
+// (x y | ux uy | uz id, three 16-byte words) and the tag array (4 bytes per slot) holds their sort tags; the region of
+// a quad is its own slot range [s0, s1): record r of the region is record s0 + r of the idle store, tag[s0 + r] its tag.
+// Regions of different quads are disjoint.
 __host__ __device__ inline long long so_slots(const DevParams &P, int isp) { return (long long)isp * P.cap; }
 __host__ __device__ inline void stage_region(long long s0, long long s1, long long *rec0, int *cap) {
-  *rec0 = (3 * s0 + 3) / 4;
-  const long long e = (3 * s1) / 4;
-  *cap = (int)(e > *rec0 ? e - *rec0 : 0);
+  *rec0 = s0;
+  *cap = (int)(s1 > s0 ? s1 - s0 : 0);
 }
 // window index -> local cell index with the periodic wraps; -1 = outside the slab
 __device__ __forceinline__ int window_cell(const DevParams &P, int li0, int lj0, int w) {
