@@ -94,7 +94,7 @@ struct V {  // Fortran-layout views of one rank
     return (size_t)(i - w->nxs) + (size_t)w->nx * (j - k->nys);
   }
   inline size_t MOM(int c, int i, int j, int isp) const {  // (7, nxgs-1:nxge+1, nys-1:nye+1, nsp)
-    return (size_t)(c - 1) + 7 * ((size_t)(i - (w->nxgs - 1)) + (size_t)(w->nx + 3) * ((size_t)(j - (k->nys - 1)) + (size_t)(k->nyl + 2) * (isp - 1)));
+    return (size_t)(c - 1) + 7 * ((size_t)(i - (w->nxgs - 1)) + (size_t)(w->nx + 2) * ((size_t)(j - (k->nys - 1)) + (size_t)(k->nyl + 2) * (isp - 1)));
   }
 };
 
@@ -1055,7 +1055,7 @@ orc_world *orc_create(const orc_config *cfg) {
     k.df.assign(6 * ng, 0.0);  // SAVEd warm start, zero on first call (field.f90:105-119)
     k.uj.assign(3 * ng, 0.0);
     k.gkl.assign((size_t)3 * w->nx * k.nyl, 0.0);
-    k.mom.assign((size_t)7 * (w->nx + 3) * (k.nyl + 2) * w->nsp, 0.0);
+    k.mom.assign((size_t)7 * (w->nx + 2) * (k.nyl + 2) * w->nsp, 0.0);
     k.np2.assign((size_t)k.nyl * w->nsp, 0);
     k.cumcnt.assign((size_t)(w->nx + 1) * k.nyl * w->nsp, 0);
     const size_t nph = (size_t)(w->nx + 2) * (k.nyl + 2), nri = (size_t)w->nx * k.nyl;

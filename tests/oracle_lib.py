@@ -154,7 +154,7 @@ class World:
         shp = {UP: (self.nsp, nyl, self.np_cap, 6), GP: (self.nsp, nyl, self.np_cap, 6),
                UF: (nyl + 4, self.nx + 4, 6), DF: (nyl + 4, self.nx + 4, 6),
                UJ: (nyl + 4, self.nx + 4, 3), GKL: (nyl, self.nx, 3),
-               MOM: (self.nsp, nyl + 2, self.nx + 3, 7)}[which]
+               MOM: (self.nsp, nyl + 2, self.nx + 2, 7)}[which]
         return a.reshape(shp)
 
     # stages ---------------------------------------------------------------

@@ -90,3 +90,34 @@ def test_restart_into_fresh_context_matches_oracle(tmp_path):
         assert ex <= tol and eu <= tol
         assert rel_to_max(b.download_field(), w.array(0, O.UF)).max() <= tol
     b.close(); w.close(); w0.close()
+
+
+def test_moment_file_matches_paraio_arithmetic(tmp_path):
+    """io__mom (common/paraio.f90:555-713): density, first and second moments divided by the density, cell-centred
+    fields with the reference's own averages (Bz: uf(3,i+1,j) twice, :684), checked against plain loops."""
+    from wumingpic2d_b200 import snapshot as S
+    prm, w = make_world(12, 8, 4, steps=2)
+    w.mom_accl(); w.mom_nvt(); w.bc_mom()
+    mom, uf = w.array(0, O.MOM).copy(), w.array(0, O.UF).copy()
+    base = str(tmp_path / "0000002_mom")
+    root = S.write_mom(base, 2, dict(_cfg(prm), np=prm["np"]), mom, uf)
+    assert list(root["dataset"]) == ["den", "vel", "temp", "uf"]
+    assert root["dataset"]["vel"]["shape"] == [3, 12, 8, 2] and root["dataset"]["uf"]["shape"] == [6, 12, 8]
+    d = S.read_datasets(base)
+    assert d["attribute"]["it"] == 2 and d["attribute"]["nsp"] == 2
+    den, vel, temp, cc = (d["dataset"][k] for k in ("den", "vel", "temp", "uf"))
+    nx, ny = 12, 8
+    for isp in range(2):
+        for j in range(ny):
+            for i in range(nx):
+                m = mom[isp, j + 1, i + 1]
+                assert den[isp, j, i] == m[0]
+                assert np.array_equal(vel[isp, j, i], m[1:4] / m[0]) and np.array_equal(temp[isp, j, i], m[4:7] / m[0])
+    for j in range(ny):
+        for i in range(nx):
+            u = lambda c, di, dj: uf[j + 2 + dj, i + 2 + di, c]
+            ref = [(u(0, 0, 0) + u(0, 0, 1)) / 2, (u(1, 0, 0) + u(1, 1, 0)) / 2,
+                   (u(2, 0, 0) + u(2, 1, 0) + u(2, 1, 0) + u(2, 1, 1)) / 4,
+                   (u(3, 0, 0) + u(3, 1, 0)) / 2, (u(4, 0, 0) + u(4, 0, 1)) / 2, u(5, 0, 0)]
+            assert np.array_equal(cc[j, i], ref)
+    w.close()

@@ -188,7 +188,7 @@ class Context:
     def shape_uj(self): return (self.nyl + 4, self.nx + 4, 3)
     def shape_np2(self): return (self.nsp, self.nyl)
     def shape_cumcnt(self): return (self.nsp, self.nyl, self.nx + 1)
-    def shape_mom(self): return (self.nsp, self.nyl + 2, self.nx + 3, 7)
+    def shape_mom(self): return (self.nsp, self.nyl + 2, self.nx + 2, 7)
 
     # ---- communicator
     def comm_unique_id(self):

@@ -137,7 +137,7 @@ __global__ void k_fold_y_local(const DevParams P, double *uj) {
 
 // mom: x fold of the single ghost column, all rows incl. ghosts   boundary_periodic.f90:579-584
 __global__ void k_mom_fold_x(const DevParams P, double *mom) {
-  const int nxp = P.nx + 3, nyp = P.nyl + 2;
+  const int nxp = P.nx + 2, nyp = P.nyl + 2;  // nxgs-1:nxge+1
   const int n = P.nsp * nyp * 7;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     const int m = t % 7, row = t / 7;  // row = isp*nyp + j
@@ -154,7 +154,7 @@ __global__ void k_mom_fold_x(const DevParams P, double *mom) {
 
 // mom: y fold when the ring has one rank (the neighbour is this rank)    boundary_periodic.f90:586-633
 __global__ void k_mom_fold_y_local(const DevParams P, double *mom) {
-  const int nxp = P.nx + 3, nyp = P.nyl + 2;
+  const int nxp = P.nx + 2, nyp = P.nyl + 2;  // nxgs-1:nxge+1
   const int w = nxp * 7;
   const int n = P.nsp * w;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
@@ -644,7 +644,7 @@ void launch_mom_fold_x(const DevParams &P, double *mom, cudaStream_t st) {
   k_mom_fold_x<<<gblocks((long long)P.nsp * (P.nyl + 2) * 7), 256, 0, st>>>(P, mom);
 }
 void launch_mom_fold_y_local(const DevParams &P, double *mom, cudaStream_t st) {
-  k_mom_fold_y_local<<<gblocks((long long)P.nsp * (P.nx + 3) * 7), 256, 0, st>>>(P, mom);
+  k_mom_fold_y_local<<<gblocks((long long)P.nsp * (P.nx + 2) * 7), 256, 0, st>>>(P, mom);
 }
 void launch_add_rows(double *dst, const double *src, long long n, cudaStream_t st) {
   k_add<<<gblocks(n), 256, 0, st>>>(dst, src, n);

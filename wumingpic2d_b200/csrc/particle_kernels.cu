@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(256) k_kinetic(const DevParams P, const PartSo
   }
 }
 
-// moments with bilinear weights (mom_calc.f90:167-249): mom (7, nx+3, nyl+2, nsp), RED.ADD.F64
+// moments with bilinear weights (mom_calc.f90:167-249): mom (7, nx+2, nyl+2, nsp) = (7, nxgs-1:nxge+1, nys-1:nye+1, nsp), RED.ADD.F64
 __global__ void k_moments(const DevParams P, const PartSoA src, const PView<double> keyx,
                           const int *__restrict__ cstart, double *mom) {
   for (int isp = 0; isp < P.nsp; isp++) {
@@ -763,9 +763,9 @@ __global__ void k_moments(const DevParams P, const PartSoA src, const PView<doub
       const double gam = 1. / sqrt(1.0 + (u1 * u1 + u2 * u2 + u3 * u3) / P.cc);
       const double val[7] = {1.0, u1 * gam, u2 * gam, u3 * gam, u1 * u1 * gam, u2 * u2 * gam, u3 * u3 * gam};
       const int mi = ih - (P.nxgs - 1), mj = jh - (P.nys - 1);
-      if (mi < 0 || mi + 1 >= P.nx + 3 || mj < 0 || mj + 1 >= P.nyl + 2) continue;
-      double *m00 = mom + (((size_t)isp * (P.nyl + 2) + mj) * (P.nx + 3) + mi) * 7;
-      double *m01 = m00 + 7, *m10 = m00 + (size_t)(P.nx + 3) * 7, *m11 = m10 + 7;
+      if (mi < 0 || mi + 1 >= P.nx + 2 || mj < 0 || mj + 1 >= P.nyl + 2) continue;
+      double *m00 = mom + (((size_t)isp * (P.nyl + 2) + mj) * (P.nx + 2) + mi) * 7;
+      double *m01 = m00 + 7, *m10 = m00 + (size_t)(P.nx + 2) * 7, *m11 = m10 + 7;
 #pragma unroll
       for (int m = 0; m < 7; m++) {
         atomicAdd(&m00[m], val[m] * dxm * dym);

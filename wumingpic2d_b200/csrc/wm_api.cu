@@ -578,7 +578,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   for (double *a : {c->f.uf, c->f.df, c->f.tmpf}) CU(cudaMemset(a, 0, ng * 6 * sizeof(double)));  // df=0: field.f90:109-111
   for (double *a : {c->f.uj, c->f.gkl, c->f.phi, c->f.p, c->f.p2, c->f.r, c->f.ap}) CU(cudaMemset(a, 0, ng * 3 * sizeof(double)));
   CU(cudaMalloc(&c->rowtmp, (size_t)P.pitch * 2 * 6 * sizeof(double)));
-  CU(cudaMalloc(&c->mom, (size_t)7 * (nx + 3) * (nyl + 2) * P.nsp * sizeof(double)));
+  CU(cudaMalloc(&c->mom, (size_t)7 * (nx + 2) * (nyl + 2) * P.nsp * sizeof(double)));
   CU(cudaMalloc(&c->gcnt, (size_t)P.nsp * P.ncell * sizeof(int)));
   CU(cudaMalloc(&c->tilebase, (size_t)P.ntx * P.nty * P.nsp * 2 * WIN * sizeof(int)));
   CU(cudaMalloc(&c->scan_scratch, (size_t)scan_scratch_ints(P.ncell) * sizeof(int)));
@@ -1251,7 +1251,7 @@ static int bc_mom_device(wm_ctx *c) {
     return 0;
   }
   if (!c->comm) return fail("nsize > 1 but wm_comm_init has not been called");
-  const size_t w = (size_t)(P.nx + 3) * 7;
+  const size_t w = (size_t)(P.nx + 2) * 7;
   const size_t nyp = (size_t)P.nyl + 2;
   for (int isp = 0; isp < P.nsp; isp++) {
     double *b = c->mom + (size_t)isp * nyp * w;
@@ -1272,7 +1272,7 @@ static int bc_mom_device(wm_ctx *c) {
   return 0;
 }
 
-static size_t mom_elems(const wm_ctx *c) { return (size_t)7 * (c->P.nx + 3) * (c->P.nyl + 2) * c->P.nsp; }
+static size_t mom_elems(const wm_ctx *c) { return (size_t)7 * (c->P.nx + 2) * (c->P.nyl + 2) * c->P.nsp; }
 
 int wm_mom_calc__accl(wm_ctx *c) {
   WM(need_state(c, ST_SORTED, "wm_mom_calc__accl"));

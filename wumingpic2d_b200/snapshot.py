@@ -109,3 +109,86 @@ def load_into_context(base, ctx, rank=0):
     ctx.upload_particles(np.ascontiguousarray(up[rank]), np.ascontiguousarray(np2[rank]))
     ctx.upload_field(np.ascontiguousarray(uf[rank]))
     return attrs
+
+
+def _write_file(base, attrs, datasets):
+    """Common writer: attrs = [(name, dtype, value)], datasets = [(name, dtype, array(C order), Fortran shape, desc)]."""
+    root = {"meta": {"endian": endian_flag(), "rawfile": os.path.basename(base) + ".raw"}, "attribute": {}, "dataset": {}}
+    disp = 0
+    with open(base + ".raw", "wb") as f:
+        for name, dt, val in attrs:
+            a = np.atleast_1d(np.asarray(val, dtype=_DT[dt]))
+            root["attribute"][name] = {"datatype": dt, "offset": disp, "size": int(a.nbytes), "ndim": 1, "shape": [int(a.size)],
+                                       "description": "", "data": (a.tolist() if a.size > 1 else a.tolist()[0])}
+            f.write(a.tobytes())
+            disp += a.nbytes
+        for name, dt, arr, shape, desc in datasets:
+            b = np.ascontiguousarray(arr, dtype=_DT[dt])
+            f.write(b.tobytes())
+            root["dataset"][name] = {"datatype": dt, "offset": disp, "size": int(b.nbytes), "ndim": len(shape),
+                                     "shape": [int(x) for x in shape], "description": desc}
+            disp += b.nbytes
+    with open(base + ".json", "w") as f:
+        json.dump(root, f, indent=2)
+    return root
+
+
+def moment_datasets(mom, uf):
+    """The arithmetic of paraio__mom (common/paraio.f90:640-694) on one slab or on the whole domain:
+    mom (nsp, nyl+2, nx+2, 7) with one ghost cell per side as mom_calc__nvt + bc__mom leave it, uf (nyl+4, nx+4, 6).
+    Returns den (nsp, ny, nx), vel, temp (nsp, ny, nx, 3) -- second moments divided by the density, not centred --
+    and the cell-centred fields (ny, nx, 6), literally as the reference averages them (its Bz average takes
+    uf(3,i+1,j) twice and never uf(3,i,j+1), paraio.f90:684)."""
+    m = np.asarray(mom)[:, 1:-1, 1:-1, :]     # nxgs:nxge, nys:nye
+    den = m[..., 0].copy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        vel = m[..., 1:4] / m[..., 0:1]
+        temp = m[..., 4:7] / m[..., 0:1]
+    u = np.asarray(uf)
+    c = u[2:-2, 2:-2]
+    xp = u[2:-2, 3:-1]      # i+1
+    yp = u[3:-1, 2:-2]      # j+1
+    xyp = u[3:-1, 3:-1]     # i+1, j+1
+    cc = np.empty(c.shape)
+    cc[..., 0] = (c[..., 0] + yp[..., 0]) / 2
+    cc[..., 1] = (c[..., 1] + xp[..., 1]) / 2
+    cc[..., 2] = (c[..., 2] + xp[..., 2] + xp[..., 2] + xyp[..., 2]) / 4
+    cc[..., 3] = (c[..., 3] + xp[..., 3]) / 2
+    cc[..., 4] = (c[..., 4] + yp[..., 4]) / 2
+    cc[..., 5] = c[..., 5]
+    return den, vel, temp, cc
+
+
+def write_mom(base, it, cfg, mom, uf, nproc=1):
+    """NNNNNNN_mom.json/.raw as paraio__mom writes it (common/paraio.f90:555-713): attributes dummy_attribute, it and
+    the common metadata, datasets den [nx,ny,nsp], vel [3,nx,ny,nsp], temp [3,nx,ny,nsp], uf [6,nx,ny] (global
+    arrays; pass the slabs concatenated along y, ghost rows only at the outer ends)."""
+    den, vel, temp, cc = moment_datasets(mom, uf)
+    nsp, ny, nx = den.shape
+    attrs = [("dummy_attribute", "i4", 8), ("it", "i4", it), ("ndim", "i4", 6), ("np", "i4", cfg.get("np", 0)),
+             ("nxgs", "i4", cfg["nxgs"]), ("nxge", "i4", cfg["nxge"]), ("nygs", "i4", cfg["nygs"]), ("nyge", "i4", cfg["nyge"]),
+             ("nsp", "i4", nsp), ("nproc", "i4", nproc), ("delx", "f8", cfg["delx"]), ("delt", "f8", cfg["delt"]),
+             ("c", "f8", cfg["c"]), ("r", "f8", list(cfg["r"])[:nsp]), ("q", "f8", list(cfg["q"])[:nsp])]
+    ds = [("den", "f8", den, [nx, ny, nsp], "density"), ("vel", "f8", vel, [3, nx, ny, nsp], "velocity"),
+          ("temp", "f8", temp, [3, nx, ny, nsp], "temperature"), ("uf", "f8", cc, [6, nx, ny], "electromagnetic field")]
+    return _write_file(base, attrs, ds)
+
+
+def read_datasets(base):
+    """Generic reader: every attribute and dataset of a NAME.json + raw pair; datasets come back in C order
+    (reversed Fortran shape)."""
+    with open(base + ".json") as f:
+        root = json.load(f)
+    swap = root["meta"]["endian"] != endian_flag()
+    raw = os.path.join(os.path.dirname(base), root["meta"]["rawfile"])
+    out = {"attribute": {}, "dataset": {}}
+    for kind in ("attribute", "dataset"):
+        for name, rec in root[kind].items():
+            dt = np.dtype(_DT[rec["datatype"]])
+            a = np.fromfile(raw, dtype=dt, count=rec["size"] // dt.itemsize, offset=rec["offset"])
+            a = a.byteswap() if swap else a
+            if kind == "attribute":
+                out[kind][name] = a.tolist() if a.size > 1 else a.tolist()[0]
+            else:
+                out[kind][name] = a.reshape(rec["shape"][::-1])
+    return out
