@@ -65,3 +65,45 @@ def test_golden_fixture_on_gpu():
         assert rel_to_max(c.download_field(), g["uf"]).max() <= tol
         assert np.allclose(c.energy(), g["energy"], rtol=1e-10, atol=0)
         c.close()
+
+
+def test_full_size_slab_invariants():
+    """BASELINE configs[1] at its full single-GPU size (4096 x 512 cells, 64 ppc x 2 species = 268,435,456 particles;
+    too large for the oracle): size-independent properties after 6 steps of the production path.
+      * particle number conserved per species, per-cell bookkeeping consistent (cumcnt monotone, ends at np2,
+        cell sums == totals), no layout rebuild, no error flag;
+      * the per-row totals of the two species are equal at t = 0 (ions and electrons are created in pairs,
+        proj/weibel/app.f90:408-411);
+      * total energy conserved to 1e-4 relative over the 6 steps, kinetic energies of the two species equal at t = 0
+        (mass ratio 1, same thermal speed) and the magnetic energy grows from 0 (Weibel);
+      * moments: the density summed over the grid equals the particle number (bilinear weights sum to 1,
+        common/mom_calc.f90:190-243) to 1e-12 relative;
+      * CG iteration counts are sane (< 30; 100 would be the reference's stop condition, field.f90:427-430)."""
+    import torch
+    import wumingpic2d_b200 as wm
+    if torch.cuda.mem_get_info(0)[0] < 60e9:
+        pytest.skip("needs 60 GB of free device memory")
+    nx, rows, ppc = 4096, 512, 64
+    prm = O.weibel_params(nx, rows, ppc, cap_factor=1.25)
+    c = wm.Context.from_params(prm)
+    c.ic_weibel(20260117, ppc, prm["vti"], prm["vte"], prm["t_ani"], prm["b0"])
+    n0 = c.particle_counts()
+    assert n0 == [nx * rows * ppc, nx * rows * ppc]
+    _, np2a, cuma = c.download_particles(want_up=False)
+    assert np.array_equal(np2a[0], np2a[1]) and int(np2a.sum()) == 2 * nx * rows * ppc
+    e0 = c.energy()
+    assert abs(e0[0] - e0[1]) <= 1e-3 * e0[0] and e0[3] == 0.0
+    c.step(6)
+    assert c.particle_counts() == n0
+    assert c.rebuilds() == 0
+    assert max(c.cg_iters()) < 30
+    _, np2, cum = c.download_particles(want_up=False)
+    assert int(np2.sum()) == 2 * nx * rows * ppc
+    assert np.all(np.diff(cum, axis=-1) >= 0) and np.all(cum[..., 0] == 0) and np.array_equal(cum[..., -1], np2)
+    e1 = c.energy()
+    assert abs(e1.sum() - e0.sum()) <= 1e-4 * e0.sum()
+    assert e1[3] > 0.0
+    mom = c.moments()     # mom_calc__accl + mom_calc__nvt + bc__mom
+    dens = mom[:, 1:-1, 1:-1, 0].sum(axis=(1, 2))
+    assert np.all(np.abs(dens - nx * rows * ppc) <= 1e-12 * nx * rows * ppc * 10)
+    c.close()
