@@ -148,6 +148,10 @@ int wm_cg_iters(wm_ctx *ctx, int32_t out[3]);  /* CG iterations of the last solv
 /* energy_history (proj/weibel/app.f90:479-545), this rank's share:
  * out[0..nsp-1] kinetic, out[nsp] = sum E^2/8pi, out[nsp+1] = sum B^2/8pi */
 int wm_energy(wm_ctx *ctx, double *out);
+/* discrete Gauss law of the current state (north_star: "div E - rho/eps0 must hold to roundoff"; Gaussian units:
+ * div E = 4 pi rho, common/field.f90:159): out[0] = max |div E - 4 pi rho| over the cells, rho with the deposit's
+ * second-order shape, out[1] = max 4 pi sum |q| S S, the scale.  Periodic boundaries, one rank. */
+int wm_gauss_residual(wm_ctx *ctx, double out[2]);
 /* mom_calc__accl (common/mom_calc.f90:48): half-step momenta into the device's idle particle
  * store (the reference's `gp`); valid until the next call that moves or transfers particles */
 int wm_mom_calc__accl(wm_ctx *ctx);

@@ -78,6 +78,7 @@ def test_full_size_slab_invariants():
         (mass ratio 1, same thermal speed) and the magnetic energy grows from 0 (Weibel);
       * moments: the density summed over the grid equals the particle number (bilinear weights sum to 1,
         common/mom_calc.f90:190-243) to 1e-12 relative;
+      * the discrete Gauss law div E = 4 pi rho holds to roundoff (charge conservation of the Esirkepov deposit);
       * CG iteration counts are sane (< 30; 100 would be the reference's stop condition, field.f90:427-430)."""
     import torch
     import wumingpic2d_b200 as wm
@@ -93,7 +94,11 @@ def test_full_size_slab_invariants():
     assert np.array_equal(np2a[0], np2a[1]) and int(np2a.sum()) == 2 * nx * rows * ppc
     e0 = c.energy()
     assert abs(e0[0] - e0[1]) <= 1e-3 * e0[0] and e0[3] == 0.0
+    r0, s0 = c.gauss_residual()
+    assert r0 <= 1e-12 * s0            # neutral at t = 0: E = 0 and the pairs cancel
     c.step(6)
+    r1, s1 = c.gauss_residual()
+    assert r1 <= 1e-12 * s1, "discrete Gauss law (div E = 4 pi rho) after 6 steps at full size: %g vs scale %g" % (r1, s1)
     assert c.particle_counts() == n0
     assert c.rebuilds() == 0
     assert max(c.cg_iters()) < 30

@@ -205,6 +205,9 @@ def test_gauss_law_and_energy_history():
         res, scale = g.gauss_residual()
         assert res <= 1e-12 * scale
         g.close()
+        # the device-side diagnostic evaluates the same definition
+        rd, sd = c.gauss_residual()
+        assert abs(sd - scale) <= 1e-12 * scale and rd <= 1e-12 * sd
     c.close()
 
 

@@ -51,7 +51,7 @@ EXPORTS = [
     "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_boundary__injection",
     "wm_set_u_inject", "wm_set_xrange", "wm_append_particles", "wm_sort__bucket",
     "wm_step", "wm_host_step", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
-    "wm_energy", "wm_moments", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_ic_weibel", "wm_timing", "wm_synchronize", "wm_layout_rebuilds",
+    "wm_energy", "wm_gauss_residual", "wm_moments", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_ic_weibel", "wm_timing", "wm_synchronize", "wm_layout_rebuilds",
 ]
 
 
@@ -111,6 +111,7 @@ def load_library():
     lib.wm_host_sort__bucket.argtypes = [P, D, D, I32, I32]
     lib.wm_cg_iters.argtypes = [P, I32]
     lib.wm_energy.argtypes = [P, D]
+    lib.wm_gauss_residual.argtypes = [P, C.POINTER(C.c_double)]
     lib.wm_moments.argtypes = [P, D]
     lib.wm_mom_calc__accl.argtypes = [P]
     lib.wm_mom_calc__nvt.argtypes = [P, D]
@@ -275,6 +276,11 @@ class Context:
         out = (C.c_double * (self.nsp + 2))()
         self._ck(self.lib.wm_energy(self.h, out))
         return np.array(list(out))
+
+    def gauss_residual(self):
+        out = (C.c_double * 2)()
+        self._ck(self.lib.wm_gauss_residual(self.h, out))
+        return out[0], out[1]
 
     def moments(self):
         mom = np.zeros(self.shape_mom())

@@ -45,6 +45,9 @@ void launch_fused_inplace(const DevParams &P, const Pass1Args &a, cudaStream_t s
 void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaStream_t st);
 void launch_kinetic(const DevParams &P, const PartSoA &src, const int *cstart, int isp, double *partial, int nblocks,
                     cudaStream_t st);
+// diagnostic: discrete Gauss law residual of the sorted store against uf (periodic, one rank)
+void launch_gauss(const DevParams &P, const PartSoA &src, const int *cstart, const double *uf, double *rho,
+                  unsigned long long *out, cudaStream_t st);
 void launch_moments(const DevParams &P, const PartSoA &src, PView<double> keyx, const int *cstart, double *mom,
                     cudaStream_t st);
 

@@ -778,6 +778,74 @@ __global__ void k_moments(const DevParams P, const PartSoA src, const PView<doub
 }
 
 
+// Charge density with the second-order shape function, periodic in x and (one rank) in y, for the discrete Gauss law
+// div E = 4 pi rho (field.f90:159; the weights are those of particle.f90:97-105):
+//   rho[0][j][i] += q S2(x - i - 1/2) S2(y - j - 1/2),  rho[1] the same with |q| (scale of the residual)
+__global__ void k_charge_density(const DevParams P, const PartSoA src, const int *__restrict__ cstart, double *rho) {
+  const size_t plane = (size_t)P.nx * P.nyl;
+  for (int isp = 0; isp < P.nsp; isp++) {
+    const int n = cstart[(size_t)isp * (P.ncell + 1) + P.ncell];
+    const size_t so = (size_t)isp * P.cap;
+    const double q = P.q[isp], qa = fabs(P.q[isp]);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+      const double x = src.x[so + p];
+      if (!slot_live(x)) continue;
+      const double y = src.y[so + p];
+      const int ic = __double2int_rz(x), jc = __double2int_rz(y);
+      double sx[3], sy[3];
+      double dh = x - 0.5 - ic;
+      sx[0] = 0.5 * (0.5 - dh) * (0.5 - dh); sx[1] = 0.75 - dh * dh; sx[2] = 0.5 * (0.5 + dh) * (0.5 + dh);
+      dh = y - 0.5 - jc;
+      sy[0] = 0.5 * (0.5 - dh) * (0.5 - dh); sy[1] = 0.75 - dh * dh; sy[2] = 0.5 * (0.5 + dh) * (0.5 + dh);
+#pragma unroll
+      for (int b = -1; b <= 1; b++) {
+        int lj = jc + b - P.nys;
+        lj = (lj < 0) ? lj + P.nyl : (lj >= P.nyl ? lj - P.nyl : lj);
+#pragma unroll
+        for (int a = -1; a <= 1; a++) {
+          int li = ic + a - P.nxgs;
+          li = (li < 0) ? li + P.nx : (li >= P.nx ? li - P.nx : li);
+          const double w = sx[a + 1] * sy[b + 1];
+          atomicAdd(&rho[(size_t)lj * P.nx + li], q * w);
+          atomicAdd(&rho[plane + (size_t)lj * P.nx + li], qa * w);
+        }
+      }
+    }
+  }
+}
+
+// max |div E - 4 pi rho| and max 4 pi rho_abs over the cells; out[0], out[1] hold non-negative doubles whose bit
+// patterns order like the values, so atomicMax on the 64-bit integers is exact
+__global__ void k_gauss_residual(const DevParams P, const double *__restrict__ uf, const double *__restrict__ rho,
+                                 unsigned long long *out) {
+  const double PI4 = 4.0 * 3.14159265358979323846;
+  const size_t plane = (size_t)P.nx * P.nyl;
+  double res = 0.0, sc = 0.0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < P.nx * P.nyl; t += gridDim.x * blockDim.x) {
+    const int lj = t / P.nx, li = t - lj * P.nx;
+    const double *c = uf + ((size_t)(lj + 2) * P.pitch + (li + 2)) * 6;
+    const double *xp = c + 6, *yp = c + (size_t)P.pitch * 6;
+    const double dive = (xp[3] - c[3] + yp[4] - c[4]) / P.delx;
+    res = fmax(res, fabs(dive - PI4 * rho[t]));
+    sc = fmax(sc, PI4 * rho[plane + t]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    res = fmax(res, __shfl_xor_sync(0xffffffffu, res, o));
+    sc = fmax(sc, __shfl_xor_sync(0xffffffffu, sc, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&out[0], (unsigned long long)__double_as_longlong(res));
+    atomicMax(&out[1], (unsigned long long)__double_as_longlong(sc));
+  }
+}
+void launch_gauss(const DevParams &P, const PartSoA &src, const int *cstart, const double *uf, double *rho,
+                  unsigned long long *out, cudaStream_t st) {
+  cudaMemsetAsync(rho, 0, (size_t)2 * P.nx * P.nyl * sizeof(double), st);
+  cudaMemsetAsync(out, 0, 2 * sizeof(unsigned long long), st);
+  k_charge_density<<<148 * 8, 256, 0, st>>>(P, src, cstart, rho);
+  k_gauss_residual<<<148 * 4, 256, 0, st>>>(P, uf, rho, out);
+}
+
 // ---------------------------------------------------------------- layout changes (order inside a cell is kept)
 __device__ __forceinline__ int cell_of(const DevParams &P, double x, double y) {
   return (__double2int_rz(y) - P.nys) * P.nx + (__double2int_rz(x) - P.nxgs);

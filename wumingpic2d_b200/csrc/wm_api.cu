@@ -1327,6 +1327,35 @@ int wm_moments(wm_ctx *c, double *mom) {
   return 0;
 }
 
+// Discrete Gauss law of the current state: out[0] = max over the cells of |div E - 4 pi rho| with
+// rho = sum_p q S2 S2 (second-order shape, the deposit's weights), out[1] = max 4 pi sum_p |q| S2 S2 (its scale).
+// Charge conservation of the Esirkepov deposit keeps out[0] at roundoff of out[1] for all times.  Periodic boundaries,
+// one rank (the ghost folds of rho are not implemented for the ring).
+int wm_gauss_residual(wm_ctx *c, double out[2]) {
+  if (!out) return fail("wm_gauss_residual: null argument");
+  WM(need_state(c, ST_SORTED, "wm_gauss_residual"));
+  if (c->P.bc != WM_BC_PERIODIC || c->P.nsize != 1) return fail("wm_gauss_residual: periodic boundaries on one rank only");
+  WM(set_device(c));
+  const DevParams &P = c->P;
+  WM(scan_tight(c));  // makes sure the per-species slot totals in cstart are current
+  double *rho = nullptr;
+  unsigned long long *d_out = nullptr;
+  CU(cudaMalloc(&rho, (size_t)2 * P.nx * P.nyl * sizeof(double)));
+  CU(cudaMalloc(&d_out, 2 * sizeof(unsigned long long)));
+  launch_gauss(P, c->soa[c->cur], c->cstart[c->cur], c->f.uf, rho, d_out, c->st);
+  c->launches += 2;
+  unsigned long long h[2];
+  CU(cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  CU(cudaFree(rho));
+  CU(cudaFree(d_out));
+  for (int k = 0; k < 2; k++) {
+    long long v = (long long)h[k];
+    std::memcpy(&out[k], &v, sizeof(double));
+  }
+  return 0;
+}
+
 int wm_ic_weibel(wm_ctx *c, uint64_t seed, int32_t n0, double vti, double vte, double t_ani, double b0) {
   if (!c) return fail("wm_ic_weibel: null context");
   c->accl_valid = false;
