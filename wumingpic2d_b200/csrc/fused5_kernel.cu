@@ -80,11 +80,9 @@ __device__ __forceinline__ double rsqrt_fast(double a) {
 __device__ __forceinline__ double rcp_fast(double a) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));    // MUFU.RCP64H
-  double e = fma(-a, y, 1.0);
-  e = fma(e, e, e);
-  y = fma(y, e, y);
-  e = fma(-a, y, 1.0);
-  return fma(y, e, y);
+  const double e = fma(-a, y, 1.0);  // 1 - a y ~ 2^-22
+  const double p = fma(e, e, e);     // third order: y (1 + e + e^2), error e^3
+  return fma(y, p, y);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -465,14 +463,13 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
               sa[6] = fma(tx1, c1, sa[6]); sa[7] = fma(tx2, c1, sa[7]);   sa[8] = fma(tx3, c1, sa[8]);
               sa[9] = fma(tx1, c2, sa[9]); sa[10] = fma(tx2, c2, sa[10]); sa[11] = fma(tx3, c2, sa[11]);
             }
-            {  // Jz = q vz (S0x S0y + DSx S0y/2 + S0x DSy/2 + DSx DSy/3) = tx*uy + hx*vy
-              const double third = 1.0 / 3.0;
-              const double hx1 = fma(third, dsx1, 0.5 * sxm), hx2 = fma(third, dsx2, 0.5 * sx0), hx3 = fma(third, dsx3, 0.5 * sxp);
-              const double uy1 = qvz * sym, uy2 = qvz * sy0, uy3 = qvz * syp;
-              const double vy1 = qvz * dsy1, vy2 = qvz * dsy2, vy3 = qvz * dsy3;
-              sa[12] = fma(hx1, vy1, fma(tx1, uy1, sa[12])); sa[13] = fma(hx2, vy1, fma(tx2, uy1, sa[13])); sa[14] = fma(hx3, vy1, fma(tx3, uy1, sa[14]));
-              sa[15] = fma(hx1, vy2, fma(tx1, uy2, sa[15])); sa[16] = fma(hx2, vy2, fma(tx2, uy2, sa[16])); sa[17] = fma(hx3, vy2, fma(tx3, uy2, sa[17]));
-              sa[18] = fma(hx1, vy3, fma(tx1, uy3, sa[18])); sa[19] = fma(hx2, vy3, fma(tx2, uy3, sa[19])); sa[20] = fma(hx3, vy3, fma(tx3, uy3, sa[20]));
+            {  // Jz = q vz (S0x S0y + DSx S0y/2 + S0x DSy/2 + DSx DSy/3) = q vz (Tx Ty + DSx DSy/12),  T = S0 + DS/2
+              const double q12 = qvz * (1.0 / 12.0);
+              const double uy1 = qvz * ty1, uy2 = qvz * ty2, uy3 = qvz * ty3;
+              const double vy1 = q12 * dsy1, vy2 = q12 * dsy2, vy3 = q12 * dsy3;
+              sa[12] = fma(dsx1, vy1, fma(tx1, uy1, sa[12])); sa[13] = fma(dsx2, vy1, fma(tx2, uy1, sa[13])); sa[14] = fma(dsx3, vy1, fma(tx3, uy1, sa[14]));
+              sa[15] = fma(dsx1, vy2, fma(tx1, uy2, sa[15])); sa[16] = fma(dsx2, vy2, fma(tx2, uy2, sa[16])); sa[17] = fma(dsx3, vy2, fma(tx3, uy2, sa[17]));
+              sa[18] = fma(dsx1, vy3, fma(tx1, uy3, sa[18])); sa[19] = fma(dsx2, vy3, fma(tx2, uy3, sa[19])); sa[20] = fma(dsx3, vy3, fma(tx3, uy3, sa[20]));
             }
           }
         }
