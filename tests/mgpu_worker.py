@@ -63,6 +63,40 @@ def main():
     dist.all_reduce(e)
     assert np.allclose(e.cpu().numpy(), w.energy(), rtol=1e-10, atol=0)
     ctx.close()
+    w.close()
+    # ---- the wall boundary modules on the ring: reconnection (reflecting / conducting walls) and shock (injection wall,
+    #      bc__injection before the deposit), both periodic in y over the ranks
+    from helpers import make_shock_world, make_wall_world
+    for kind in ("reconnection", "shock"):
+        if kind == "shock" and os.environ.get("WM_INPLACE") == "0":
+            continue   # WM_BC_SHOCK runs on k_fused_sm (in-place sort) and on the exact path only
+        if kind == "reconnection":
+            prm, w = make_wall_world(40, 8 * world + 3, 8, nranks=world)
+        else:
+            prm, w = make_shock_world(40, 8 * world + 3, 8, u0=-0.3, nranks=world)
+        nys, nye = w.bounds(rank)
+        ctx = wm.Context.from_params(prm, nys=nys, nye=nye, nrank=rank, nsize=world, device=local)
+        ids = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0])
+        if kind == "shock":
+            ctx.set_u_inject(-0.3)
+        ctx.upload_particles_sorted(w.array(rank, O.UP).copy(), w.array(rank, O.NP2).copy(), w.array(rank, O.CUMCNT).copy())
+        ctx.upload_field(w.array(rank, O.UF).copy())
+        for it in range(nsteps):
+            w.step(1)
+            ctx.step(1)
+            assert ctx.cg_iters() == w.cg_iters(), (kind, ctx.cg_iters(), w.cg_iters())
+            up, np2, cum = ctx.download_particles()
+            assert np.array_equal(cum, w.array(rank, O.CUMCNT)), "%s: per-cell counts differ on rank %d step %d" % (kind, rank, it)
+            a, b = flatten_by_id(up, np2), flatten_by_id(w.array(rank, O.UP), w.array(rank, O.NP2))
+            assert np.array_equal(a[0], b[0])
+            ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+            tol = 1e-12 if it == 0 else 1e-10
+            assert ex <= tol and eu <= tol, (kind, it, ex, eu)
+            assert rel_to_max(ctx.download_field(), w.array(rank, O.UF)).max() <= tol, kind
+        ctx.close()
+        w.close()
     dist.barrier()
     dist.destroy_process_group()
     print("rank %d/%d ok" % (rank, world))
