@@ -12,12 +12,18 @@
 //     the closed form ds(-1,0,+1) = (A - h, -2A, A + h), A = (d'-d)(d'+d)/2, h = (d'-d)/2, and no selects;
 //   * a particle that changes cell ("mover") pushes a 48-byte record (old offsets, new offsets, q*vz, q*dx/dt)
 //     on a shared-memory queue of its cell's 8 lanes;
-//   * when the cell is finished the 8 lanes drain the queue with the full shifted-stencil deposit into the 65-sum
-//     block (the 21 stayer sums are the start values of their entries), reduce-scatter it with shuffles and add
-//     it once to the shared-memory current tile, as before.
+//   * when the cell is finished the 8 lanes drain the queue with the full shifted-stencil deposit, one pass per
+//     current component (Jz, Jx, Jy: at most 25 sums live, no spills), the 21 stayer sums being the start values
+//     of their entries; each pass ends with a reduce-scatter over the 8 lanes (shuffles) and one add per entry to
+//     the shared-memory current tile.
 //  The loop body is ~130 instructions shorter per particle and needs 88 fewer registers: 3 CTAs (12 warps) per
 //  SM instead of 2.  A queue that could fill up mid-cell (more than QCAP - 8 movers in a cell) is drained early and
 //  the particle loop re-entered, so any density is handled correctly.
+//  Particle store: blocks of 8 slots x three 16-byte words (wm_internal.h): a record is loaded with three LDG.128 at
+//  the top of its iteration (L1 prefetch hints two iterations ahead), stayers are compacted in place with three
+//  STG.128, cell changers are staged as 48-byte records + 4-byte tags for k_place.
+//  template <WALL>: 0 periodic x, 1 reflecting walls after the deposit (proj/reconnection), 2 bc__injection before
+//  the deposit (proj/shock).
 #include <cstdint>
 #include <cstdlib>
 
