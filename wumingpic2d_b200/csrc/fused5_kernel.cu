@@ -631,44 +631,41 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         }
         rs_add<32>(v, l8, valid, sj0, 40, 25);
       }
-      {  // Jx block = Cx (x) Ty     acc[b*4 + q],  C = running sum of -q*dx/dt*DSx
-        double v[24];
+      {  // Jx block = Cx (x) Ty  acc[b*4 + q] and Jy block = Tx (x) Cy  acc[20 + b*5 + q] in one pass over the queue
+         // (C = running sum of -q*dx/dt*DS): 40 sums live, the weights of a mover are computed once for both
+        double v[24], u[24];
 #pragma unroll
-        for (int e = 0; e < 24; e++) v[e] = (e < 20 && stay_slot(e < 20 ? e : 0) >= 0) ? sa[stay_slot(e < 20 ? e : 0) >= 0 ? stay_slot(e < 20 ? e : 0) : 0] : 0.0;
+        for (int e = 0; e < 24; e++) {
+          v[e] = (e < 20 && stay_slot(e < 20 ? e : 0) >= 0) ? sa[stay_slot(e < 20 ? e : 0) >= 0 ? stay_slot(e < 20 ? e : 0) : 0] : 0.0;
+          u[e] = (e < 20 && stay_slot(20 + (e < 20 ? e : 0)) >= 0) ? sa[stay_slot(20 + (e < 20 ? e : 0)) >= 0 ? stay_slot(20 + (e < 20 ? e : 0)) : 0] : 0.0;
+        }
         for (int k = l8; k - l8 < nqm; k += 8) {
           if (k < qn) {
             MoverW w;
             mover_weights(myq + k * 3, w);
-            const double ty0 = 0.5 * w.dsy0, ty1 = fma(0.5, w.dsy1, w.sym), ty2 = fma(0.5, w.dsy2, w.sy0), ty3 = fma(0.5, w.dsy3, w.syp),
-                         ty4 = 0.5 * w.dsy4;
-            const double c0 = -w.qf * w.dsx0, c1 = fma(-w.qf, w.dsx1, c0), c2 = fma(-w.qf, w.dsx2, c1), c3 = w.qf * w.dsx4;
-            v[0] = fma(c0, ty0, v[0]);   v[1] = fma(c1, ty0, v[1]);   v[2] = fma(c2, ty0, v[2]);   v[3] = fma(c3, ty0, v[3]);
-            v[4] = fma(c0, ty1, v[4]);   v[5] = fma(c1, ty1, v[5]);   v[6] = fma(c2, ty1, v[6]);   v[7] = fma(c3, ty1, v[7]);
-            v[8] = fma(c0, ty2, v[8]);   v[9] = fma(c1, ty2, v[9]);   v[10] = fma(c2, ty2, v[10]); v[11] = fma(c3, ty2, v[11]);
-            v[12] = fma(c0, ty3, v[12]); v[13] = fma(c1, ty3, v[13]); v[14] = fma(c2, ty3, v[14]); v[15] = fma(c3, ty3, v[15]);
-            v[16] = fma(c0, ty4, v[16]); v[17] = fma(c1, ty4, v[17]); v[18] = fma(c2, ty4, v[18]); v[19] = fma(c3, ty4, v[19]);
+            {
+              const double ty0 = 0.5 * w.dsy0, ty1 = fma(0.5, w.dsy1, w.sym), ty2 = fma(0.5, w.dsy2, w.sy0), ty3 = fma(0.5, w.dsy3, w.syp),
+                           ty4 = 0.5 * w.dsy4;
+              const double c0 = -w.qf * w.dsx0, c1 = fma(-w.qf, w.dsx1, c0), c2 = fma(-w.qf, w.dsx2, c1), c3 = w.qf * w.dsx4;
+              v[0] = fma(c0, ty0, v[0]);   v[1] = fma(c1, ty0, v[1]);   v[2] = fma(c2, ty0, v[2]);   v[3] = fma(c3, ty0, v[3]);
+              v[4] = fma(c0, ty1, v[4]);   v[5] = fma(c1, ty1, v[5]);   v[6] = fma(c2, ty1, v[6]);   v[7] = fma(c3, ty1, v[7]);
+              v[8] = fma(c0, ty2, v[8]);   v[9] = fma(c1, ty2, v[9]);   v[10] = fma(c2, ty2, v[10]); v[11] = fma(c3, ty2, v[11]);
+              v[12] = fma(c0, ty3, v[12]); v[13] = fma(c1, ty3, v[13]); v[14] = fma(c2, ty3, v[14]); v[15] = fma(c3, ty3, v[15]);
+              v[16] = fma(c0, ty4, v[16]); v[17] = fma(c1, ty4, v[17]); v[18] = fma(c2, ty4, v[18]); v[19] = fma(c3, ty4, v[19]);
+            }
+            {
+              const double tx0 = 0.5 * w.dsx0, tx1 = fma(0.5, w.dsx1, w.sxm), tx2 = fma(0.5, w.dsx2, w.sx0), tx3 = fma(0.5, w.dsx3, w.sxp),
+                           tx4 = 0.5 * w.dsx4;
+              const double c0 = -w.qf * w.dsy0, c1 = fma(-w.qf, w.dsy1, c0), c2 = fma(-w.qf, w.dsy2, c1), c3 = w.qf * w.dsy4;
+              u[0] = fma(tx0, c0, u[0]);   u[1] = fma(tx1, c0, u[1]);   u[2] = fma(tx2, c0, u[2]);   u[3] = fma(tx3, c0, u[3]);   u[4] = fma(tx4, c0, u[4]);
+              u[5] = fma(tx0, c1, u[5]);   u[6] = fma(tx1, c1, u[6]);   u[7] = fma(tx2, c1, u[7]);   u[8] = fma(tx3, c1, u[8]);   u[9] = fma(tx4, c1, u[9]);
+              u[10] = fma(tx0, c2, u[10]); u[11] = fma(tx1, c2, u[11]); u[12] = fma(tx2, c2, u[12]); u[13] = fma(tx3, c2, u[13]); u[14] = fma(tx4, c2, u[14]);
+              u[15] = fma(tx0, c3, u[15]); u[16] = fma(tx1, c3, u[16]); u[17] = fma(tx2, c3, u[17]); u[18] = fma(tx3, c3, u[18]); u[19] = fma(tx4, c3, u[19]);
+            }
           }
         }
         rs_add<24>(v, l8, valid, sj0, 0, 20);
-      }
-      {  // Jy block = Tx (x) Cy     acc[20 + b*5 + q]
-        double v[24];
-#pragma unroll
-        for (int e = 0; e < 24; e++) v[e] = (e < 20 && stay_slot(20 + (e < 20 ? e : 0)) >= 0) ? sa[stay_slot(20 + (e < 20 ? e : 0)) >= 0 ? stay_slot(20 + (e < 20 ? e : 0)) : 0] : 0.0;
-        for (int k = l8; k - l8 < nqm; k += 8) {
-          if (k < qn) {
-            MoverW w;
-            mover_weights(myq + k * 3, w);
-            const double tx0 = 0.5 * w.dsx0, tx1 = fma(0.5, w.dsx1, w.sxm), tx2 = fma(0.5, w.dsx2, w.sx0), tx3 = fma(0.5, w.dsx3, w.sxp),
-                         tx4 = 0.5 * w.dsx4;
-            const double c0 = -w.qf * w.dsy0, c1 = fma(-w.qf, w.dsy1, c0), c2 = fma(-w.qf, w.dsy2, c1), c3 = w.qf * w.dsy4;
-            v[0] = fma(tx0, c0, v[0]);   v[1] = fma(tx1, c0, v[1]);   v[2] = fma(tx2, c0, v[2]);   v[3] = fma(tx3, c0, v[3]);   v[4] = fma(tx4, c0, v[4]);
-            v[5] = fma(tx0, c1, v[5]);   v[6] = fma(tx1, c1, v[6]);   v[7] = fma(tx2, c1, v[7]);   v[8] = fma(tx3, c1, v[8]);   v[9] = fma(tx4, c1, v[9]);
-            v[10] = fma(tx0, c2, v[10]); v[11] = fma(tx1, c2, v[11]); v[12] = fma(tx2, c2, v[12]); v[13] = fma(tx3, c2, v[13]); v[14] = fma(tx4, c2, v[14]);
-            v[15] = fma(tx0, c3, v[15]); v[16] = fma(tx1, c3, v[16]); v[17] = fma(tx2, c3, v[17]); v[18] = fma(tx3, c3, v[18]); v[19] = fma(tx4, c3, v[19]);
-          }
-        }
-        rs_add<24>(v, l8, valid, sj0, 20, 20);
+        rs_add<24>(u, l8, valid, sj0, 20, 20);
       }
       __syncwarp();
     }
