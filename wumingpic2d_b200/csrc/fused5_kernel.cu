@@ -12,8 +12,8 @@
 //     the closed form ds(-1,0,+1) = (A - h, -2A, A + h), A = (d'-d)(d'+d)/2, h = (d'-d)/2, and no selects;
 //   * a particle that changes cell ("mover") pushes a 48-byte record (old offsets, new offsets, q*vz, q*dx/dt)
 //     on a shared-memory queue of its cell's 8 lanes;
-//   * when the cell is finished the 8 lanes drain the queue with the full shifted-stencil deposit, one pass per
-//     current component (Jz, Jx, Jy: at most 25 sums live, no spills), the 21 stayer sums being the start values
+//   * when the cell is finished the 8 lanes drain the queue with the full shifted-stencil deposit in two passes
+//     (Jz: 25 sums; Jx and Jy together: 40 sums), the 21 stayer sums being the start values
 //     of their entries; each pass ends with a reduce-scatter over the 8 lanes (shuffles) and one add per entry to
 //     the shared-memory current tile.
 //  The loop body is ~130 instructions shorter per particle and needs 88 fewer registers: 3 CTAs (12 warps) per
