@@ -595,8 +595,8 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
       }
     }
 
-    // ---- drain the mover queue of the cell: one pass per current component (Jz, Jx, Jy), so that at most 25
-    //      sums are live at a time; the stayer sums are the start values of their entries.  Each pass ends with
+    // ---- drain the mover queue of the cell in two passes (Jz; Jx and Jy together), so that at most 40 sums are
+    //      live at a time; the stayer sums are the start values of their entries.  Each pass ends with
     //      the reduce-scatter over the 8 lanes of the cell and one add per entry to the shared-memory tile
     //      (field.f90:304-310).
     {
