@@ -57,7 +57,7 @@ struct wm_ctx {
   DevParams P;
   int dev = 0;
   cudaStream_t st = nullptr, st2 = nullptr;
-  // particles: two SoA stores; `cur` holds the sorted state (the reference's `up`),
+  // particles: two stores of blocked 48-byte records (wm_internal.h, PView); `cur` holds the sorted state (the reference's `up`),
   // the other one is `gp` in stage mode and the scatter target in the fused step
   double *pbuf[2] = {nullptr, nullptr};
   PartSoA soa[2];
