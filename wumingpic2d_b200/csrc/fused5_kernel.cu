@@ -198,13 +198,14 @@ __device__ __forceinline__ void rs_add(double (&v)[NP], int l8, bool valid, doub
 
 // MINB resident CTAs per SM: 3 -> at most 168 registers.  DRAIN = false drops the movers' current (wrong physics:
 // only for timing the particle loop in isolation).
-template <int MINB, bool DRAIN, int WALL, int PFD>
+template <int MINB, bool DRAIN, int WALL, int PFD, bool TAIL>
 __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const Pass1Args a) {
   __shared__ __align__(128) double s_f[WINY * WINX * 6];
   __shared__ __align__(16) double s_j[3 * JY * JX];
   __shared__ __align__(16) double2 s_q[FW * 4 * QCAP * 3];  // [warp][cell of the quad][slot] x (hx hy | dxn dyn | qvz qf)
   __shared__ int s_arr[WM_NSP_MAX * WIN];
   __shared__ int s_nmv[WM_NSP_MAX * NQ];
+  __shared__ int s_nst[TAIL ? WM_NSP_MAX * TX * TY : 1];  // stayers per (species, cell of the tile)
   __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x;
@@ -584,7 +585,11 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         }
       }
       if (k >= nmax) {
-        if (valid && l8 == 0) a.cnt_tail[(size_t)isp * P.ncell + cell] = nst;  // arrivals are added by k_place
+        if (TAIL) {
+          if (l8 == 0) s_nst[isp * (TX * TY) + cy * TX + cx] = nst;  // the new count is written by the tail of the CTA
+        } else {
+          if (valid && l8 == 0) a.cnt_tail[(size_t)isp * P.ncell + cell] = nst;  // arrivals are added by k_place
+        }
         if (lane == 0) s_nmv[isp * NQ + q] = nmv;
         isp++;
         k0 = 0;
@@ -684,6 +689,140 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
       if (v != 0.0) atomicAdd(&a.uj[((size_t)(lj0 + jy) * P.pitch + (li0 + jx)) * 3 + comp], v);
     }
   }
+  // ---- sort, in-tile part (TAIL): a cell changer whose new cell belongs to this tile (88 % of them) is appended to the
+  //      tail of its new segment right here (sort.f90:71-75 reduced to the cell changers).  Every cell of the tile is
+  //      finished (the barrier after the quad loop), so the slots behind the stayers of a segment are free, and this CTA
+  //      alone knows the stayer counts: slot = segment start + stayers + rank, the rank being the one the particle loop
+  //      drew from the shared-memory arrival counter.  One pass in staging order: a thread has TB records in flight (tag +
+  //      three 16-byte words each, read back from L2 with ld.global.cg: this CTA wrote them a moment ago); the 16-byte
+  //      pieces of a destination line written by different threads merge in L2.  k_place is left with the arrivals of
+  //      the window's rim (other tiles' cells).  Shared memory: the field tile is dead by now and holds the tables.
+  if (TAIL) {
+    constexpr int TB = 7;  // records in flight per thread
+    static_assert((2 * WM_NSP_MAX * WIN + WM_NSP_MAX * NQ + 2) * 4 + WM_NSP_MAX * NQ * 8 <= (int)sizeof(double) * WINY * WINX * 6,
+                  "tail tables must fit the field tile");
+    static_assert(TX * TY == FT, "one thread per cell of the tile");
+    int *const t_base = reinterpret_cast<int *>(s_f);     // [nwin] first slot of the arrivals, -1 = not my cell
+    int *const t_end = t_base + WM_NSP_MAX * WIN;         // [nwin] end of the segment
+    int *const t_off = t_end + WM_NSP_MAX * WIN;          // [nreg + 1] staged records before region r
+    long long *const t_rec0 = reinterpret_cast<long long *>(t_base + ((2 * WM_NSP_MAX * WIN + WM_NSP_MAX * NQ + 2) & ~1));
+    const int nwin = P.nsp * WIN, nreg = P.nsp * NQ;
+    for (int e = tid; e < nwin; e += FT) t_base[e] = -1;  // rim of the window: not mine
+    for (int r = tid; r < nreg; r += FT) {
+      const int isp = r / NQ, q = r - isp * NQ;
+      const int cy = q / QX, cx0 = (q - cy * QX) * 4;
+      long long rec0 = 0;
+      int cap = 0;
+      if (cy < th && cx0 < tw) {
+        const int c0 = (lj0 + cy) * P.nx + li0 + cx0;
+        const int *cs = a.cstart + (size_t)isp * (P.ncell + 1);
+        stage_region(so_slots(P, isp) + cs[c0], so_slots(P, isp) + cs[min(c0 + 4, (lj0 + cy + 1) * P.nx)], &rec0, &cap);
+      }
+      t_rec0[r] = rec0;
+      t_off[r + 1] = min(s_nmv[isp * NQ + q], cap);
+    }
+    __syncthreads();
+    {  // thread = cell of the tile: its arrivals go to [start + stayers, start + capacity)
+      const int cy = tid / TX, cx = tid - cy * TX;
+      if (cx < tw && cy < th) {
+        const int cell = (lj0 + cy) * P.nx + (li0 + cx);
+        int cb[WM_NSP_MAX], ce[WM_NSP_MAX];
+#pragma unroll
+        for (int isp = 0; isp < WM_NSP_MAX; isp++)
+          if (isp < P.nsp) {
+            const int *cs = a.cstart + (size_t)isp * (P.ncell + 1);
+            cb[isp] = cs[cell];
+            ce[isp] = cs[cell + 1];
+          }
+#pragma unroll
+        for (int isp = 0; isp < WM_NSP_MAX; isp++)
+          if (isp < P.nsp) {
+            const int e = isp * WIN + (cy + 1) * WINX + (cx + 1);
+            const int n = s_arr[e], ns = s_nst[isp * (TX * TY) + tid];
+            t_base[e] = cb[isp] + ns;
+            t_end[e] = ce[isp];
+            s_arr[e] = 0;  // placed here: nothing left for k_place
+            a.cnt_tail[(size_t)isp * P.ncell + cell] = ns + n;  // k_place adds the arrivals from other tiles
+          }
+      }
+    }
+    if (wid == 0) {  // inclusive scan of the staged-record counts
+      const int per = (nreg + 31) >> 5;
+      int sum = 0;
+      for (int i = 0; i < per; i++) {
+        const int idx = lane * per + i;
+        if (idx < nreg) sum += t_off[idx + 1];
+      }
+      int inc = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+      }
+      int run = inc - sum;
+      for (int i = 0; i < per; i++) {
+        const int idx = lane * per + i;
+        if (idx < nreg) {
+          run += t_off[idx + 1];
+          t_off[idx + 1] = run;
+        }
+      }
+      if (lane == 0) t_off[0] = 0;
+    }
+    __syncthreads();
+    const int nstaged = t_off[nreg];
+    const double2 *const stage = reinterpret_cast<const double2 *>(a.dst.x.p);
+    for (int k0 = tid; k0 < nstaged; k0 += TB * FT) {
+      uint32_t tg[TB];
+      int sp[TB];
+      double2 r0[TB], r1[TB], r2[TB];
+#pragma unroll
+      for (int u = 0; u < TB; u++) {
+        const int k = k0 + u * FT;
+        tg[u] = TAG_DEAD;
+        sp[u] = 0;
+        if (k < nstaged) {
+          int lo = 0, hi = nreg;  // largest r with t_off[r] <= k
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (t_off[mid] <= k) lo = mid; else hi = mid;
+          }
+          const long long ri = t_rec0[lo] + (k - t_off[lo]);
+          sp[u] = lo / NQ;
+          tg[u] = __ldcg(a.tag + ri);
+          const double2 *r = stage + ri * 3;
+          r0[u] = __ldcg(r);
+          r1[u] = __ldcg(r + 1);
+          r2[u] = __ldcg(r + 2);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < TB; u++) {
+        const uint32_t t = tg[u];
+        if (t == TAG_DEAD) continue;  // left the slab: already in the send buffer
+        const int e = sp[u] * WIN + (int)((t >> TAG_WSHIFT) & 0xff);
+        const int bs = t_base[e];
+        if (bs < 0) continue;  // rim of the window: k_place
+        const int d = bs + (int)(t & TAG_RANK_MASK);
+        if (d < t_end[e]) {
+          double2 *o = a.src.word((size_t)sp[u] * P.cap + (size_t)d);
+          o[0] = r0[u];
+          o[8] = r1[u];
+          o[16] = r2[u];
+        } else {  // segment full: park the record; the host rebuilds the layout after this step
+          const int kk = atomicAdd(a.ovfcnt, 1);
+          if (kk < a.ovfcap) {
+            double *o = a.ovf + (size_t)kk * 6;
+            o[0] = r0[u].x; o[1] = r0[u].y; o[2] = r1[u].x; o[3] = r1[u].y; o[4] = r2[u].x; o[5] = r2[u].y;
+            a.ovfsp[kk] = sp[u];
+          } else {
+            atomicOr(a.err, ERR_OVERFLOW);
+          }
+        }
+      }
+    }
+    __syncthreads();  // s_arr is handed over below
+  }
   // ---- hand the tile's arrival counts per window cell and its staged-record counts to k_place
   int *tb = a.tilebase + (size_t)tile * P.nsp * (2 * WIN);
   for (int e = tid; e < P.nsp * WIN; e += FT) {
@@ -696,17 +835,19 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
 void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaStream_t st) {
   const int grid = P.ntx * P.nty;
   if (P.bc == WM_BC_SHOCK)
-    k_fused_sm<3, true, 2, 2><<<grid, FT, 0, st>>>(P, a);
+    k_fused_sm<3, true, 2, 2, true><<<grid, FT, 0, st>>>(P, a);
   else if (P.bc == WM_BC_RECONNECTION)
-    k_fused_sm<3, true, 1, 2><<<grid, FT, 0, st>>>(P, a);
+    k_fused_sm<3, true, 1, 2, true><<<grid, FT, 0, st>>>(P, a);
   else if (variant == 9)
-    k_fused_sm<3, false, 0, 2><<<grid, FT, 0, st>>>(P, a);  // timing experiment: movers' current dropped
+    k_fused_sm<3, false, 0, 2, true><<<grid, FT, 0, st>>>(P, a);  // timing experiment: movers' current dropped
   else if (variant == 2)
-    k_fused_sm<2, true, 0, 2><<<grid, FT, 0, st>>>(P, a);   // 2 CTAs per SM, up to 255 registers
+    k_fused_sm<2, true, 0, 2, true><<<grid, FT, 0, st>>>(P, a);   // 2 CTAs per SM, up to 255 registers
+  else if (variant == 3)
+    k_fused_sm<3, true, 0, 2, false><<<grid, FT, 0, st>>>(P, a);  // every cell changer left to k_place
   else if (variant == 10)
-    k_fused_sm<3, true, 0, 3><<<grid, FT, 0, st>>>(P, a);   // hints three iterations ahead
+    k_fused_sm<3, true, 0, 3, true><<<grid, FT, 0, st>>>(P, a);   // hints three iterations ahead
   else
-    k_fused_sm<3, true, 0, 2><<<grid, FT, 0, st>>>(P, a);
+    k_fused_sm<3, true, 0, 2, true><<<grid, FT, 0, st>>>(P, a);
 }
 
 }  // namespace wm

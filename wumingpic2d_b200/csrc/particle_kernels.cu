@@ -1037,6 +1037,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const d
       const uint32_t t = tag[ri];
       if (t == TAG_DEAD) continue;  // left the slab: already in the send buffer
       const int e = (lo / PL_NQ) * WIN + (int)((t >> TAG_WSHIFT) & 0xff);
+      if (s_base[e] < 0) continue;  // placed by k_fused_sm itself (new cell inside the tile)
       const int j = s_pref[e] + (int)(t & TAG_RANK_MASK) - j0;
       if (j >= 0 && j < PL_MAX) s_inv[j] = (int)(ri - s_rec0[0]);
     }
