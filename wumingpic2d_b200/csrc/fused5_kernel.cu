@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
   __shared__ int s_arr[WM_NSP_MAX * WIN];
   __shared__ int s_nmv[WM_NSP_MAX * NQ];
   __shared__ int s_nst[TAIL ? WM_NSP_MAX * TX * TY : 1];  // stayers per (species, cell of the tile)
+  __shared__ int s_cs[TAIL ? WM_NSP_MAX * TY * (TX + 1) : 1];  // segment offsets of the tile's cells (+ one column)
   __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x;
@@ -330,6 +331,11 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         const int c0 = (lj0 + cy) * P.nx + li0 + (q - cy * QX) * 4;
         const int *cs = a.cstart + (size_t)isp * (P.ncell + 1);
         stage_region(so_slots(P, isp) + cs[c0], so_slots(P, isp) + cs[min(c0 + 4, (lj0 + cy + 1) * P.nx)], &qrec, &qcap);
+      }
+      if (TAIL) {  // segment offsets of the tile's cells for the tail of the CTA (end of the quad = start of the next one)
+        int *const scs = &s_cs[(isp * TY + cy) * (TX + 1)];
+        if (valid && l8 == 0) scs[cx] = beg;
+        if (lane == 0 && qcap > 0) scs[min((q - cy * QX) * 4 + 4, tw)] = (int)(qrec - so_slots(P, isp)) + qcap;
       }
       int p = beg + l8 + k0;
       double2 *pbase = reinterpret_cast<double2 *>(px + 6 * ((size_t)isp * P.cap));  // slot 0 of this species (cap % 8 == 0)
@@ -693,144 +699,119 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
   //      tail of its new segment right here (sort.f90:71-75 reduced to the cell changers).  Every cell of the tile is
   //      finished (the barrier after the quad loop), so the slots behind the stayers of a segment are free, and this CTA
   //      alone knows the stayer counts: slot = segment start + stayers + rank, the rank being the one the particle loop
-  //      drew from the shared-memory arrival counter.  One pass in staging order: a thread has TB records in flight (tag +
-  //      three 16-byte words each, read back from L2 with ld.global.cg: this CTA wrote them a moment ago); the 16-byte
-  //      pieces of a destination line written by different threads merge in L2.  k_place is left with the arrivals of
-  //      the window's rim (other tiles' cells).  Shared memory: the field tile is dead by now and holds the tables.
+  //      drew from the shared-memory arrival counter.  One pass in staging order, a warp per staging region (quad,
+  //      species), four regions x 64 records in flight per warp: tag + three 16-byte words each (ld.global.cg: this CTA
+  //      wrote them a moment ago); the 16-byte pieces of a destination line written by different threads merge in L2.
+  //      k_place is left with the arrivals of the window's rim (other tiles' cells).  Shared memory: the field tile is
+  //      dead by now and holds the tables.
   if (TAIL) {
-    constexpr int TB = 7;  // records in flight per thread
-    static_assert((2 * WM_NSP_MAX * WIN + WM_NSP_MAX * NQ + 2) * 4 + WM_NSP_MAX * NQ * 8 <= (int)sizeof(double) * WINY * WINX * 6,
-                  "tail tables must fit the field tile");
+    constexpr int RB = 4;  // regions in flight per warp
+    static_assert(2 * WM_NSP_MAX * WIN * 4 <= (int)sizeof(double) * WINY * WINX * 6, "tail tables must fit the field tile");
     static_assert(TX * TY == FT, "one thread per cell of the tile");
+    static_assert((WM_NSP_MAX * NQ) % (FW * RB) == 0, "regions per warp");
     int *const t_base = reinterpret_cast<int *>(s_f);     // [nwin] first slot of the arrivals, -1 = not my cell
     int *const t_end = t_base + WM_NSP_MAX * WIN;         // [nwin] end of the segment
-    int *const t_off = t_end + WM_NSP_MAX * WIN;          // [nreg + 1] staged records before region r
-    long long *const t_rec0 = reinterpret_cast<long long *>(t_base + ((2 * WM_NSP_MAX * WIN + WM_NSP_MAX * NQ + 2) & ~1));
     const int nwin = P.nsp * WIN, nreg = P.nsp * NQ;
-    for (int e = tid; e < nwin; e += FT) t_base[e] = -1;  // rim of the window: not mine
-    for (int r = tid; r < nreg; r += FT) {
-      const int isp = r / NQ, q = r - isp * NQ;
-      const int cy = q / QX, cx0 = (q - cy * QX) * 4;
-      long long rec0 = 0;
-      int cap = 0;
-      if (cy < th && cx0 < tw) {
-        const int c0 = (lj0 + cy) * P.nx + li0 + cx0;
-        const int *cs = a.cstart + (size_t)isp * (P.ncell + 1);
-        stage_region(so_slots(P, isp) + cs[c0], so_slots(P, isp) + cs[min(c0 + 4, (lj0 + cy + 1) * P.nx)], &rec0, &cap);
-      }
-      t_rec0[r] = rec0;
-      t_off[r + 1] = min(s_nmv[isp * NQ + q], cap);
+    for (int e = tid; e < nwin; e += FT) {  // rim of the window: not mine
+      const int w = e % WIN, wy = w / WINX, wx = w - wy * WINX;
+      if (!(wx >= 1 && wx <= tw && wy >= 1 && wy <= th)) t_base[e] = -1;
     }
-    __syncthreads();
     {  // thread = cell of the tile: its arrivals go to [start + stayers, start + capacity)
       const int cy = tid / TX, cx = tid - cy * TX;
       if (cx < tw && cy < th) {
         const int cell = (lj0 + cy) * P.nx + (li0 + cx);
-        int cb[WM_NSP_MAX], ce[WM_NSP_MAX];
 #pragma unroll
         for (int isp = 0; isp < WM_NSP_MAX; isp++)
           if (isp < P.nsp) {
-            const int *cs = a.cstart + (size_t)isp * (P.ncell + 1);
-            cb[isp] = cs[cell];
-            ce[isp] = cs[cell + 1];
-          }
-#pragma unroll
-        for (int isp = 0; isp < WM_NSP_MAX; isp++)
-          if (isp < P.nsp) {
+            const int *cs = &s_cs[(isp * TY + cy) * (TX + 1) + cx];
             const int e = isp * WIN + (cy + 1) * WINX + (cx + 1);
             const int n = s_arr[e], ns = s_nst[isp * (TX * TY) + tid];
-            t_base[e] = cb[isp] + ns;
-            t_end[e] = ce[isp];
-            s_arr[e] = 0;  // placed here: nothing left for k_place
-            a.cnt_tail[(size_t)isp * P.ncell + cell] = ns + n;  // k_place adds the arrivals from other tiles
+            t_base[e] = cs[0] + ns;
+            t_end[e] = cs[1];
+            a.cnt_tail[(size_t)isp * P.ncell + cell] = ns + n;  // k_place_rim adds the arrivals from other tiles
+            // retire the slots the cell does not fill any more (k_mark_dead); rim arrivals may overwrite some later
+            const int nold = a.cnt[(size_t)isp * P.ncell + cell];
+            for (int pp = ns + n; pp < nold; pp++) a.src.x[(size_t)isp * P.cap + (size_t)(cs[0] + pp)] = dead_x();
           }
       }
-    }
-    if (wid == 0) {  // inclusive scan of the staged-record counts
-      const int per = (nreg + 31) >> 5;
-      int sum = 0;
-      for (int i = 0; i < per; i++) {
-        const int idx = lane * per + i;
-        if (idx < nreg) sum += t_off[idx + 1];
-      }
-      int inc = sum;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += o;
-      }
-      int run = inc - sum;
-      for (int i = 0; i < per; i++) {
-        const int idx = lane * per + i;
-        if (idx < nreg) {
-          run += t_off[idx + 1];
-          t_off[idx + 1] = run;
-        }
-      }
-      if (lane == 0) t_off[0] = 0;
     }
     __syncthreads();
-    const int nstaged = t_off[nreg];
     const double2 *const stage = reinterpret_cast<const double2 *>(a.dst.x.p);
-    for (int k0 = tid; k0 < nstaged; k0 += TB * FT) {
-      uint32_t tg[TB];
-      int sp[TB];
-      double2 r0[TB], r1[TB], r2[TB];
+#pragma unroll 1
+    for (int rb = wid * RB; rb < nreg; rb += FW * RB) {
+      // regions rb .. rb + RB - 1 of this warp: start and number of staged records (same bounds as the staging stores)
+      int roff[RB], rcnt[RB], nmaxr = 0;
 #pragma unroll
-      for (int u = 0; u < TB; u++) {
-        const int k = k0 + u * FT;
-        tg[u] = TAG_DEAD;
-        sp[u] = 0;
-        if (k < nstaged) {
-          int lo = 0, hi = nreg;  // largest r with t_off[r] <= k
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (t_off[mid] <= k) lo = mid; else hi = mid;
-          }
-          const long long ri = t_rec0[lo] + (k - t_off[lo]);
-          sp[u] = lo / NQ;
-          tg[u] = __ldcg(a.tag + ri);
-          const double2 *r = stage + ri * 3;
-          r0[u] = __ldcg(r);
-          r1[u] = __ldcg(r + 1);
-          r2[u] = __ldcg(r + 2);
+      for (int v = 0; v < RB; v++) {
+        const int r = rb + v, isp = r / NQ, q = r - isp * NQ;
+        const int cy = q / QX, cx0 = (q - cy * QX) * 4;
+        roff[v] = 0;
+        rcnt[v] = 0;
+        if (cy < th && cx0 < tw) {
+          const int *cs = &s_cs[(isp * TY + cy) * (TX + 1)];
+          roff[v] = cs[cx0];
+          rcnt[v] = min(s_nmv[r], cs[min(cx0 + 4, tw)] - cs[cx0]);
         }
+        nmaxr = max(nmaxr, rcnt[v]);
       }
+      const int isp = rb / NQ;  // RB regions never straddle the species (NQ % RB == 0)
+      const size_t so = (size_t)isp * P.cap;
+#pragma unroll 1
+      for (int kb = 0; kb < nmaxr; kb += 64) {
+        uint32_t tg[2 * RB];
+        double2 r0[2 * RB], r1[2 * RB], r2[2 * RB];
 #pragma unroll
-      for (int u = 0; u < TB; u++) {
-        const uint32_t t = tg[u];
-        if (t == TAG_DEAD) continue;  // left the slab: already in the send buffer
-        const int e = sp[u] * WIN + (int)((t >> TAG_WSHIFT) & 0xff);
-        const int bs = t_base[e];
-        if (bs < 0) continue;  // rim of the window: k_place
-        const int d = bs + (int)(t & TAG_RANK_MASK);
-        if (d < t_end[e]) {
-          double2 *o = a.src.word((size_t)sp[u] * P.cap + (size_t)d);
-          o[0] = r0[u];
-          o[8] = r1[u];
-          o[16] = r2[u];
-        } else {  // segment full: park the record; the host rebuilds the layout after this step
-          const int kk = atomicAdd(a.ovfcnt, 1);
-          if (kk < a.ovfcap) {
-            double *o = a.ovf + (size_t)kk * 6;
-            o[0] = r0[u].x; o[1] = r0[u].y; o[2] = r1[u].x; o[3] = r1[u].y; o[4] = r2[u].x; o[5] = r2[u].y;
-            a.ovfsp[kk] = sp[u];
-          } else {
-            atomicOr(a.err, ERR_OVERFLOW);
+        for (int u = 0; u < 2 * RB; u++) {
+          const int k = kb + lane + 32 * (u & 1);
+          tg[u] = TAG_DEAD;
+          if (k < rcnt[u >> 1]) {
+            const size_t ri = so + (size_t)(roff[u >> 1] + k);
+            tg[u] = __ldcg(a.tag + ri);
+            const double2 *r = stage + ri * 3;
+            r0[u] = __ldcg(r);
+            r1[u] = __ldcg(r + 1);
+            r2[u] = __ldcg(r + 2);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2 * RB; u++) {
+          const uint32_t t = tg[u];
+          if (t == TAG_DEAD) continue;  // left the slab: already in the send buffer
+          const int e = isp * WIN + (int)((t >> TAG_WSHIFT) & 0xff);
+          const int bs = t_base[e];
+          if (bs < 0) continue;  // rim of the window: k_place
+          const int d = bs + (int)(t & TAG_RANK_MASK);
+          if (d < t_end[e]) {
+            double2 *o = a.src.word(so + (size_t)d);
+            o[0] = r0[u];
+            o[8] = r1[u];
+            o[16] = r2[u];
+          } else {  // segment full: park the record; the host rebuilds the layout after this step
+            const int kk = atomicAdd(a.ovfcnt, 1);
+            if (kk < a.ovfcap) {
+              double *o = a.ovf + (size_t)kk * 6;
+              o[0] = r0[u].x; o[1] = r0[u].y; o[2] = r1[u].x; o[3] = r1[u].y; o[4] = r2[u].x; o[5] = r2[u].y;
+              a.ovfsp[kk] = isp;
+            } else {
+              atomicOr(a.err, ERR_OVERFLOW);
+            }
           }
         }
       }
     }
-    __syncthreads();  // s_arr is handed over below
   }
   // ---- hand the tile's arrival counts per window cell and its staged-record counts to k_place
   int *tb = a.tilebase + (size_t)tile * P.nsp * (2 * WIN);
   for (int e = tid; e < P.nsp * WIN; e += FT) {
     const int isp = e / WIN, w = e - isp * WIN;
-    tb[isp * (2 * WIN) + w] = s_arr[e];
+    const int wy = w / WINX, wx = w - wy * WINX;
+    const bool mine = TAIL && wx >= 1 && wx <= tw && wy >= 1 && wy <= th;  // placed by the tail above
+    tb[isp * (2 * WIN) + w] = mine ? 0 : s_arr[e];
     if (w < NQ) tb[isp * (2 * WIN) + WIN + w] = s_nmv[isp * NQ + w];
   }
 }
+
+bool fused_sm_has_tail(int variant) { return variant != 3; }
 
 void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaStream_t st) {
   const int grid = P.ntx * P.nty;

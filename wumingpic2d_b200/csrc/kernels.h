@@ -34,9 +34,13 @@ void launch_relayout_soa(const DevParams &P, const PartSoA &src, const int *csta
 void launch_incoming_append(const DevParams &P, const double *rec, int n, int isp, const int *cstart, int *cnt_tail,
                             const PartSoA &dst, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
                             cudaStream_t st);
-// in-place sort: append the records staged by k_fused<INPLACE> to their new segments, retire vacated slots
+// in-place sort: append the records staged by k_fused<INPLACE> to their new segments, retire vacated slots;
+// rim_only: k_fused_sm<TAIL> served the tile's own cells, only the window rim is left (k_place_rim)
 void launch_place(const DevParams &P, const double *stage, const uint32_t *tag, const PartSoA &dst, const int *cstart,
-                  int *cnt_new, const int *tilebase, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err, cudaStream_t st);
+                  int *cnt_new, const int *tilebase, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
+                  bool rim_only, cudaStream_t st);
+// does launch_fused_sm(variant) place the in-tile cell changers itself?
+bool fused_sm_has_tail(int variant);
 void launch_clamp_counts(const DevParams &P, const int *cstart, int *cnt, cudaStream_t st);
 void launch_mark_dead(const DevParams &P, PView<double> x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st);
 // fused push + deposit + boundaries that moves cell changers itself (no tags, no scatter pass)

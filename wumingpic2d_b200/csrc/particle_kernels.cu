@@ -1076,6 +1076,123 @@ __global__ void __launch_bounds__(PL_THREADS) k_place(const DevParams P, const d
   }
 }
 
+// k_place for what k_fused_sm<TAIL> leaves over: the tile's own cells were served by the CTA itself, only the rim of its
+// window (cells of other tiles, 12 % of the cell changers) still has arrivals.  One pass in staging order, a warp per
+// staging region (quad, species): the tags of four regions x 64 records in flight per warp, then the records of the rim
+// arrivals among them (compacted over the warp); slot = reserved base + rank, no destination-order map (the 16-byte pieces of a line merge in L2).
+constexpr int PR_THREADS = 256;
+constexpr int PR_RB = 4;
+__global__ void __launch_bounds__(PR_THREADS) k_place_rim(const DevParams P, const double2 *__restrict__ stage,
+                                                          const uint32_t *__restrict__ tag, const PartSoA dst,
+                                                          const int *__restrict__ cstart, int *cnt_new,
+                                                          const int *__restrict__ tilebase, double *ovf, int *ovfsp, int *ovfcnt,
+                                                          int ovfcap, unsigned *err) {
+  __shared__ int s_base[WM_NSP_MAX * WIN], s_end[WM_NSP_MAX * WIN];
+  __shared__ int s_roff[WM_NSP_MAX * PL_NQ], s_rcnt[WM_NSP_MAX * PL_NQ];
+  __shared__ int2 s_list[(PR_THREADS / 32) * 2 * PR_RB * 32];
+  static_assert(PL_NQ % PR_RB == 0, "regions in flight never straddle the species");
+  const int tid = threadIdx.x, tile = blockIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int li0 = (tile % P.ntx) * TX, lj0 = (tile / P.ntx) * TY;
+  const int tw = min(TX, P.nx - li0), th = min(TY, P.nyl - lj0);
+  const int *tb = tilebase + (size_t)tile * P.nsp * (2 * WIN);
+  const int nreg = P.nsp * PL_NQ, nwin = P.nsp * WIN;
+  for (int e = tid; e < nwin; e += PR_THREADS) {
+    const int isp = e / WIN, w = e - isp * WIN;
+    const int n = tb[isp * (2 * WIN) + w];
+    int base = -1, end = 0;
+    if (n > 0) {
+      const int cell = window_cell(P, li0, lj0, w);
+      if (cell < 0) {
+        atomicOr(err, ERR_MOVED_TOO_FAR);
+      } else {
+        const int *cs = cstart + (size_t)isp * (P.ncell + 1);
+        base = cs[cell] + atomicAdd(&cnt_new[(size_t)isp * P.ncell + cell], n);
+        end = cs[cell + 1];
+      }
+    }
+    s_base[e] = base;
+    s_end[e] = end;
+  }
+  for (int r = tid; r < nreg; r += PR_THREADS) {
+    const int isp = r / PL_NQ, q = r - isp * PL_NQ;
+    const int cy = q / (TX / 4), cx0 = (q - cy * (TX / 4)) * 4;
+    long long rec0 = so_slots(P, isp);
+    int cap = 0;
+    if (cy < th && cx0 < tw) {
+      const int c0 = (lj0 + cy) * P.nx + li0 + cx0;
+      const int *cs = cstart + (size_t)isp * (P.ncell + 1);
+      stage_region(so_slots(P, isp) + cs[c0], so_slots(P, isp) + cs[min(c0 + 4, (lj0 + cy + 1) * P.nx)], &rec0, &cap);
+    }
+    s_roff[r] = (int)(rec0 - so_slots(P, isp));
+    s_rcnt[r] = min(tb[isp * (2 * WIN) + WIN + q], cap);
+  }
+  __syncthreads();
+  int2 *const mylist = s_list + wid * (2 * PR_RB * 32);
+  const unsigned lanelt = (1u << lane) - 1u;
+#pragma unroll 1
+  for (int rb = wid * PR_RB; rb < nreg; rb += (PR_THREADS / 32) * PR_RB) {
+    int roff[PR_RB], rcnt[PR_RB], nmaxr = 0;
+#pragma unroll
+    for (int v = 0; v < PR_RB; v++) {
+      roff[v] = s_roff[rb + v];
+      rcnt[v] = s_rcnt[rb + v];
+      nmaxr = max(nmaxr, rcnt[v]);
+    }
+    const int isp = rb / PL_NQ;
+    const size_t so = (size_t)isp * P.cap;
+#pragma unroll 1
+    for (int kb = 0; kb < nmaxr; kb += 64) {
+      uint32_t tg[2 * PR_RB];
+#pragma unroll
+      for (int u = 0; u < 2 * PR_RB; u++) {
+        const int k = kb + lane + 32 * (u & 1);
+        tg[u] = TAG_DEAD;
+        if (k < rcnt[u >> 1]) tg[u] = tag[so + (size_t)(roff[u >> 1] + k)];
+      }
+      // the rim arrivals among them (about one in eight): compacted into the warp's list (source record, destination)
+      int nact = 0;
+#pragma unroll
+      for (int u = 0; u < 2 * PR_RB; u++) {
+        const uint32_t t = tg[u];
+        int dd = -1;  // destination slot, -1 = nothing to do, -2 = segment full
+        if (t != TAG_DEAD) {  // (dead: left the slab, already in the send buffer)
+          const int e = isp * WIN + (int)((t >> TAG_WSHIFT) & 0xff);
+          const int bs = s_base[e];
+          if (bs >= 0) {  // (< 0: placed by k_fused_sm itself, new cell inside the tile)
+            dd = bs + (int)(t & TAG_RANK_MASK);
+            if (dd >= s_end[e]) dd = -2;
+          }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, dd != -1);
+        if (dd != -1) mylist[nact + __popc(bal & lanelt)] = make_int2(roff[u >> 1] + kb + lane + 32 * (u & 1), dd);
+        nact += __popc(bal);
+      }
+      __syncwarp();
+      for (int i = lane; i < nact; i += 32) {
+        const int2 m = mylist[i];
+        const double2 *r = stage + (so + (size_t)m.x) * 3;
+        const double2 r0 = r[0], r1 = r[1], r2 = r[2];
+        if (m.y >= 0) {
+          double2 *o = dst.word(so + (size_t)m.y);  // three 16-byte words of the record, one per 128-byte row
+          o[0] = r0;
+          o[8] = r1;
+          o[16] = r2;
+        } else {  // segment full: park the record; the host rebuilds the layout after this step
+          const int kk = atomicAdd(ovfcnt, 1);
+          if (kk < ovfcap) {
+            double *o = ovf + (size_t)kk * 6;
+            o[0] = r0.x; o[1] = r0.y; o[2] = r1.x; o[3] = r1.y; o[4] = r2.x; o[5] = r2.y;
+            ovfsp[kk] = isp;
+          } else {
+            atomicOr(err, ERR_OVERFLOW);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // in-place sort, last step: clamp the new counts to the segment capacity (the surplus is in the
 // overflow list) and retire the slots between the new and the old count
 __global__ void k_mark_dead(const DevParams P, const PView<double> x, const int *__restrict__ cstart, const int *__restrict__ cnt_old,
@@ -1180,7 +1297,12 @@ void launch_incoming_append(const DevParams &P, const double *rec, int n, int is
 }
 void launch_place(const DevParams &P, const double *stage, const uint32_t *tag, const PartSoA &dst, const int *cstart,
                   int *cnt_new, const int *tilebase, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
-                  cudaStream_t st) {
+                  bool rim_only, cudaStream_t st) {
+  if (rim_only) {
+    k_place_rim<<<P.ntx * P.nty, PR_THREADS, 0, st>>>(P, reinterpret_cast<const double2 *>(stage), tag, dst, cstart, cnt_new,
+                                                      tilebase, ovf, ovfsp, ovfcnt, ovfcap, err);
+    return;
+  }
   k_place<<<P.ntx * P.nty, PL_THREADS, 0, st>>>(P, reinterpret_cast<const double2 *>(stage), tag, dst, cstart, cnt_new, tilebase,
                                                ovf, ovfsp, ovfcnt, ovfcap, err);
 }

@@ -71,6 +71,7 @@ struct wm_ctx {
   float slack = 6.0f;                    // segment slack in std deviations of the count change (WM_SLACK)
   bool inplace = true;                   // WM_INPLACE=0 selects the tag + scatter sort for wm_step
   bool cg3 = false;                      // WM_CG3=1: three-kernel CG iteration (k_cg_ap, k_cg_update, k_cg_pupdate)
+  bool rimplace = true;                  // k_place_rim after k_fused_sm<TAIL> (WM_RIMPLACE=0: the general k_place)
   int sm = 1;                            // stayer/mover split deposit (k_fused_sm); WM_SM=0 selects k_fused<INPLACE>
   long long rebuilds = 0;
   int cur = 0;
@@ -508,6 +509,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   if (const char *v = getenv("WM_SLACK")) c->slack = (float)atof(v);
   if (const char *v = getenv("WM_INPLACE")) c->inplace = atoi(v) != 0;
   if (const char *v = getenv("WM_SM")) c->sm = atoi(v);
+  if (const char *v = getenv("WM_RIMPLACE")) c->rimplace = atoi(v) != 0;
   if (const char *v = getenv("WM_CG3")) c->cg3 = atoi(v) != 0;
   if (const char *v = getenv("WM_OVERLAP")) c->overlap = atoi(v) != 0;
   if (g->flags & WM_FLAG_EXACT_PUSH) c->inplace = false;  // the exact path keeps the reference's two-pass structure
@@ -1071,6 +1073,7 @@ static int rebuild_layout(wm_ctx *c, int novf) {
   const DevParams &P = c->P;
   const int dst = c->cur ^ 1;
   if (novf > c->ovfcap) return fail("in-place sort: %d records overflowed their segments, list holds %d", novf, c->ovfcap);
+  launch_clamp_counts(P, c->cstart[c->cur], c->cnt[c->cur], c->st);  // the surplus of a full segment is in the overflow list
   CU(cudaMemcpyAsync(c->gcnt, c->cnt[c->cur], (size_t)P.nsp * P.ncell * sizeof(int), cudaMemcpyDeviceToDevice, c->st));
   launch_incoming_tag(P, c->ovf, novf, 0, c->ovfsp, c->gcnt, c->ovfrank, c->d_err, c->st);
   WM(scan_counts(c, dst));
@@ -1093,6 +1096,8 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
   const size_t ng = (size_t)P.pitch * (P.nyl + 4);
   const int mode = M_PUSH | M_DEPOSIT | M_BOUND | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
   const bool inplace = c->inplace && !(c->cfg.flags & WM_FLAG_EXACT_PUSH);
+  // k_fused_sm<TAIL> places the in-tile cell changers and retires the vacated slots itself: k_place_rim for the rest
+  const bool rim = inplace && c->sm && fused_sm_has_tail(c->sm) && c->rimplace;
   if (P.bc == WM_BC_SHOCK) {
     if (!c->u_inject_set) return fail("wm_step: WM_BC_SHOCK needs wm_set_u_inject(u0) first (bc__injection, proj/shock/app.f90:113)");
     if (!(c->cfg.flags & WM_FLAG_EXACT_PUSH) && !(inplace && c->sm))
@@ -1127,9 +1132,9 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
       CU(cudaStreamWaitEvent(c->st2, c->ev_fork, 0));
       if (c->timing) CU(cudaEventRecord(c->ev_b[0], c->st2));
       launch_place(P, c->pbuf[c->cur ^ 1], c->tag, a, c->cstart[c->cur], c->cnt_tail, c->tilebase, c->ovf, c->ovfsp, c->ovfcnt,
-                   c->ovfcap, c->d_err, c->st2);
-      launch_mark_dead(P, a.x, c->cstart[c->cur], c->cnt[c->cur], c->cnt_tail, c->st2);
-      c->launches += 2;
+                   c->ovfcap, c->d_err, rim, c->st2);
+      if (!rim) launch_mark_dead(P, a.x, c->cstart[c->cur], c->cnt[c->cur], c->cnt_tail, c->st2);  // (rim: done by the fused pass)
+      c->launches += rim ? 1 : 2;
       std::swap(c->cnt[c->cur], c->cnt_tail);  // cnt_tail held the new counts
       CU(cudaMemcpyAsync(c->h_ovf, c->ovfcnt, sizeof(int), cudaMemcpyDeviceToHost, c->st2));
       if (c->timing) CU(cudaEventRecord(c->ev_b[1], c->st2));
@@ -1147,9 +1152,9 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
       if (c->timing) CU(cudaEventRecord(c->ev[4], c->st));
       // sort__bucket, reduced to the cell changers: append them to their new segments
       launch_place(P, c->pbuf[c->cur ^ 1], c->tag, a, c->cstart[c->cur], c->cnt_tail, c->tilebase, c->ovf, c->ovfsp, c->ovfcnt,
-                   c->ovfcap, c->d_err, c->st);
-      launch_mark_dead(P, a.x, c->cstart[c->cur], c->cnt[c->cur], c->cnt_tail, c->st);
-      c->launches += 2;
+                   c->ovfcap, c->d_err, rim, c->st);
+      if (!rim) launch_mark_dead(P, a.x, c->cstart[c->cur], c->cnt[c->cur], c->cnt_tail, c->st);
+      c->launches += rim ? 1 : 2;
       std::swap(c->cnt[c->cur], c->cnt_tail);  // cnt_tail held the new counts
       CU(cudaMemcpyAsync(c->h_ovf, c->ovfcnt, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     } else {
