@@ -262,7 +262,7 @@ def main():
         fp64_pipe = tj.get("fp64_pipe_pct_of_peak")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_pass1<PUSH|DEPOSIT|BOUND> (exact)" if args.exact else ("k_fused_sm (push + Esirkepov deposit split into stayers/movers + particle boundaries + in-place cell sort of the stayers, one pass)" if os.environ.get("WM_SM", "1") != "0" else "k_fused<INPLACE>"),
+    roofline = {"bound": "hbm", "kernel": "k_pass1<PUSH|DEPOSIT|BOUND> (exact)" if args.exact else ("k_fused_sm (push + Esirkepov deposit split into stayers/movers + particle boundaries + in-place cell sort: stayers compacted, in-tile cell changers appended to their new segments; one pass)" if os.environ.get("WM_SM", "1") != "0" else "k_fused<INPLACE>"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_kind, "alg_bytes_per_particle": ALG_BYTES_PASS1, "ms_per_launch": ms_pass1,
                 "fp64_pipe_pct_of_peak_ncu": fp64_pipe,

@@ -11,7 +11,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --fo
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > $OUT/ncu_launch_bench.log 2>&1
 # full capture of the particle kernels at the benchmark size (one launch each, after two warm-up steps)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_fused_sm|k_place" -s 4 -c 2 -o $OUT/prof_pass -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_fused_sm|k_place_rim" -s 4 -c 2 -o $OUT/prof_pass -f \
     python bench.py --steps 2 --warmup 2 --no-e2e --no-cpu > $OUT/ncu_full.log 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:"k_cg_pap|k_cg_update2" -s 12 -c 2 -o $OUT/prof_cg -f \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > $OUT/ncu_cg.log 2>&1

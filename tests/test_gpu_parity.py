@@ -281,12 +281,16 @@ def test_call_order_is_enforced(warm):
 
 
 @pytest.mark.parametrize("env", [{"WM_INPLACE": "0"}, {"WM_SLACK": "0.4"}, {"WM_SLACK": "12"}, {"WM_SM": "0"},
-                                 {"WM_CG3": "1"}, {"WM_OVERLAP": "0"}])
+                                 {"WM_CG3": "1"}, {"WM_OVERLAP": "0"}, {"WM_SM": "3"}, {"WM_RIMPLACE": "0"},
+                                 {"WM_SM": "3", "WM_SLACK": "0.4"}])
 def test_sort_variants_match_oracle(env, monkeypatch):
     """wm_step with (a) the tag + scatter sort, (b) the in-place sort with so little segment slack that
     segments overflow and the layout is rebuilt nearly every step, (c) generous slack, (d) k_fused<INPLACE> (65
     register sums per lane) instead of k_fused_sm, (e) the three-kernel CG iteration, (f) everything on one
-    stream: per-cell counts bit-exact and particles/fields within tolerance in every case."""
+    stream, (g) k_fused_sm without its in-tile tail (every cell changer through k_place + k_mark_dead), (h) the tail
+    with the general k_place instead of k_place_rim, (i) = (g) with overflowing segments: per-cell counts bit-exact and
+    particles/fields within tolerance in every case.  (The default path -- k_fused_sm<TAIL> + k_place_rim -- is what
+    every other test runs; (b) drives its overflow branch.)"""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     prm, w = make_world(40, 24, 16)
@@ -304,7 +308,7 @@ def test_sort_variants_match_oracle(env, monkeypatch):
         ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
         assert ex <= 1e-9 and eu <= 1e-9
         assert rel_to_max(c.download_field(), w.array(0, O.UF)).max() <= 1e-9
-    if env.get("WM_SLACK") == "0.4":
+    if env.get("WM_SLACK") == "0.4":  # noqa
         assert c.rebuilds() > 0, "the overflow -> rebuild path was not exercised"
     c.close()
 
