@@ -1124,7 +1124,7 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
     c->launches += 2;
     if (c->timing) CU(cudaEventRecord(c->ev[2], c->st));
     if (inplace && c->overlap) {
-      // The rest of the sort (migration, k_place, k_mark_dead) only needs what the fused pass left behind, the rest
+      // The rest of the sort (migration, k_place_rim -- or k_place + k_mark_dead on the variant paths) only needs what the fused pass left behind, the rest
       // of field__fdtd_i only needs uj: the two run side by side, the sort on the second stream.  (NCCL calls stay
       // on the main stream, in program order.)
       WM(migrate(c, true));  // ring exchange of the leavers; arrivals are appended to their segments
@@ -1184,7 +1184,7 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
         CU(cudaEventElapsedTime(&tb, c->ev_b[0], c->ev_b[1]));
         c->ms[1] += t[3];         // field solve
         c->ms[2] += t[0] + t[2];  // prep + migration
-        c->ms[3] += tb;           // k_place + k_mark_dead, overlapped with the field solve
+        c->ms[3] += tb;           // k_place_rim (k_place + k_mark_dead), overlapped with the field solve
       } else {
         c->ms[1] += t[2];
         c->ms[2] += t[0] + t[3];
