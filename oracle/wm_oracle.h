@@ -10,7 +10,14 @@
  * this image (no Fortran compiler, no MPI).  The oracle is therefore pinned by
  * (a) an independent numpy restatement of the same Fortran (tests/np_restate.py),
  * (b) analytic invariants (discrete Gauss law, per-cell count identities,
- *     N-rank == 1-rank equivalence, energy behaviour), see tests/.
+ *     N-rank == 1-rank equivalence, energy behaviour),
+ * (c) known answers of the physics the scheme must reproduce
+ *     (tests/test_oracle_pins.py): Boris rotation angle, exact gather of linear
+ *     fields, Esirkepov moments and continuity, the CG solution against a dense
+ *     solve, the amplification factor of a vacuum wave under the implicit
+ *     theta-scheme, G = (1 + i s (1 - gfac)) / (1 - i s gfac), step by step, and
+ *     the frequency and amplitude of a cold Langmuir oscillation
+ *     (omega = 0.994 omega_pe, e E_max = m v0 omega_pe).
  *
  * All arrays use the reference's Fortran (column-major) layout, per rank:
  *   up,gp  (ndim=6, np, nys:nye, nsp)            proj/weibel/app.f90:75-76,281-282
