@@ -157,3 +157,41 @@ def shock_relocate(prm, up, np2, uf, nxe_new, n0, u0, b0, seed):
         uf[:, i - (nxgs - 2), 1] = b0
     uf[:, (nxe_new - 1) - (nxgs - 2), 5] = -v0 * b0 / prm["c"]
     return [np.concatenate(a) for a in added]
+
+
+def make_langmuir_world(nx=32, ny=4, ppc=16, v0=1e-3, m=1, wpe=0.1):
+    """Cold uniform plasma with heavy ions: both species on the same quiet 4 x 4 lattice per cell (ppc = 16), the
+    electrons with ux = v0 sin(k x).  Written into gp and bucket-sorted by the oracle (the restart path)."""
+    assert ppc == 16
+    prm = O.weibel_params(nx, ny, ppc, mass_ratio=1e8, omega_pe=wpe, cap_factor=4.0)
+    w = O.World(prm)
+    nxgs, nygs = prm["nxgs"], prm["nygs"]
+    k = 2 * np.pi * m / nx
+    gp, np2 = w.array(0, O.GP), w.array(0, O.NP2)
+    sub = (np.arange(4) + 0.5) / 4
+    x = (nxgs + np.arange(nx)[:, None, None] + sub[None, :, None] + 0 * sub[None, None, :]).reshape(-1)
+    yo = (0 * np.arange(nx)[:, None, None] + 0 * sub[None, :, None] + sub[None, None, :]).reshape(-1)
+    npr = x.size
+    for jl in range(ny):
+        for isp in range(2):
+            gp[isp, jl, :npr, 0] = x
+            gp[isp, jl, :npr, 1] = nygs + jl + yo
+            gp[isp, jl, :npr, 2:5] = 0.0
+            if isp == 1:
+                gp[isp, jl, :npr, 2] = v0 * np.sin(k * (x - nxgs))
+            gp[isp, jl, :npr, 5].view(np.int64)[:] = -(np.arange(npr) + 1 + jl * npr)
+            np2[isp, jl] = npr
+    w.sort_bucket()
+    w.array(0, O.GP)[...] = w.array(0, O.UP)
+    return prm, w
+
+
+def langmuir_fit(series, delt):
+    """Frequency from the zero crossings of Ex(t) at the probe, and the peak |Ex| of every half period."""
+    e = np.asarray(series)
+    sgn = np.sign(e)
+    idx = np.where(sgn[1:] * sgn[:-1] < 0)[0]
+    tz = idx + e[idx] / (e[idx] - e[idx + 1])      # linear interpolation of the crossing times
+    omega = np.pi / (np.diff(tz).mean() * delt)
+    peaks = [np.abs(e[int(a):int(b) + 1]).max() for a, b in zip(tz[:-1], tz[1:])]
+    return omega, peaks, len(idx)

@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from helpers import flatten_by_id, make_world, oracle_state, particle_err, rel_to_max
+from helpers import (flatten_by_id, langmuir_fit, make_langmuir_world, make_world, oracle_state, particle_err,
+                     rel_to_max)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -311,6 +312,32 @@ def test_sort_variants_match_oracle(env, monkeypatch):
     if env.get("WM_SLACK") == "0.4":  # noqa
         assert c.rebuilds() > 0, "the overflow -> rebuild path was not exercised"
     c.close()
+
+
+def test_langmuir_oscillation_on_device():
+    """A known answer for the CUDA path itself, not through the oracle: cold uniform plasma, heavy ions, electrons on a
+    quiet lattice with ux = v0 sin(k x) (the oracle is only the container of the initial condition).  260 wm_step on the
+    device must make Ex oscillate at the plasma frequency the set-up asked for (0.994 omega_pe with the spline shape
+    factors; tolerance 3 %), with the cold-plasma amplitude e E_max = m v0 omega_pe (2 %) and no growth or damping
+    (tests/test_oracle_pins.py::test_known_answer_langmuir_frequency is the same check on the oracle)."""
+    nx, wpe, v0 = 32, 0.1, 1e-3
+    prm, w = make_langmuir_world(nx, 4, 16, v0=v0, m=1, wpe=wpe)
+    s = oracle_state(w)
+    w.close()
+    c = ctx_for(prm)
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    c.upload_field(s["uf"])
+    series = []
+    for n in range(260):
+        c.step(1)
+        series.append(c.download_field()[2:-2, 2 + nx // 4, 3].mean())
+    c.close()
+    omega, peaks, ncross = langmuir_fit(series, prm["delt"])
+    assert ncross >= 6
+    assert abs(omega / wpe - 1.0) <= 0.03, omega
+    assert 0.8 <= peaks[-1] / peaks[0] <= 1.2, peaks
+    e_max = prm["r"][1] * v0 * wpe / abs(prm["q"][1])
+    assert abs(peaks[0] / e_max - 1.0) <= 0.02, (peaks[0], e_max)
 
 
 def test_dense_cells_drain_early():
