@@ -340,6 +340,43 @@ def test_langmuir_oscillation_on_device():
     assert abs(peaks[0] / e_max - 1.0) <= 0.02, (peaks[0], e_max)
 
 
+@pytest.mark.parametrize("m,cfl,gfac", [(1, 1.0, 0.501), (3, 0.5, 0.75)])
+def test_vacuum_wave_amplification_on_device(m, cfl, gfac):
+    """The second known answer for the CUDA path itself: a standing wave Ez = cos(k x), B = 0 in (effectively) vacuum --
+    the particles carry a charge of 1e-14 -- must be multiplied per wm_step by Re(G^n), G = (1 + i s (1 - gfac)) /
+    (1 - i s gfac), s = (c dt / delx) 2 sin(k delx / 2): the amplification factor of the implicit scheme of
+    field.f90:125-171 (derivation in tests/test_oracle_pins.py::test_known_answer_vacuum_wave_dispersion).  Checks
+    k_rhs, the CG kernels, k_efield, the halo fills and k_update_uf against the algebra of the scheme."""
+    nx, ny, nsteps = 24, 8, 24
+    prm = O.weibel_params(nx, ny, 2, cfl=cfl, gfac=gfac)
+    prm["q"] = [1e-14, -1e-14]
+    w = O.World(prm)
+    w.ic_weibel(3)
+    s = oracle_state(w)
+    w.close()
+    k = 2 * np.pi * m / nx
+    uf = np.zeros_like(s["uf"])
+    ii = np.arange(uf.shape[1]) + (prm["nxgs"] - 2)
+    ez0 = np.cos(k * (ii + 0.5))[None, :] * np.ones((uf.shape[0], 1))
+    uf[:, :, 5] = ez0
+    c = ctx_for(prm)
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    c.upload_field(uf)
+    s_ = prm["c"] * prm["delt"] / prm["delx"] * 2 * np.sin(k * prm["delx"] / 2)
+    G = (1 + 1j * s_ * (1 - gfac)) / (1 - 1j * s_ * gfac)
+    Gn = 1.0 + 0j
+    for n in range(1, nsteps + 1):
+        c.step(1)
+        Gn *= G
+        f = c.download_field()[2:-2, 2:-2]
+        # CG tolerance 1e-6 per solve (field.f90:339), accumulated over the steps
+        assert np.abs(f[:, :, 5] - Gn.real * ez0[2:-2, 2:-2]).max() <= 2e-5, n
+        assert abs(np.abs(f[:, :, 1]).max() - abs(Gn.imag)) <= 2e-5, n
+        for comp in (0, 2, 3, 4):
+            assert np.abs(f[:, :, comp]).max() <= 1e-10, (n, comp)
+    c.close()
+
+
 def test_dense_cells_drain_early():
     """k_fused_sm queues the movers of a cell (40 slots per cell) and drains the queue when the cell is done.  With
     200 particles per cell per species about 60 particles per cell change cell in a step, so the queue is drained
