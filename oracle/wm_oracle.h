@@ -17,7 +17,8 @@
  *     solve, the amplification factor of a vacuum wave under the implicit
  *     theta-scheme, G = (1 + i s (1 - gfac)) / (1 - i s gfac), step by step, and
  *     the frequency and amplitude of a cold Langmuir oscillation
- *     (omega = 0.994 omega_pe, e E_max = m v0 omega_pe).
+ *     (omega = 0.994 omega_pe, e E_max = m v0 omega_pe), and the frequency of a
+ *     light wave in a cold plasma (omega^2 = omega_pe^2 + c^2 k^2).
  *
  * All arrays use the reference's Fortran (column-major) layout, per rank:
  *   up,gp  (ndim=6, np, nys:nye, nsp)            proj/weibel/app.f90:75-76,281-282

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from helpers import (flatten_by_id, langmuir_fit, make_langmuir_world, make_world, oracle_state, particle_err,
+from helpers import (em_wave_in_plasma_setup, flatten_by_id, langmuir_fit, make_langmuir_world, make_world, oracle_state, particle_err,
                      rel_to_max)
 
 pytestmark = pytest.mark.gpu
@@ -375,6 +375,28 @@ def test_vacuum_wave_amplification_on_device(m, cfl, gfac):
         for comp in (0, 2, 3, 4):
             assert np.abs(f[:, :, comp]).max() <= 1e-10, (n, comp)
     c.close()
+
+
+def test_light_wave_in_plasma_on_device():
+    """Third known answer for the CUDA path itself: an Ez standing wave in a cold plasma at rest oscillates at
+    omega^2 = omega_pe^2 + c^2 k^2 (2 %), and at the scheme's own dispersion relation to 0.3 % -- the uz push, the Jz
+    deposit and the implicit solve together (tests/test_oracle_pins.py::test_known_answer_light_wave_in_plasma)."""
+    prm, w, uf, om_scheme, om_text = em_wave_in_plasma_setup(2)
+    s = oracle_state(w)
+    w.close()
+    c = ctx_for(prm)
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    c.upload_field(uf)
+    series = []
+    for n in range(300):
+        c.step(1)
+        series.append(c.download_field()[2:-2, 2, 5].mean())
+    c.close()
+    omega, peaks, ncross = langmuir_fit(series, prm["delt"])
+    assert ncross >= 15
+    assert abs(omega / om_scheme - 1.0) <= 3e-3, (omega, om_scheme)
+    assert abs(omega / om_text - 1.0) <= 0.02, (omega, om_text)
+    assert 0.85 <= peaks[-1] / peaks[0] <= 1.05, peaks
 
 
 def test_dense_cells_drain_early():
