@@ -266,6 +266,9 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_kind, "alg_bytes_per_particle": ALG_BYTES_PASS1, "ms_per_launch": ms_pass1,
                 "fp64_pipe_pct_of_peak_ncu": fp64_pipe,
+                "note": ("alg_bytes_per_particle counts the push pass only (48 B read + 48 B written, SURVEY 8d); since r01t the "
+                         "kernel also appends the cell changers that stay in their tile to their new segments (sort work, "
+                         "about 13 B/particle more traffic, not counted): compare whole_step across rounds, not this frac"),
                 "whole_step": {"alg_bytes_per_particle_step": ALG_BYTES_STEP,
                                "achieved": ALG_BYTES_STEP * n_local / (allmax(ms[4]) / args.steps * 1e-3) / 1e9,
                                "frac": ALG_BYTES_STEP * n_local / (allmax(ms[4]) / args.steps * 1e-3) / 1e9 / peak}}
