@@ -253,6 +253,14 @@ contains
     end if
   end subroutine wm_shim__try_create
 
+  !> forward the active x range of a call (its nxs, nxe arguments) to the library.  Only boundary_shock works on a
+  !! sub-range and moves nxe in time (proj/shock/app.f90:611-621); the other modules always pass nxgs, nxge.
+  subroutine wm_shim__set_xrange(nxs, nxe)
+    integer, intent(in) :: nxs, nxe
+    if (bc_kind /= WM_BC_SHOCK) return
+    call wm_check(wm_set_xrange(ctx, int(nxs, c_int32_t), int(nxe, c_int32_t)), 'wm_set_xrange')
+  end subroutine wm_shim__set_xrange
+
   !> tell the shim that the application changed up/uf/np2/cumcnt on the host (restart load,
   !! shock `inject`/`relocate` when not using the device-side injection)
   subroutine wm_shim__mark_host_dirty()

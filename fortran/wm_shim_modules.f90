@@ -15,6 +15,9 @@
 !!    applies them inside wm_field__fdtd_i);
 !!  * sort__bucket declares np2 intent(inout): it is where the host copies of up/np2/cumcnt/uf are
 !!    refreshed (every WM_SYNC_INTERVAL-th call);
+!!  * every procedure that receives the active range (nxs, nxe) forwards it with wm_set_xrange before its own call when
+!!    the boundary module is boundary_shock (proj/shock/app.f90 `relocate` moves nxe between two steps, and
+!!    particle__solv is the first call of the next step: its cell-centre fields must cover the new columns);
 !!  * `gp` is never written on the host (it is device scratch); nothing in the apps reads it
 !!    between particle__solv and sort__bucket except the routines replaced here.
 
@@ -49,6 +52,7 @@ contains
        write(6,*) 'Initialize first by calling particle__init()'
        stop
     end if
+    call wm_shim__set_xrange(nxs, nxe)   ! first call of a step: relocate() may have moved nxe since the last one
     call wm_shim__upload_if_dirty(up, uf, cumcnt)
     call wm_check(wm_particle__solv(ctx), 'particle__solv')
   end subroutine particle__solv
@@ -88,6 +92,7 @@ contains
        write(6,*) 'Initialize first by calling field__init()'
        stop
     end if
+    call wm_shim__set_xrange(nxs, nxe)
     ! ele_cur + bc__curre + cgm x3 + bc__dfield x2 + uf update, all on the device
     call wm_check(wm_field__fdtd_i(ctx), 'field__fdtd_i')
     ! uf is final for this step: refresh the host copy if this step's sort__bucket will sync
@@ -123,6 +128,7 @@ contains
        call wm_check(wm_download_particles(ctx, gp, np2, cumcnt), 'sort__bucket(download)')
        return                      ! uf is still only on the host: stay dirty until particle__solv
     end if
+    call wm_shim__set_xrange(nxs, nxe)
     call wm_check(wm_sort__bucket(ctx), 'sort__bucket')
     nstep_since_sync = nstep_since_sync + 1
     if (sync_interval > 0 .and. nstep_since_sync >= sync_interval) then
@@ -218,6 +224,7 @@ contains
     real(8), intent(in)  :: up(cfg%ndim,cfg%np,cfg%nys:cfg%nye,cfg%nsp)
     real(8), intent(in)  :: uf(6,cfg%nxgs-2:cfg%nxge+2,cfg%nys-2:cfg%nye+2)
     real(8), intent(out) :: gp(cfg%ndim,cfg%np,cfg%nys:cfg%nye,cfg%nsp)
+    call wm_shim__set_xrange(nxs, nxe)
     call wm_shim__upload_if_dirty(up, uf, cumcnt)
     call wm_check(wm_mom_calc__accl(ctx), 'mom_calc__accl')
   end subroutine mom_calc__accl
@@ -362,7 +369,7 @@ contains
     real(8), intent(inout) :: up(cfg%ndim,cfg%np,cfg%nys:cfg%nye,cfg%nsp)
     real(8), intent(in)    :: u0
     ! the shock app moves nxe (relocate): tell the library the active range of this step's calls
-    call wm_check(wm_set_xrange(ctx, nxs, nxe), 'boundary_shock__injection (wm_set_xrange)')
+    call wm_shim__set_xrange(nxs, nxe)
     call wm_check(wm_boundary__injection(ctx, u0), 'boundary_shock__injection')
   end subroutine boundary_shock__injection
 

@@ -1,6 +1,7 @@
 """Restart snapshots in the reference's NAME.json + NAME.raw format (common/paraio.f90:93-426)."""
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -26,7 +27,9 @@ def test_restart_file_layout_and_roundtrip(tmp_path):
     S.write_restart(base, 2, prm["nxgs"], prm["nxgs"] + 15, _cfg(prm), ups, np2s, ufs)
     root = json.load(open(base + ".json"))
     assert list(root) == ["meta", "attribute", "dataset"]
-    assert root["meta"]["rawfile"] == "0000002_restart.raw" and root["meta"]["endian"] in (1, 16777216)
+    assert root["meta"]["rawfile"] == "0000002_restart.raw"
+    # mpiio_get_endian_flag (utils/iocore/mpiio.f90:97-109): 1 on a little-endian writer, 16777216 on a big-endian one
+    assert root["meta"]["endian"] == (1 if sys.byteorder == "little" else 16777216)
     names = list(root["attribute"])
     assert names == ["dummy_attribute", "it", "nxs", "nxe", "ndim", "np", "nxgs", "nxge", "nygs", "nyge", "nsp", "nproc",
                      "delx", "delt", "c", "r", "q"]
@@ -121,3 +124,53 @@ def test_moment_file_matches_paraio_arithmetic(tmp_path):
                    (u(3, 0, 0) + u(3, 1, 0)) / 2, (u(4, 0, 0) + u(4, 0, 1)) / 2, u(5, 0, 0)]
             assert np.array_equal(cc[j, i], ref)
     w.close()
+
+
+def test_endian_flag_of_a_reference_written_file(tmp_path):
+    """A snapshot as the Fortran code writes it on x86 -- meta.endian = 1 (utils/iocore/mpiio.f90:97-109), little-endian
+    raw data -- must read back unswapped, and one labelled 16777216 with big-endian raw data must be swapped
+    (python/json2hdf5.py:38-41 maps 1 -> '<', 16777216 -> '>')."""
+    from wumingpic2d_b200 import snapshot as S
+    vals = np.arange(1, 7, dtype=np.float64) * 0.5
+    ints = np.array([3, 1, 4], dtype=np.int32)
+    for flag, order in ((1, "<"), (16777216, ">")):
+        base = str(tmp_path / ("e%d" % flag))
+        with open(base + ".raw", "wb") as f:
+            f.write(ints.astype(order + "i4").tobytes())
+            f.write(vals.astype(order + "f8").tobytes())
+        root = {"meta": {"endian": flag, "rawfile": os.path.basename(base) + ".raw"},
+                "attribute": {"n": {"datatype": "i4", "offset": 0, "size": 12, "ndim": 1, "shape": [3], "description": "", "data": [3, 1, 4]}},
+                "dataset": {"a": {"datatype": "f8", "offset": 12, "size": 48, "ndim": 2, "shape": [3, 2], "description": "a"}}}
+        json.dump(root, open(base + ".json", "w"))
+        out = S.read_datasets(base)
+        assert out["attribute"]["n"] == [3, 1, 4]
+        assert np.array_equal(out["dataset"]["a"], vals.reshape(2, 3))
+    assert S.endian_flag() == int(np.frombuffer(np.array([1, 0, 0, 0], np.uint8).tobytes(), np.int32)[0])
+
+
+def test_metadata_writer_reproduces_the_reference_fixture(tmp_path):
+    """The one golden file the reference ships for this format: utils/iocore/jsonio_expected.json, which its jsonio_test
+    (utils/iocore/jsonio_test.f90: nx=16, ny=32, ns=2, mass, charge, emf (6,ny,nx), mom (10,ny,nx), meta info /
+    large_int) must reproduce (utils/iocore/unittest.py:63-76).  The same calls through this package's writer give
+    the same JSON key by key -- names, order, datatypes, offsets, sizes, shapes, descriptions, data
+    (tests/golden/jsonio_expected.json = that fixture parsed and re-serialised by tests/golden/make_jsonio_fixture.py)."""
+    from wumingpic2d_b200 import snapshot as S
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jsonio_expected.json")))
+    nx, ny = 16, 32
+    base = str(tmp_path / "test")
+    attrs = [("nx", "i4", nx, "# grid in x"), ("ny", "i4", ny, "# grid in y"), ("ns", "i4", 2, "# species"),
+             ("mass", "f8", [1.0, 100.0], "mass"), ("charge", "f8", [-1.0, 1.0], "charge")]
+    ds = [("emf", "f8", np.zeros((nx, ny, 6)), [6, ny, nx], "electromagnetic fields"),
+          ("mom", "f8", np.zeros((nx, ny, 10)), [10, ny, nx], "moments")]
+    S._write_file(base, attrs, ds, meta={"info": "some information", "large_int": 2 ** 32})
+    mine = json.load(open(base + ".json"))
+    if sys.byteorder != "little":
+        gold["meta"]["endian"] = 16777216
+    assert list(mine) == list(gold)
+    for sec in gold:
+        assert list(mine[sec]) == list(gold[sec]), sec
+        for name, rec in gold[sec].items():
+            if isinstance(rec, dict):
+                assert list(mine[sec][name]) == list(rec), (sec, name)
+            assert mine[sec][name] == rec, (sec, name, mine[sec][name], rec)
+    assert os.path.getsize(base + ".raw") == gold["dataset"]["mom"]["offset"] + gold["dataset"]["mom"]["size"]

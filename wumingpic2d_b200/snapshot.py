@@ -27,8 +27,9 @@ _F8_ATTRS = ("delx", "delt", "c", "r", "q")
 
 
 def endian_flag():
-    """mpiio_get_endian_flag (utils/iocore/mpiio.f90): the int32 1 as the writer's memory holds it, read big-endian."""
-    return 1 if sys.byteorder == "big" else 16777216
+    """mpiio_get_endian_flag (utils/iocore/mpiio.f90:97-109): the bytes (1, 0, 0, 0) transferred into an int32, i.e. 1
+    on a little-endian writer and 16777216 on a big-endian one; python/json2hdf5.py:38-41 reads them as '<' and '>'."""
+    return 1 if sys.byteorder == "little" else 16777216
 
 
 def write_restart(base, it, nxs, nxe, cfg, up, np2, uf):
@@ -111,15 +112,17 @@ def load_into_context(base, ctx, rank=0):
     return attrs
 
 
-def _write_file(base, attrs, datasets):
-    """Common writer: attrs = [(name, dtype, value)], datasets = [(name, dtype, array(C order), Fortran shape, desc)]."""
+def _write_file(base, attrs, datasets, meta=None):
+    """Common writer: attrs = [(name, dtype, value[, description])], datasets = [(name, dtype, array(C order), Fortran
+    shape, desc)]; meta = extra entries of the "meta" object (jsonio_put_metadata of scalars, utils/iocore/jsonio.f90)."""
     root = {"meta": {"endian": endian_flag(), "rawfile": os.path.basename(base) + ".raw"}, "attribute": {}, "dataset": {}}
+    root["meta"].update(meta or {})
     disp = 0
     with open(base + ".raw", "wb") as f:
-        for name, dt, val in attrs:
+        for name, dt, val, *desc in attrs:
             a = np.atleast_1d(np.asarray(val, dtype=_DT[dt]))
             root["attribute"][name] = {"datatype": dt, "offset": disp, "size": int(a.nbytes), "ndim": 1, "shape": [int(a.size)],
-                                       "description": "", "data": (a.tolist() if a.size > 1 else a.tolist()[0])}
+                                       "description": desc[0] if desc else "", "data": (a.tolist() if a.size > 1 else a.tolist()[0])}
             f.write(a.tobytes())
             disp += a.nbytes
         for name, dt, arr, shape, desc in datasets:
