@@ -107,12 +107,29 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_config(nx, rows, ppc, world):
+    """The `config` object of both arms (the reference arm runs a bounded sample of exactly this workload)."""
+    return {"workload": "weibel %dx%d grid (%d rows per GPU), %d ppc/species, e-/ion, uniform Maxwellian "
+                        "(BASELINE configs[1] slab)" % (nx, rows * world, rows, ppc),
+            "particles": 2 * nx * rows * world * ppc, "parallelism": "y-slab x%d" % world}
+
+
+def host_threads():
+    """All host cores of the box.  Set explicitly: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, and
+    under it only rank 0 runs the CPU arm, so it takes every core (the ranks do not share the CPU arm)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_rate(steps, warmup, rows=32, nx=NX, ppc=PPC):
     """The CPU oracle (timing build, all host threads) on a bounded sample of the workload:
     same nx, ppc, physics and IC recipe, `rows` rows instead of 512 per GPU."""
     import oracle_lib as O
     prm = weibel_params(nx, rows, ppc)
     w = O.World(prm, fast=True)
+    w.lib.orc_set_num_threads(host_threads())
     w.ic_weibel(SEED)
     npart = 2 * nx * rows * ppc
     if warmup:
@@ -133,16 +150,21 @@ def cpu_reference_rate(steps, warmup, rows=32, nx=NX, ppc=PPC):
 
 
 def run_reference(args, rank, world):
+    """The reference's CPU path (C++/OpenMP restatement: the Fortran + MPI build cannot be produced here) on all host
+    cores of the box, rank 0 only, on a bounded sample of the GPU arm's workload: the same nx, ppc, physics and initial
+    condition, REF_ROWS rows (4096 x 256 cells x 64 ppc x 2 = 134 M particles -- the particle count of BASELINE.md
+    section 4's 1024^2 sample, kept at the slab's own nx so the row length / cache behaviour is the workload's).  The
+    metric is a rate, so it does not depend on the number of rows once the working set is far beyond the caches."""
     if rank != 0:
         return
-    base = cpu_reference_rate(args.steps, args.warmup)
+    base = cpu_reference_rate(args.steps, args.warmup, rows=args.ref_rows, nx=args.nx, ppc=args.ppc)
     line = {
         "impl": "reference", "metric": "particle-steps/sec (push+deposit+sort+field)", "value": base["value"],
         "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "weibel 4096x(512 per GPU) 64 ppc/species e-/ion uniform Maxwellian; "
-                               "CPU arm runs a bounded 4096x32-row sample of it", "parallelism": "openmp%d" % base["cores"]},
+        "config": workload_config(args.nx, args.rows, args.ppc, args.gpus),
+        "cpu_parallelism": "openmp%d (rank 0 of %d, all host cores)" % (base["cores"], world),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -159,6 +181,7 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU (default: the named workload)")
     ap.add_argument("--nx", type=int, default=NX)
     ap.add_argument("--ppc", type=int, default=PPC)
+    ap.add_argument("--ref-rows", type=int, default=256, help="rows of the CPU arm's sample (--impl reference)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -244,6 +267,17 @@ def main():
     ms_pass1 = allmax(ms[0]) / args.steps
     cg = ctx.cg_iters()
 
+    # ---- did the physics survive?  (every N: particle number over all ranks, discrete Gauss law over the ring)
+    n_after = allsum(float(sum(ctx.particle_counts())))
+    g_res, g_scale = ctx.gauss_residual()
+    g_res, g_scale = allmax(g_res), allmax(g_scale)
+    check = {"particles_conserved": bool(n_after == n_total), "particles": int(n_after),
+             "gauss_rel": g_res / g_scale if g_scale > 0 else None, "gauss_tol": 1e-10,
+             "steps_run": args.warmup + args.steps,
+             "what": "sum over ranks of the particle counts after the run == before; max |div E - 4 pi rho| / max 4 pi rho_abs "
+                     "over all cells of all ranks (rho folded over the rank ring), must stay at roundoff (Esirkepov)"}
+    check["ok"] = bool(check["particles_conserved"] and check["gauss_rel"] is not None and check["gauss_rel"] <= check["gauss_tol"])
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -316,13 +350,15 @@ def main():
             "metric": "particle-steps/sec (push+deposit+sort+field)", "value": value, "unit": "particle-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "weibel %dx%d grid (%d rows per GPU), %d ppc/species, e-/ion, uniform Maxwellian "
-                                   "(BASELINE configs[1] slab)" % (nx, ny, rows, ppc),
-                       "particles": int(n_total), "parallelism": "y-slab x%d" % world,
-                       "l2": "working set %.1f GB per GPU >> 126 MB L2" % (n_local * 96 / 1e9),
-                       "push_arithmetic": "exact" if args.exact else "fma", "cg_iters": cg,
-                       "sort": "tag+scatter" if (args.exact or os.environ.get("WM_INPLACE") == "0") else "in-place",
-                       "layout_rebuilds": ctx.rebuilds()},
+            "config": workload_config(nx, rows, ppc, world),
+            "run_info": {"l2": "working set %.1f GB per GPU >> 126 MB L2: no flush needed between steps" % (n_local * 96 / 1e9),
+                         "push_arithmetic": "exact" if args.exact else "fma", "cg_iters": cg,
+                         "cg_path": {0: "host loop of small kernels (+ NCCL per iteration on a ring)",
+                                     1: "persistent cooperative kernel", 2: "persistent cooperative kernel, ring exchange and "
+                                     "all-reduce in the kernel over CUDA-IPC peer memory"}[ctx.cg_path()],
+                         "sort": "tag+scatter" if (args.exact or os.environ.get("WM_INPLACE") == "0") else "in-place",
+                         "layout_rebuilds": ctx.rebuilds()},
+            "check": check,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "stage_ms": stage_ms, "wall_ms_per_step": wall_step,
         }
@@ -330,6 +366,8 @@ def main():
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+    if not check["ok"]:
+        raise SystemExit("bench.py: correctness check failed: %s" % json.dumps(check))
 
 
 if __name__ == "__main__":

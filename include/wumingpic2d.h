@@ -145,12 +145,21 @@ int wm_host_sort__bucket(wm_ctx *ctx, double *gp_out, const double *up_in, int32
 
 /* ---- diagnostics ------------------------------------------------------------------- */
 int wm_cg_iters(wm_ctx *ctx, int32_t out[3]);  /* CG iterations of the last solve, l=1..3 */
+/* Which implementation of cgm (common/field.f90:319-461) the next field solve uses: 0 = host loop of small kernels with NCCL
+ * all-reduces / halo exchanges per iteration, 1 = one persistent cooperative kernel (one rank), 2 = the persistent kernel
+ * with the ring exchange and the all-reduce done in the kernel over CUDA-IPC mapped peer memory.  WM_CG=0 forces 0. */
+int wm_cg_path(wm_ctx *ctx, int32_t *path);
+/* Block decomposition the persistent CG kernel uses for an nx x nyl slab on a device with nsm SMs and smem_max bytes of
+ * shared memory per CTA: out = {blocks in x, blocks in y, shared-memory bytes}; error if the slab does not fit (pure host
+ * logic, no device needed). */
+int wm_cg_plan(int32_t nx, int32_t nyl, int32_t nsm, int64_t smem_max, int32_t out[3]);
 /* energy_history (proj/weibel/app.f90:479-545), this rank's share:
  * out[0..nsp-1] kinetic, out[nsp] = sum E^2/8pi, out[nsp+1] = sum B^2/8pi */
 int wm_energy(wm_ctx *ctx, double *out);
 /* discrete Gauss law of the current state (north_star: "div E - rho/eps0 must hold to roundoff"; Gaussian units:
  * div E = 4 pi rho, common/field.f90:159): out[0] = max |div E - 4 pi rho| over the cells, rho with the deposit's
- * second-order shape, out[1] = max 4 pi sum |q| S S, the scale.  Periodic boundaries, one rank. */
+ * second-order shape, out[1] = max 4 pi sum |q| S S, the scale; both over this rank's cells.  Periodic boundaries; on a ring
+ * every rank calls it (one exchange of the edge rows of rho per direction). */
 int wm_gauss_residual(wm_ctx *ctx, double out[2]);
 /* mom_calc__accl (common/mom_calc.f90:48): half-step momenta into the device's idle particle
  * store (the reference's `gp`); valid until the next call that moves or transfers particles */

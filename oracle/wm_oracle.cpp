@@ -1328,4 +1328,14 @@ int orc_num_threads(void) {
 #endif
 }
 
+// OpenMP team size of the following calls (bench.py sets it explicitly: launchers such as torch.distributed.run export
+// OMP_NUM_THREADS=1 to their workers)
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 }  // extern "C"

@@ -118,6 +118,7 @@ double orc_rng_uniform(uint64_t seed, int isp, uint64_t gid, int stream);
 
 /* number of OpenMP threads the oracle will use */
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

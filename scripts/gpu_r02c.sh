@@ -1,0 +1,9 @@
+#!/bin/bash
+TAG=${1:-r02c}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+( timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 ) > $OUT/pytest_gpu.log
+( WM_OVERLAP=0 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu 2> $OUT/bench.err | tail -1 ) > $OUT/bench_nooverlap.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > $OUT/ncu_launch_bench.log 2>&1
+cat $OUT/pytest_gpu.log $OUT/bench_nooverlap.json

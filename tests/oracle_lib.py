@@ -80,6 +80,7 @@ def load(fast=False):
     lib.orc_rng_uniform.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_int]
     lib.orc_rng_uniform.restype = C.c_double
     lib.orc_num_threads.restype = C.c_int
+    lib.orc_set_num_threads.argtypes = [C.c_int]
     _libs[key] = lib
     return lib
 

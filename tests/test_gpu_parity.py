@@ -282,12 +282,13 @@ def test_call_order_is_enforced(warm):
 
 
 @pytest.mark.parametrize("env", [{"WM_INPLACE": "0"}, {"WM_SLACK": "0.4"}, {"WM_SLACK": "12"}, {"WM_SM": "0"},
-                                 {"WM_CG3": "1"}, {"WM_OVERLAP": "0"}, {"WM_SM": "3"}, {"WM_RIMPLACE": "0"},
+                                 {"WM_CG3": "1", "WM_CG": "0"}, {"WM_CG": "0"}, {"WM_OVERLAP": "0"}, {"WM_SM": "3"}, {"WM_RIMPLACE": "0"},
                                  {"WM_SM": "3", "WM_SLACK": "0.4"}])
 def test_sort_variants_match_oracle(env, monkeypatch):
     """wm_step with (a) the tag + scatter sort, (b) the in-place sort with so little segment slack that
     segments overflow and the layout is rebuilt nearly every step, (c) generous slack, (d) k_fused<INPLACE> (65
-    register sums per lane) instead of k_fused_sm, (e) the three-kernel CG iteration, (f) everything on one
+    register sums per lane) instead of k_fused_sm, (e) the host-loop CG with the three-kernel / two-kernel iteration instead of
+    the persistent cooperative kernel, (f) everything on one
     stream, (g) k_fused_sm without its in-tile tail (every cell changer through k_place + k_mark_dead), (h) the tail
     with the general k_place instead of k_place_rim, (i) = (g) with overflowing segments: per-cell counts bit-exact and
     particles/fields within tolerance in every case.  (The default path -- k_fused_sm<TAIL> + k_place_rim -- is what
@@ -312,6 +313,41 @@ def test_sort_variants_match_oracle(env, monkeypatch):
     if env.get("WM_SLACK") == "0.4":  # noqa
         assert c.rebuilds() > 0, "the overflow -> rebuild path was not exercised"
     c.close()
+
+
+@pytest.mark.parametrize("kind", ["periodic", "reconnection", "shock"])
+def test_persistent_cg_many_blocks(kind):
+    """cgm (common/field.f90:319-461) as the persistent cooperative kernel on a grid that is split over many CTAs in both
+    directions (block edges, the halo ring through the global r array, wrapped / wall columns): equal CG iteration counts
+    per component and fields <= 1e-12 against the oracle step by step, and the same against the host-loop CG."""
+    from helpers import make_shock_world, make_wall_world
+    import wumingpic2d_b200 as wm
+    if kind == "periodic":
+        prm, w = make_world(208, 150, 3)
+    elif kind == "reconnection":
+        prm, w = make_wall_world(160, 128, 3)
+    else:
+        prm, w = make_shock_world(160, 128, 3, u0=-0.3)
+    s = oracle_state(w)
+    c = ctx_for(prm)
+    assert c.cg_path() == 1, "the persistent CG kernel must be the default on one rank"
+    plan = wm.api.cg_plan(prm["nx"], prm["ny"])
+    assert plan[0] > 1 and plan[1] > 1, plan
+    if kind == "shock":
+        c.set_u_inject(-0.3)
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    c.upload_field(s["uf"])
+    for it in range(4):
+        w.step(1)
+        c.step(1)
+        assert c.cg_iters() == w.cg_iters(), (it, c.cg_iters(), w.cg_iters())
+        assert max(c.cg_iters()) > 0
+        assert rel_to_max(c.download_field(), w.array(0, O.UF)).max() <= (TOL if it == 0 else 1e-10)
+        assert rel_to_max(c.download_dfield()[..., :3], w.array(0, O.DF)[..., :3]).max() <= (1e-11 if it == 0 else 1e-9)
+    up, np2, cum = c.download_particles()
+    assert np.array_equal(cum, w.array(0, O.CUMCNT))
+    c.close()
+    w.close()
 
 
 def test_langmuir_oscillation_on_device():

@@ -49,9 +49,10 @@ void launch_fused_inplace(const DevParams &P, const Pass1Args &a, cudaStream_t s
 void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaStream_t st);
 void launch_kinetic(const DevParams &P, const PartSoA &src, const int *cstart, int isp, double *partial, int nblocks,
                     cudaStream_t st);
-// diagnostic: discrete Gauss law residual of the sorted store against uf (periodic, one rank)
-void launch_gauss(const DevParams &P, const PartSoA &src, const int *cstart, const double *uf, double *rho,
-                  unsigned long long *out, cudaStream_t st);
+// diagnostic: discrete Gauss law residual of the sorted store against uf (periodic x).  rho: 2 planes of (nyl + 2) rows; the
+// rows 0 and nyl + 1 belong to the ring neighbours and are folded by the host between the two launches
+void launch_charge_density(const DevParams &P, const PartSoA &src, const int *cstart, double *rho, cudaStream_t st);
+void launch_gauss(const DevParams &P, const double *uf, const double *rho, unsigned long long *out, cudaStream_t st);
 void launch_moments(const DevParams &P, const PartSoA &src, PView<double> keyx, const int *cstart, double *mom,
                     cudaStream_t st);
 
@@ -89,6 +90,34 @@ void launch_cg_finish(const DevParams &P, const FieldBufs &f, cudaStream_t st); 
 void launch_efield(const DevParams &P, const FieldBufs &f, cudaStream_t st);       // df(4:6)
 void launch_update_uf(const DevParams &P, const FieldBufs &f, cudaStream_t st);    // uf += df
 void launch_field_energy(const DevParams &P, const double *uf, double *partial, int nblocks, cudaStream_t st);
+// ---- persistent cooperative CG (cg_persist_kernel.cu): the three solves of cgm in one kernel, state on chip
+constexpr int CGP_T = 1024;   // threads per CTA, one CTA per SM
+constexpr int CGP_K = 14;     // cells per thread at most (r in registers): 148 x 14336 >= 4096 x 512
+constexpr int CGP_MAXR = 8;   // ranks on the ring the in-kernel all-reduce supports
+struct CgpShared {            // one per rank, mapped by every other rank (CUDA IPC)
+  unsigned long long flag[CGP_MAXR];  // flag[src] = last barrier sequence number rank src has published here
+  double xsum[4][CGP_MAXR][4];        // [sequence & 3][src][value]: rank src's sums of that barrier
+};
+struct CgpArgs {
+  int cbx, cby;               // block decomposition of the slab: cbx x cby CTAs
+  double *df;                 // in: df(1:3) warm start (+ ghost rows of the ring neighbours); out: df(1:3) interior
+  const double *gkl;          // right-hand side before the f5 scaling
+  double *rg;                 // AoS3 padded: r of the blocks' perimeter cells, ghost rows written by the ring neighbours
+  double *phipl, *bpl;        // 3 dense planes each: phi and b, cell e of CTA c at plane[l] + base(c) + e
+  double *partial;            // [2][G][4] partial sums of the CTAs
+  unsigned *bar;              // barrier counter, zero at launch
+  int *abort;                 // set by a CTA whose wait timed out: everybody leaves
+  int *out;                   // ite[3], stop, barriers
+  unsigned *err;
+  int nrank, nsize;
+  unsigned long long seq0;    // barrier sequence base of this solve (same on every rank)
+  CgpShared *sh[CGP_MAXR];    // every rank's block as mapped here (sh[nrank] = mine)
+  double *r_up, *r_down;      // rg of nup / ndown as mapped here
+  int nyl_down;               // rows of ndown: its upper ghost row is local row nyl_down
+};
+bool cgp_plan(int nx, int nyl, int nsm, size_t smem_max, int *cbx, int *cby, size_t *smem);
+cudaError_t cgp_prepare(size_t smem);
+cudaError_t launch_cg_persist(const DevParams &P, const CgpArgs &a, size_t smem, cudaStream_t st);
 size_t cgctl_bytes();
 size_t cgctl_active_offset();       // int active[3]; int ite[3]; int stop  (contiguous)
 size_t cgctl_sums_offset(int which); // 0 sumb, 1 sumr(+sum2 adjacent), 2 sum2, 3 sum1

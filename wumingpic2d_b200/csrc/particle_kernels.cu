@@ -778,11 +778,13 @@ __global__ void k_moments(const DevParams P, const PartSoA src, const PView<doub
 }
 
 
-// Charge density with the second-order shape function, periodic in x and (one rank) in y, for the discrete Gauss law
+// Charge density with the second-order shape function, periodic in x, for the discrete Gauss law
 // div E = 4 pi rho (field.f90:159; the weights are those of particle.f90:97-105):
 //   rho[0][j][i] += q S2(x - i - 1/2) S2(y - j - 1/2),  rho[1] the same with |q| (scale of the residual)
+// Planes of (nyl + 2) rows: row lj + 1 holds local row lj; rows 0 and nyl + 1 collect what belongs to the ring neighbours
+// (folded by the host with one exchange per direction); with one rank the rows wrap onto the slab itself.
 __global__ void k_charge_density(const DevParams P, const PartSoA src, const int *__restrict__ cstart, double *rho) {
-  const size_t plane = (size_t)P.nx * P.nyl;
+  const size_t plane = (size_t)P.nx * (P.nyl + 2);
   for (int isp = 0; isp < P.nsp; isp++) {
     const int n = cstart[(size_t)isp * (P.ncell + 1) + P.ncell];
     const size_t so = (size_t)isp * P.cap;
@@ -800,14 +802,14 @@ __global__ void k_charge_density(const DevParams P, const PartSoA src, const int
 #pragma unroll
       for (int b = -1; b <= 1; b++) {
         int lj = jc + b - P.nys;
-        lj = (lj < 0) ? lj + P.nyl : (lj >= P.nyl ? lj - P.nyl : lj);
+        if (P.nsize == 1) lj = (lj < 0) ? lj + P.nyl : (lj >= P.nyl ? lj - P.nyl : lj);
 #pragma unroll
         for (int a = -1; a <= 1; a++) {
           int li = ic + a - P.nxgs;
           li = (li < 0) ? li + P.nx : (li >= P.nx ? li - P.nx : li);
           const double w = sx[a + 1] * sy[b + 1];
-          atomicAdd(&rho[(size_t)lj * P.nx + li], q * w);
-          atomicAdd(&rho[plane + (size_t)lj * P.nx + li], qa * w);
+          atomicAdd(&rho[(size_t)(lj + 1) * P.nx + li], q * w);
+          atomicAdd(&rho[plane + (size_t)(lj + 1) * P.nx + li], qa * w);
         }
       }
     }
@@ -819,7 +821,8 @@ __global__ void k_charge_density(const DevParams P, const PartSoA src, const int
 __global__ void k_gauss_residual(const DevParams P, const double *__restrict__ uf, const double *__restrict__ rho,
                                  unsigned long long *out) {
   const double PI4 = 4.0 * 3.14159265358979323846;
-  const size_t plane = (size_t)P.nx * P.nyl;
+  const size_t plane = (size_t)P.nx * (P.nyl + 2);
+  rho += P.nx;  // row lj + 1
   double res = 0.0, sc = 0.0;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < P.nx * P.nyl; t += gridDim.x * blockDim.x) {
     const int lj = t / P.nx, li = t - lj * P.nx;
@@ -838,11 +841,12 @@ __global__ void k_gauss_residual(const DevParams P, const double *__restrict__ u
     atomicMax(&out[1], (unsigned long long)__double_as_longlong(sc));
   }
 }
-void launch_gauss(const DevParams &P, const PartSoA &src, const int *cstart, const double *uf, double *rho,
-                  unsigned long long *out, cudaStream_t st) {
-  cudaMemsetAsync(rho, 0, (size_t)2 * P.nx * P.nyl * sizeof(double), st);
-  cudaMemsetAsync(out, 0, 2 * sizeof(unsigned long long), st);
+void launch_charge_density(const DevParams &P, const PartSoA &src, const int *cstart, double *rho, cudaStream_t st) {
+  cudaMemsetAsync(rho, 0, (size_t)2 * P.nx * (P.nyl + 2) * sizeof(double), st);
   k_charge_density<<<148 * 8, 256, 0, st>>>(P, src, cstart, rho);
+}
+void launch_gauss(const DevParams &P, const double *uf, const double *rho, unsigned long long *out, cudaStream_t st) {
+  cudaMemsetAsync(out, 0, 2 * sizeof(unsigned long long), st);
   k_gauss_residual<<<148 * 4, 256, 0, st>>>(P, uf, rho, out);
 }
 

@@ -99,6 +99,24 @@ struct wm_ctx {
   double u_inject = 0.0;
   bool u_inject_set = false;             // WM_BC_SHOCK: wm_set_u_inject / wm_boundary__injection has been called
   int cg_ite[3] = {0, 0, 0};
+  // persistent cooperative CG (k_cg_persist): one launch per solve, state on chip, barriers and sums in the kernel
+  int cg_mode = 1;                       // WM_CG=0 selects the host loop of small kernels (k_cg_pap / k_cg_update2)
+  bool cgp_ok = false;                   // the slab fits the on-chip solver on this device
+  bool cgp_ring = false;                 // nsize > 1: the neighbours' arrays are mapped (CUDA IPC) on every rank
+  int cgp_cbx = 0, cgp_cby = 0, nsm = 0;
+  int cgp_planned_nxa = -1;
+  bool cgp_plan_ok = false;
+  size_t cgp_smem = 0, cgp_smem_max = 0;
+  double *cgp_partial = nullptr;
+  unsigned *cgp_bar = nullptr;           // {barrier counter, abort word}
+  int *cgp_out = nullptr, *h_cgp_out = nullptr;
+  bool cg_pending = false;               // h_cgp_out of the last solve has not been looked at yet
+  unsigned long long cgp_seq = 0;
+  CgpShared *cgp_sh[CGP_MAXR] = {nullptr}, *cgp_sh_mine = nullptr;
+  void *cgp_ipc_open[CGP_MAXR + 2] = {nullptr};  // mappings to close at destroy
+  int cgp_nopen = 0;
+  double *cgp_r_up = nullptr, *cgp_r_down = nullptr;
+  int cgp_nyl_down = 0;
   // comm
   ncclComm_t comm = nullptr;
   int nup = 0, ndown = 0;
@@ -172,19 +190,30 @@ inline DevParams fieldp(const wm_ctx *c) {
   return P;
 }
 
+// result of the last persistent CG solve (copied to pinned memory behind the kernel): call after a synchronisation
+int cg_collect(wm_ctx *c) {
+  if (!c->cg_pending) return 0;
+  c->cg_pending = false;
+  for (int l = 0; l < 3; l++) c->cg_ite[l] = c->h_cgp_out[l];
+  if (c->h_cgp_out[3]) return fail("********** stop at cgm after ite_max ********** (field.f90:427-430)");
+  return 0;
+}
+
 int check_errors(wm_ctx *c, const char *where) {
   CU(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, c->st));
   CU(cudaStreamSynchronize(c->st));
   const unsigned e = *c->h_err;
-  if (!e) return 0;
+  if (!e) return cg_collect(c);
+  c->cg_pending = false;
   CU(cudaMemsetAsync(c->d_err, 0, sizeof(unsigned), c->st));
   std::string m = std::string(where) + ":";
   if (e & ERR_MOVED_TOO_FAR) m += " particle moved more than one cell (CFL violated or NaN);";
   if (e & ERR_CAPACITY) m += " memory over (particle slots exhausted, cf. boundary_periodic.f90:231-234);";
   if (e & ERR_SENDBUF) m += " migration buffer exhausted;";
   if (e & ERR_BAD_CELL) m += " particle outside the slab;";
-  if (e & ERR_TAG_RANK) m += " more than 2^24 particles from one tile into one cell;";
+  if (e & ERR_TAG_RANK) m += " more than 2^23 particles from one tile into one cell;";
   if (e & ERR_OVERFLOW) m += " in-place sort overflow list exhausted (raise WM_SLACK or wm_config.capacity);";
+  if (e & ERR_CG_TIMEOUT) m += " persistent CG kernel: a barrier timed out (a CTA or a ring neighbour never arrived);";
   return fail("%s", m.c_str());
 }
 
@@ -276,8 +305,69 @@ int allreduce_and_halo(wm_ctx *c, int which, int n, double *a) {
   return 0;
 }
 
+// cgm for l = 1..3 in one persistent cooperative kernel (cg_persist_kernel.cu)     field.f90:319-461
+int cg_solve_persist(wm_ctx *c) {
+  const DevParams P = fieldp(c);
+  CgpArgs a{};
+  a.cbx = c->cgp_cbx;
+  a.cby = c->cgp_cby;
+  a.df = c->f.df;
+  a.gkl = c->f.gkl;
+  a.rg = c->f.r;
+  a.phipl = c->f.phi;
+  a.bpl = c->f.ap;
+  a.partial = c->cgp_partial;
+  a.bar = c->cgp_bar;
+  a.abort = reinterpret_cast<int *>(c->cgp_bar + 1);
+  a.out = c->cgp_out;
+  a.err = c->d_err;
+  a.nrank = c->cfg.nrank;
+  a.nsize = P.nsize;
+  a.seq0 = c->cgp_seq;
+  c->cgp_seq += 1024;  // more than the 3 x (1 + 2 x 100) barriers a solve can take
+  for (int q = 0; q < CGP_MAXR; q++) a.sh[q] = c->cgp_sh[q];
+  a.r_up = c->cgp_r_up;
+  a.r_down = c->cgp_r_down;
+  a.nyl_down = c->cgp_nyl_down;
+  CU(cudaMemsetAsync(c->cgp_bar, 0, 2 * sizeof(unsigned), c->st));
+  CU(launch_cg_persist(P, a, c->cgp_smem, c->st));
+  CU(cudaMemcpyAsync(c->h_cgp_out, c->cgp_out, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  c->cg_pending = true;
+  c->launches++;
+  return 0;
+}
+
+// Block decomposition for the active x range of this call (only the shock module moves nxe).  With more than one rank the
+// plan must also hold for a slab with one more row (mpi_set.f90:37-41 spreads the remainder), so that all ranks decide alike.
+bool cg_persist_usable(wm_ctx *c) {
+  if (!c->cg_mode || !c->cgp_ok) return false;
+  if (c->P.nsize > 1 && !c->cgp_ring) return false;
+  if (c->cgp_planned_nxa != c->nxa) {
+    int cbx, cby;
+    size_t sm;
+    const int nyl = c->P.nyl;
+    bool ok = cgp_plan(c->nxa, nyl, c->nsm, c->cgp_smem_max, &cbx, &cby, &sm);
+    if (ok && c->P.nsize > 1) {  // slabs hold ny / nsize rows, the first mod(ny, nsize) ranks one more
+      const int ny = c->cfg.nyge - c->cfg.nygs + 1, base = ny / c->P.nsize;
+      int bx2, by2;
+      size_t sm2;
+      ok = cgp_plan(c->nxa, base, c->nsm, c->cgp_smem_max, &bx2, &by2, &sm2) &&
+           cgp_plan(c->nxa, base + (ny % c->P.nsize ? 1 : 0), c->nsm, c->cgp_smem_max, &bx2, &by2, &sm2);
+    }
+    c->cgp_planned_nxa = c->nxa;
+    c->cgp_plan_ok = ok;
+    if (ok) {
+      c->cgp_cbx = cbx;
+      c->cgp_cby = cby;
+      c->cgp_smem = sm;
+    }
+  }
+  return c->cgp_plan_ok;
+}
+
 // cgm for l = 1..3 together                                                field.f90:319-461
 int cg_solve(wm_ctx *c) {
+  if (cg_persist_usable(c)) return cg_solve_persist(c);
   const DevParams P = fieldp(c);
   launch_cg_init(P, c->f, c->st);
   WM(allreduce_ctl(c, 0, 3));
@@ -512,6 +602,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   if (const char *v = getenv("WM_RIMPLACE")) c->rimplace = atoi(v) != 0;
   if (const char *v = getenv("WM_CG3")) c->cg3 = atoi(v) != 0;
   if (const char *v = getenv("WM_OVERLAP")) c->overlap = atoi(v) != 0;
+  if (const char *v = getenv("WM_CG")) c->cg_mode = atoi(v);
   if (g->flags & WM_FLAG_EXACT_PUSH) c->inplace = false;  // the exact path keeps the reference's two-pass structure
   if (g->device >= 0) {
     c->dev = g->device;
@@ -596,6 +687,21 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   CU(cudaMemset(c->f.cgstate, 0, cgctl_bytes()));
   for (double *a : {c->f.uf, c->f.df, c->f.tmpf}) CU(cudaMemset(a, 0, ng * 6 * sizeof(double)));  // df=0: field.f90:109-111
   for (double *a : {c->f.uj, c->f.gkl, c->f.phi, c->f.p, c->f.p2, c->f.r, c->f.ap}) CU(cudaMemset(a, 0, ng * 3 * sizeof(double)));
+  {
+    // persistent CG: one CTA per SM, the block's p tile in (opt-in) shared memory
+    c->nsm = prop.multiProcessorCount;
+    c->cgp_smem_max = prop.sharedMemPerBlockOptin > 4096 ? prop.sharedMemPerBlockOptin - 2048 : 0;  // s_red, s_tot are static
+    int cbx, cby;
+    size_t sm;
+    c->cgp_ok = prop.cooperativeLaunch && cgp_plan(nx, nyl, c->nsm, c->cgp_smem_max, &cbx, &cby, &sm) &&
+                cgp_prepare(c->cgp_smem_max) == cudaSuccess;
+    (void)cudaGetLastError();
+    CU(cudaMalloc(&c->cgp_partial, (size_t)2 * c->nsm * 4 * sizeof(double)));
+    CU(cudaMalloc(&c->cgp_bar, 2 * sizeof(unsigned)));
+    CU(cudaMalloc(&c->cgp_out, 8 * sizeof(int)));
+    CU(cudaMemset(c->cgp_out, 0, 8 * sizeof(int)));
+    CU(cudaMallocHost(&c->h_cgp_out, 8 * sizeof(int)));
+  }
   CU(cudaMalloc(&c->rowtmp, (size_t)P.pitch * 2 * 6 * sizeof(double)));
   CU(cudaMalloc(&c->mom, (size_t)7 * (nx + 2) * (nyl + 2) * P.nsp * sizeof(double)));
   CU(cudaMalloc(&c->gcnt, (size_t)P.nsp * P.ncell * sizeof(int)));
@@ -639,6 +745,15 @@ int wm_destroy(wm_ctx *c) {
                   (void *)c->f.red, (void *)c->f.cgstate, (void *)c->rowtmp, (void *)c->mom, (void *)c->partial,
                   (void *)c->d_err})
     cudaFree(p);
+  for (int k = 0; k < c->cgp_nopen; k++) cudaIpcCloseMemHandle(c->cgp_ipc_open[k]);
+  cudaFree(c->cgp_sh_mine);
+  cudaFree(c->cgp_partial);
+  cudaFree(c->cgp_bar);
+  cudaFree(c->cgp_out);
+  cudaFreeHost(c->h_cgp_out);
+  for (auto &e : c->ev_b) cudaEventDestroy(e);
+  cudaEventDestroy(c->ev_fork);
+  cudaEventDestroy(c->ev_join);
   cudaFree(c->cnt_tail);
   cudaFree(c->tight);
   cudaFree(c->ovf);
@@ -659,6 +774,66 @@ int wm_destroy(wm_ctx *c) {
   return 0;
 }
 
+// Peer memory for the kernels that exchange data themselves (k_cg_persist): every rank exports its CgpShared block and its
+// CG residual array with CUDA IPC, the handles travel once through NCCL, and every rank maps what it needs.  All ranks then
+// agree (all-reduce) on whether the mapped path is usable; if not, the ring falls back to NCCL calls per CG iteration.
+static int ring_map_peers(wm_ctx *c) {
+  const int N = c->P.nsize, me = c->cfg.nrank;
+  struct Info {
+    cudaIpcMemHandle_t sh, r;
+    int nyl, ok, pad[2];
+  };
+  static_assert(sizeof(Info) % 8 == 0, "Info is exchanged as 8-byte words");
+  int ok = (c->cg_mode && c->cgp_ok && N <= CGP_MAXR) ? 1 : 0;
+  Info mine{};
+  CgpShared *sh = nullptr;
+  CU(cudaMalloc(&sh, 2u << 20));  // its own 2 MiB block: the IPC mapping exposes nothing else
+  CU(cudaMemset(sh, 0, 2u << 20));
+  c->cgp_sh_mine = sh;
+  if (me < CGP_MAXR) c->cgp_sh[me] = sh;
+  if (ok && (cudaIpcGetMemHandle(&mine.sh, sh) != cudaSuccess || cudaIpcGetMemHandle(&mine.r, c->f.r) != cudaSuccess)) ok = 0;
+  (void)cudaGetLastError();
+  mine.nyl = c->P.nyl;
+  mine.ok = ok;
+  Info *d_all = nullptr;
+  std::vector<Info> all(N);
+  CU(cudaMalloc(&d_all, sizeof(Info) * N));
+  CU(cudaMemcpy(d_all + me, &mine, sizeof(Info), cudaMemcpyHostToDevice));
+  NC(ncclAllGather(d_all + me, d_all, sizeof(Info) / 8, ncclUint64, c->comm, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  CU(cudaMemcpy(all.data(), d_all, sizeof(Info) * N, cudaMemcpyDeviceToHost));
+  for (int q = 0; q < N; q++) ok = ok && all[q].ok;
+  if (ok) {
+    auto open = [&](const cudaIpcMemHandle_t &h, void **out) {
+      if (cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+      }
+      c->cgp_ipc_open[c->cgp_nopen++] = *out;
+      return true;
+    };
+    for (int q = 0; q < N && ok; q++)
+      if (q != me) ok = open(all[q].sh, reinterpret_cast<void **>(&c->cgp_sh[q]));
+    if (ok) ok = open(all[c->nup].r, reinterpret_cast<void **>(&c->cgp_r_up));
+    if (ok) {
+      if (c->ndown == c->nup)
+        c->cgp_r_down = c->cgp_r_up;
+      else
+        ok = open(all[c->ndown].r, reinterpret_cast<void **>(&c->cgp_r_down));
+    }
+    c->cgp_nyl_down = all[c->ndown].nyl;
+  }
+  // everybody or nobody
+  int *d_ok = reinterpret_cast<int *>(d_all);
+  CU(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  NC(ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c->comm, c->st));
+  CU(cudaStreamSynchronize(c->st));
+  CU(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+  CU(cudaFree(d_all));
+  c->cgp_ring = ok != 0;
+  return 0;
+}
+
 int wm_comm_unique_id(void *id128) {
   static_assert(sizeof(ncclUniqueId) == WM_UNIQUE_ID_BYTES, "ncclUniqueId size");
   ncclUniqueId id;
@@ -674,8 +849,7 @@ int wm_comm_init(wm_ctx *c, const void *id128) {
   ncclUniqueId id;
   memcpy(&id, id128, sizeof id);
   NC(ncclCommInitRank(&c->comm, c->P.nsize, id, c->cfg.nrank));
-  // migration buffers: a generous multiple of one row's worth of particles per direction and species
-  return 0;
+  return ring_map_peers(c);
 }
 
 static int ensure_migration_buffers(wm_ctx *c, long long n_per_species) {
@@ -1231,7 +1405,29 @@ int wm_host_sort__bucket(wm_ctx *c, double *gp_out, const double *up_in, int32_t
 // ---------------------------------------------------------------- diagnostics
 int wm_cg_iters(wm_ctx *c, int32_t out[3]) {
   if (!c) return fail("wm_cg_iters: null context");
+  if (c->cg_pending) {
+    WM(set_device(c));
+    CU(cudaStreamSynchronize(c->st));
+    WM(cg_collect(c));
+  }
   for (int l = 0; l < 3; l++) out[l] = c->cg_ite[l];
+  return 0;
+}
+
+int wm_cg_path(wm_ctx *c, int32_t *path) {
+  if (!c || !path) return fail("wm_cg_path: null argument");
+  *path = cg_persist_usable(c) ? (c->P.nsize > 1 ? 2 : 1) : 0;
+  return 0;
+}
+
+int wm_cg_plan(int32_t nx, int32_t nyl, int32_t nsm, int64_t smem_max, int32_t out[3]) {
+  if (!out) return fail("wm_cg_plan: null argument");
+  int cbx = 0, cby = 0;
+  size_t sm = 0;
+  if (!cgp_plan(nx, nyl, nsm, (size_t)smem_max, &cbx, &cby, &sm)) return fail("wm_cg_plan: the slab does not fit the on-chip solver");
+  out[0] = cbx;
+  out[1] = cby;
+  out[2] = (int32_t)sm;
   return 0;
 }
 
@@ -1349,22 +1545,44 @@ int wm_moments(wm_ctx *c, double *mom) {
   return 0;
 }
 
-// Discrete Gauss law of the current state: out[0] = max over the cells of |div E - 4 pi rho| with
+// Discrete Gauss law of the current state: out[0] = max over this rank's cells of |div E - 4 pi rho| with
 // rho = sum_p q S2 S2 (second-order shape, the deposit's weights), out[1] = max 4 pi sum_p |q| S2 S2 (its scale).
-// Charge conservation of the Esirkepov deposit keeps out[0] at roundoff of out[1] for all times.  Periodic boundaries,
-// one rank (the ghost folds of rho are not implemented for the ring).
+// Charge conservation of the Esirkepov deposit keeps out[0] at roundoff of out[1] for all times.  Periodic boundaries;
+// on a ring every rank calls it (the charge that particles of the edge rows deposit into the neighbour's rows is folded
+// with one exchange per direction, like bc__curre folds the current).
 int wm_gauss_residual(wm_ctx *c, double out[2]) {
   if (!out) return fail("wm_gauss_residual: null argument");
   WM(need_state(c, ST_SORTED, "wm_gauss_residual"));
-  if (c->P.bc != WM_BC_PERIODIC || c->P.nsize != 1) return fail("wm_gauss_residual: periodic boundaries on one rank only");
+  if (c->P.bc != WM_BC_PERIODIC) return fail("wm_gauss_residual: periodic boundaries only");
+  if (c->P.nsize > 1 && !c->comm) return fail("nsize > 1 but wm_comm_init has not been called");
   WM(set_device(c));
   const DevParams &P = c->P;
   WM(scan_tight(c));  // makes sure the per-species slot totals in cstart are current
   double *rho = nullptr;
   unsigned long long *d_out = nullptr;
-  CU(cudaMalloc(&rho, (size_t)2 * P.nx * P.nyl * sizeof(double)));
+  const size_t plane = (size_t)P.nx * (P.nyl + 2);
+  CU(cudaMalloc(&rho, 2 * plane * sizeof(double)));
   CU(cudaMalloc(&d_out, 2 * sizeof(unsigned long long)));
-  launch_gauss(P, c->soa[c->cur], c->cstart[c->cur], c->f.uf, rho, d_out, c->st);
+  launch_charge_density(P, c->soa[c->cur], c->cstart[c->cur], rho, c->st);
+  if (P.nsize > 1) {
+    for (int k = 0; k < 2; k++) {
+      double *pl = rho + k * plane;
+      // my row below the slab -> ndown ; nup's lands in rowtmp and is added to my last row
+      NC(ncclGroupStart());
+      NC(ncclSend(pl, P.nx, ncclDouble, c->ndown, c->comm, c->st));
+      NC(ncclRecv(c->rowtmp, P.nx, ncclDouble, c->nup, c->comm, c->st));
+      NC(ncclGroupEnd());
+      launch_add_rows(pl + (size_t)P.nyl * P.nx, c->rowtmp, P.nx, c->st);
+      // my row above the slab -> nup ; ndown's is added to my first row
+      NC(ncclGroupStart());
+      NC(ncclSend(pl + (size_t)(P.nyl + 1) * P.nx, P.nx, ncclDouble, c->nup, c->comm, c->st));
+      NC(ncclRecv(c->rowtmp, P.nx, ncclDouble, c->ndown, c->comm, c->st));
+      NC(ncclGroupEnd());
+      launch_add_rows(pl + (size_t)P.nx, c->rowtmp, P.nx, c->st);
+    }
+    c->launches += 4;
+  }
+  launch_gauss(P, c->f.uf, rho, d_out, c->st);
   c->launches += 2;
   unsigned long long h[2];
   CU(cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, c->st));

@@ -83,7 +83,8 @@ enum : unsigned {
   ERR_SENDBUF = 4u,         // migration buffer exhausted
   ERR_BAD_CELL = 8u,        // uploaded particle outside the slab
   ERR_TAG_RANK = 16u,       // more than 2^23 particles from one tile into one cell
-  ERR_OVERFLOW = 32u        // in-place sort: overflow list exhausted
+  ERR_OVERFLOW = 32u,       // in-place sort: overflow list exhausted
+  ERR_CG_TIMEOUT = 64u      // persistent CG kernel: a CTA or a ring neighbour never arrived at a barrier
 };
 
 // capacity of a cell segment that holds n particles now: slack ~ sl standard deviations of the
