@@ -150,9 +150,9 @@ int wm_cg_iters(wm_ctx *ctx, int32_t out[3]);  /* CG iterations of the last solv
  * with the ring exchange and the all-reduce done in the kernel over CUDA-IPC mapped peer memory.  WM_CG=0 forces 0. */
 int wm_cg_path(wm_ctx *ctx, int32_t *path);
 /* Block decomposition the persistent CG kernel uses for an nx x nyl slab on a device with nsm SMs and smem_max bytes of
- * shared memory per CTA: out = {blocks in x, blocks in y, shared-memory bytes}; error if the slab does not fit (pure host
- * logic, no device needed). */
-int wm_cg_plan(int32_t nx, int32_t nyl, int32_t nsm, int64_t smem_max, int32_t out[3]);
+ * shared memory per CTA: out = {blocks in x, blocks in y, shared-memory bytes, cells per thread}; error if the slab does not
+ * fit (pure host logic, no device needed). */
+int wm_cg_plan(int32_t nx, int32_t nyl, int32_t nsm, int64_t smem_max, int32_t out[4]);
 /* energy_history (proj/weibel/app.f90:479-545), this rank's share:
  * out[0..nsp-1] kinetic, out[nsp] = sum E^2/8pi, out[nsp+1] = sum B^2/8pi */
 int wm_energy(wm_ctx *ctx, double *out);

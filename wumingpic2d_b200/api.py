@@ -126,8 +126,9 @@ def load_library():
 
 
 def cg_plan(nx, nyl, nsm=148, smem_max=227 * 1024 - 2048):
-    """Block decomposition of the persistent CG kernel for an nx x nyl slab: (blocks in x, blocks in y, smem bytes)."""
-    out = (C.c_int32 * 3)()
+    """Block decomposition of the persistent CG kernel for an nx x nyl slab: (blocks in x, blocks in y, smem bytes, cells
+    per thread)."""
+    out = (C.c_int32 * 4)()
     lib = load_library()
     if lib.wm_cg_plan(nx, nyl, nsm, smem_max, out):
         raise WmError(lib.wm_last_error().decode())

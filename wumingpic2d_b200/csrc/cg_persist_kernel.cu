@@ -57,6 +57,16 @@ __device__ __forceinline__ int ld_volatile(const int *p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+// WM_CGTRACE=1: thread 0 of every CTA records the global timer at the points of barrier number a.trace_seq .. +3
+__device__ __forceinline__ void trace(const CgpArgs &a, int cta, unsigned seq, int ev) {
+  if (a.trace && seq >= a.trace_seq && seq < a.trace_seq + 4) a.trace[((size_t)cta * 4 + (seq - a.trace_seq)) * 4 + ev] = gtime();
+}
+
 constexpr long long SPIN_LIMIT = 6000000000LL;  // ~3 s of SM clocks: a peer that never shows up ends the solve with an error
 
 struct Ctx {
@@ -81,11 +91,13 @@ __device__ __forceinline__ void spin_until(const CgpArgs &a, F pred) {
 
 // Sum of NV values over all cells of all ranks.  In: every thread's private sums.  Out: the global sums, bit-identical in
 // every thread of every CTA of every rank.  Also a grid-wide (and ring-wide) barrier with release / acquire semantics for
-// the stores made before it (perimeter r values, peers' ghost rows).
-template <int NV>
-__device__ void allsum(Ctx &c, double (&v)[NV], double *s_red, double *s_tot) {
+// the stores made before it (perimeter r values, peers' ghost rows).  `between` runs after this CTA has arrived and before
+// it waits: work that nothing on the critical path depends on (the phi update).
+constexpr int GMAX = 160;  // CTAs at most (one per SM)
+template <int NV, typename F>
+__device__ __forceinline__ void allsum(Ctx &c, double (&v)[NV], double *s_red, F between) {
   const CgpArgs &a = *c.a;
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, nw = blockDim.x >> 5;
 #pragma unroll
   for (int k = 0; k < NV; k++) {
 #pragma unroll
@@ -93,48 +105,61 @@ __device__ void allsum(Ctx &c, double (&v)[NV], double *s_red, double *s_tot) {
   }
   if (lane == 0)
 #pragma unroll
-    for (int k = 0; k < NV; k++) s_red[wid * 4 + k] = v[k];
+    for (int k = 0; k < NV; k++) s_red[wid * 2 + k] = v[k];
   if (a.nsize > 1) __threadfence_system();  // my stores into the neighbours' ghost rows
   __syncthreads();
   const unsigned seq = ++c.nsync;
-  double *part = a.partial + (size_t)(seq & 1u) * c.G * 4;
+  double2 *part = reinterpret_cast<double2 *>(a.partial) + (size_t)(seq & 1u) * GMAX;
   if (wid == 0) {
-    double w[NV];
+    double w[2] = {0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < NV; k++) {
-      w[k] = (lane < CGP_T / 32) ? s_red[lane * 4 + k] : 0.0;
+      w[k] = (lane < nw) ? s_red[lane * 2 + k] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) w[k] += __shfl_xor_sync(0xffffffffu, w[k], o);
     }
     if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < NV; k++) part[c.cta * 4 + k] = w[k];
+      trace(a, c.cta, seq, 0);
+      part[c.cta] = make_double2(w[0], w[1]);
       __threadfence();
       atomicAdd(a.bar, 1u);
+      trace(a, c.cta, seq, 1);
     }
   }
+  between();
+  if (t == 0) trace(a, c.cta, seq, 2);
   const unsigned target = seq * (unsigned)c.G;
+  // the CTAs' partial sums, added in a fixed order by every warp on its own (no broadcast through shared memory)
+  auto sum_partials = [&](double (&w)[2]) {
+    double2 q[GMAX / 32];
+#pragma unroll
+    for (int j = 0; j < GMAX / 32; j++) {
+      const int b = lane + 32 * j;
+      q[j] = (b < c.G) ? __ldcg(&part[b]) : make_double2(0.0, 0.0);
+    }
+    w[0] = q[0].x;
+    w[1] = q[0].y;
+#pragma unroll
+    for (int j = 1; j < GMAX / 32; j++) {
+      w[0] += q[j].x;
+      w[1] += q[j].y;
+    }
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) w[k] += __shfl_xor_sync(0xffffffffu, w[k], o);
+    }
+  };
   if (a.nsize == 1) {
-    if (t == 0) spin_until(a, [&] { return ld_acquire_gpu(a.bar) >= target; });
-    __syncthreads();
-    if (wid == 0) {
-      double w[NV];
-#pragma unroll
-      for (int k = 0; k < NV; k++) w[k] = 0.0;
-      for (int b = lane; b < c.G; b += 32) {
-#pragma unroll
-        for (int k = 0; k < NV; k++) w[k] += __ldcg(&part[b * 4 + k]);
-      }
-#pragma unroll
-      for (int k = 0; k < NV; k++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) w[k] += __shfl_xor_sync(0xffffffffu, w[k], o);
-      }
-      if (lane == 0)
-#pragma unroll
-        for (int k = 0; k < NV; k++) s_tot[k] = w[k];
+    if (t == 0) {
+      spin_until(a, [&] { return ld_acquire_gpu(a.bar) >= target; });
+      trace(a, c.cta, seq, 3);
     }
     __syncthreads();
+    double w[2];
+    sum_partials(w);
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = w[k];
   } else {
     // ring: CTA 0 adds the slab's partials and publishes them to every rank (itself included); everybody waits for the
     // flags of all ranks in its own memory
@@ -144,18 +169,8 @@ __device__ void allsum(Ctx &c, double (&v)[NV], double *s_red, double *s_tot) {
       if (t == 0) spin_until(a, [&] { return ld_acquire_gpu(a.bar) >= target; });
       __syncthreads();
       if (wid == 0) {
-        double w[NV];
-#pragma unroll
-        for (int k = 0; k < NV; k++) w[k] = 0.0;
-        for (int b = lane; b < c.G; b += 32) {
-#pragma unroll
-          for (int k = 0; k < NV; k++) w[k] += __ldcg(&part[b * 4 + k]);
-        }
-#pragma unroll
-        for (int k = 0; k < NV; k++) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) w[k] += __shfl_xor_sync(0xffffffffu, w[k], o);
-        }
+        double w[2];
+        sum_partials(w);
         if (lane < a.nsize) {
           CgpShared *dst = a.sh[lane];
 #pragma unroll
@@ -168,30 +183,36 @@ __device__ void allsum(Ctx &c, double (&v)[NV], double *s_red, double *s_tot) {
     CgpShared *me = a.sh[a.nrank];
     if (t < a.nsize) spin_until(a, [&] { return ld_acquire_sys(&me->flag[t]) >= gseq; });
     __syncthreads();
-    if (t == 0) {
-      double w[NV];
+    double w[2] = {0.0, 0.0};
+    for (int q = 0; q < a.nsize; q++) {
 #pragma unroll
-      for (int k = 0; k < NV; k++) w[k] = 0.0;
-      for (int q = 0; q < a.nsize; q++) {
-#pragma unroll
-        for (int k = 0; k < NV; k++) w[k] += __ldcg(&me->xsum[slot][q][k]);
-      }
-#pragma unroll
-      for (int k = 0; k < NV; k++) s_tot[k] = w[k];
+      for (int k = 0; k < NV; k++) w[k] += __ldcg(&me->xsum[slot][q][k]);
     }
-    __syncthreads();
-  }
 #pragma unroll
-  for (int k = 0; k < NV; k++) v[k] = s_tot[k];
-  __syncthreads();  // s_red / s_tot are reused by the next call
+    for (int k = 0; k < NV; k++) v[k] = w[k];
+  }
+}
+
+// element k (run-time) of a register array, by a chain of selects (no local-memory indexing)
+template <int K>
+__device__ __forceinline__ double r_at(const double (&r)[K], int k) {
+  double v = r[0];
+#pragma unroll
+  for (int j = 1; j < K; j++) v = (k == j) ? r[j] : v;
+  return v;
 }
 
 }  // namespace
 
+// Thread layout: a block of bw x bh cells, bw * ng <= 1024 threads; thread (cx, g) owns the vertical run of rl = ceil(bh / ng)
+// cells (cx, g * rl ...) of one column, so the stencil slides down the column with three shared-memory loads per cell (the
+// shared-memory pipe bounds the compute phases: 8-byte loads are two wavefronts per warp).  The halo ring is served by the
+// threads next to it: the first / last thread of a column takes the cell below / above, the threads of the first / last column
+// the cells left / right of their rows.
+template <int K>
 __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__ DevParams P, const __grid_constant__ CgpArgs a) {
   extern __shared__ __align__(16) double T[];  // p (phi during the set-up) of the block with its halo ring: (bw+2) x (bh+2)
-  __shared__ double s_red[32 * 4];
-  __shared__ double s_tot[4];
+  __shared__ double s_red[32 * 2];
 
   const int t = threadIdx.x;
   Ctx c;
@@ -202,178 +223,195 @@ __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__
   const int bx = c.cta % a.cbx, by = c.cta / a.cbx;
   const int x0 = (int)((long long)bx * P.nx / a.cbx), x1 = (int)((long long)(bx + 1) * P.nx / a.cbx);
   const int y0 = (int)((long long)by * P.nyl / a.cby), y1 = (int)((long long)(by + 1) * P.nyl / a.cby);
-  const int bw = x1 - x0, bh = y1 - y0, tp = bw + 2, ncl = bw * bh;
-  const size_t pbase = (size_t)y0 * P.nx + (size_t)x0 * bh;  // dense packing of the blocks: row of blocks, then block
+  const int bw = x1 - x0, bh = y1 - y0, tp = bw + 2;
+  const int rl = a.rl;                        // rows per thread
+  const int ngr = (bh + rl - 1) / rl;         // row groups in this block
+  const int nthr = bw * ngr;                  // threads that own cells
+  const bool own = t < nthr;
+  const int cx = own ? t % bw : 0, cyb = own ? (t / bw) * rl : 0;
+  const int nrow = own ? min(rl, bh - cyb) : 0;              // cells of this thread: (cx, cyb .. cyb + nrow - 1)
+  const int i0 = (cyb + 1) * tp + cx + 1;                     // tile index of its first cell
   const size_t plane = (size_t)P.nx * P.nyl;
-  const int dq = CGP_T / bw, dr = CGP_T - dq * bw;           // (cx, cy) of cell e + CGP_T from those of cell e
-  const int cx0 = t % bw, cy0 = t / bw;
+  const size_t pbase = (size_t)y0 * P.nx + (size_t)x0 * bh + t;  // dense packing: cell k of thread t at pbase + k * nthr
   const bool wall = P.bc != WM_BC_PERIODIC;
   const double f4 = P.f4;
-  const int nhalo = 2 * (bw + bh);
+  const int li_own = x0 + cx;
+  // ---- the halo cells this thread serves, as offsets into the AoS3 array rg (component 0) / tile indices
+  const bool has_bot = own && cyb == 0, has_top = own && cyb + nrow == bh;
+  const bool first_col = own && cx == 0, last_col = own && cx == bw - 1;
+  int ljb = y0 - 1, ljt = y0 + bh;  // rows below / above the block; on one rank the ring neighbour is this slab itself
+  if (P.nsize == 1) {
+    if (ljb < 0) ljb += P.nyl;
+    if (ljt >= P.nyl) ljt -= P.nyl;
+  }
+  const size_t g_bot = pidx(P, li_own, ljb) * 3, g_top = pidx(P, li_own, ljt) * 3;
+  const int i_bot = i0 - tp, i_top = i0 + nrow * tp;
+  // left / right neighbours of the block's first / last column: the wrapped column, or a wall ghost (kind 1 / 2)
+  int lil = x0 - 1, lir = x0 + bw, kindl = 0, kindr = 0;
+  if (lil < 0) { if (wall) kindl = 1; else lil += P.nx; }
+  if (lir >= P.nx) { if (wall) kindr = 2; else lir -= P.nx; }
+  const bool slab_bot = P.nsize > 1 && y0 == 0, slab_top = P.nsize > 1 && y0 + bh == P.nyl;  // rows the ring neighbours need
 
-  // halo position h -> tile index, local cell (li, lj) it mirrors, kind: 0 = a cell of this slab or of a ring neighbour
-  // (read from the global array), 1 = left wall ghost, 2 = right wall ghost
-  auto halo_pos = [&](int h, int &ti, int &li, int &lj, int &kind) {
-    int hx, hy;
-    if (h < bw) { hx = h; hy = -1; }
-    else if (h < 2 * bw) { hx = h - bw; hy = bh; }
-    else if (h < 2 * bw + bh) { hx = -1; hy = h - 2 * bw; }
-    else { hx = bw; hy = h - 2 * bw - bh; }
-    ti = (hy + 1) * tp + hx + 1;
-    li = x0 + hx;
-    lj = y0 + hy;
-    kind = 0;
-    if (li < 0) {
-      if (wall) kind = 1; else li += P.nx;
-    } else if (li >= P.nx) {
-      if (wall) kind = 2; else li -= P.nx;
-    }
-    if (P.nsize == 1) {  // the ring neighbour is this slab itself
-      if (lj < 0) lj += P.nyl; else if (lj >= P.nyl) lj -= P.nyl;
-    }
+  // r of the perimeter cells goes to the global array (and to the ring neighbours' ghost rows)
+  auto publish_one = [&](int l, int cy, double rr) {
+    const int lj = y0 + cy;
+    a.rg[pidx(P, li_own, lj) * 3 + l] = rr;
+    if (slab_bot && cy == 0) a.r_down[pidx(P, li_own, a.nyl_down) * 3 + l] = rr;
+    if (slab_top && cy == bh - 1) a.r_up[pidx(P, li_own, -1) * 3 + l] = rr;
+  };
+  // the halo ring from get(global offset of component 0 of the cell) and mix(value, tile index): rows first, then columns
+  auto fill_halo = [&](int l, auto get, auto mix) {
+    double hb = 0.0, ht = 0.0;
+    if (has_bot) hb = get(g_bot + l);
+    if (has_top) ht = get(g_top + l);
+    if (has_bot) T[i_bot] = mix(hb, i_bot);
+    if (has_top) T[i_top] = mix(ht, i_top);
+    if (first_col && kindl == 0)
+      for (int k = 0; k < nrow; k++) T[i0 + k * tp - 1] = mix(get(pidx(P, lil, y0 + cyb + k) * 3 + l), i0 + k * tp - 1);
+    if (last_col && kindr == 0)
+      for (int k = 0; k < nrow; k++) T[i0 + k * tp + 1] = mix(get(pidx(P, lir, y0 + cyb + k) * 3 + l), i0 + k * tp + 1);
+  };
+  // wall ghosts from the block's own cells (after a barrier: the neighbour thread's column is read)   set_boundary_phi
+  auto wall_halo = [&](int l) {
+    if (!wall) return;
+    if (first_col && kindl == 1)
+      for (int k = 0; k < nrow; k++) T[i0 + k * tp - 1] = (l == 0) ? -T[i0 + k * tp] : T[i0 + k * tp + 1];
+    if (last_col && kindr == 2)
+      for (int k = 0; k < nrow; k++) T[i0 + k * tp + 1] = 0.0;
+    __syncthreads();
   };
 
   // ---- set-up: phi <- df(l), b <- f5 gkl(l) for the three components into the per-thread planes   field.f90:349-360
 #pragma unroll
-  for (int k = 0, cx = cx0, cy = cy0; k < CGP_K; k++) {
-    const int e = t + k * CGP_T;
-    if (e < ncl) {
-      const size_t o = pidx(P, x0 + cx, y0 + cy);
+  for (int k = 0; k < K; k++) {
+    if (k < nrow) {
+      const size_t o = pidx(P, li_own, y0 + cyb + k);
 #pragma unroll
       for (int l = 0; l < 3; l++) {
-        a.phipl[l * plane + pbase + e] = a.df[o * 6 + l];
-        a.bpl[l * plane + pbase + e] = P.f5 * a.gkl[o * 3 + l];
+        a.phipl[l * plane + pbase + (size_t)k * nthr] = a.df[o * 6 + l];
+        a.bpl[l * plane + pbase + (size_t)k * nthr] = P.f5 * a.gkl[o * 3 + l];
       }
     }
-    cx += dr; cy += dq;
-    if (cx >= bw) { cx -= bw; cy++; }
   }
 
   int stop = 0;
 #pragma unroll 1
   for (int l = 0; l < 3; l++) {
-    double *const phi = a.phipl + l * plane + pbase;
-    const double *const bb = a.bpl + l * plane + pbase;
-    double r[CGP_K];
+    double *__restrict__ const phi = a.phipl + l * plane + pbase;
+    const double *__restrict__ const bb = a.bpl + l * plane + pbase;
+    double r[K];
     // ---- T <- phi with the halo ring (set_boundary_phi(phi), field.f90:367): neighbours' values are df(l) itself, rows of
     //      the ring neighbours are df's ghost rows (kept current by bc__dfield, field.f90:151,173)
     __syncthreads();
 #pragma unroll
-    for (int k = 0, cx = cx0, cy = cy0; k < CGP_K; k++) {
-      const int e = t + k * CGP_T;
-      if (e < ncl) T[e + 2 * cy + tp + 1] = phi[e];
-      cx += dr; cy += dq;
-      if (cx >= bw) { cx -= bw; cy++; }
-    }
+    for (int k = 0; k < K; k++)
+      if (k < nrow) T[i0 + k * tp] = phi[(size_t)k * nthr];
+    fill_halo(l, [&](size_t g) { return a.df[(g - l) * 2 + l]; }, [](double v, int) { return v; });
     __syncthreads();
-    for (int h = t; h < nhalo; h += CGP_T) {
-      int ti, li, lj, kind;
-      halo_pos(h, ti, li, lj, kind);
-      double v;
-      if (kind == 0) v = a.df[pidx(P, li, lj) * 6 + l];
-      else if (kind == 1) v = (l == 0) ? -T[ti + 1] : T[ti + 2];
-      else v = 0.0;
-      T[ti] = v;
-    }
-    __syncthreads();
+    wall_halo(l);
     // ---- r <- b + N4 phi - f4 phi, sum b^2, sum r^2                                               field.f90:362-383
     double s[2] = {0.0, 0.0};
+    {
+      double up = T[i0 - tp], cc = T[i0];
 #pragma unroll
-    for (int k = 0, cx = cx0, cy = cy0; k < CGP_K; k++) {
-      const int e = t + k * CGP_T;
-      r[k] = 0.0;
-      if (e < ncl) {
-        const int i = e + 2 * cy + tp + 1;
-        const double b = bb[e];
-        const double rr = b + T[i - tp] + T[i - 1] - f4 * T[i] + T[i + 1] + T[i + tp];
-        r[k] = rr;
-        s[0] = s[0] + b * b;
-        s[1] = s[1] + rr * rr;
-        if (cx == 0 || cx == bw - 1 || cy == 0 || cy == bh - 1) {
-          const int li = x0 + cx, lj = y0 + cy;
-          a.rg[pidx(P, li, lj) * 3 + l] = rr;
-          if (P.nsize > 1) {
-            if (lj == 0) a.r_down[pidx(P, li, a.nyl_down) * 3 + l] = rr;
-            if (lj == P.nyl - 1) a.r_up[pidx(P, li, -1) * 3 + l] = rr;
-          }
+      for (int k = 0; k < K; k++) {
+        r[k] = 0.0;
+        if (k < nrow) {
+          const int i = i0 + k * tp;
+          const double dn = T[i + tp];
+          const double b = bb[(size_t)k * nthr];
+          const double rr = b + up + T[i - 1] - f4 * cc + T[i + 1] + dn;
+          r[k] = rr;
+          s[0] = s[0] + b * b;
+          s[1] = s[1] + rr * rr;
+          up = cc;
+          cc = dn;
         }
       }
-      cx += dr; cy += dq;
-      if (cx >= bw) { cx -= bw; cy++; }
     }
-    allsum<2>(c, s, s_red, s_tot);
+    auto publish = [&]() {
+      if (first_col || last_col) {
+        for (int k = 0; k < nrow; k++) publish_one(l, cyb + k, r_at(r, k));
+      } else {
+        if (has_bot) publish_one(l, cyb, r[0]);
+        if (has_top) publish_one(l, cyb + nrow - 1, r_at(r, nrow - 1));
+      }
+    };
+    publish();
+    allsum<2>(c, s, s_red, [] {});
     const double sumb = s[0];
     double sumr = s[1];
     const double eps = sqrt(sumb) * 1e-6;                                                        // field.f90:364
     int act = 0, ite = 0;
     if (sqrt(sumr) > eps) act = sumb > eps;  // the first test compares sum(b^2), not its sqrt      field.f90:385-387
     // ---- p <- r                                                                                  field.f90:379
+    __syncthreads();
 #pragma unroll
-    for (int k = 0, cx = cx0, cy = cy0; k < CGP_K; k++) {
-      const int e = t + k * CGP_T;
-      if (e < ncl) T[e + 2 * cy + tp + 1] = r[k];
-      cx += dr; cy += dq;
-      if (cx >= bw) { cx -= bw; cy++; }
-    }
+    for (int k = 0; k < K; k++)
+      if (k < nrow) T[i0 + k * tp] = r[k];
+    fill_halo(l, [&](size_t g) { return __ldcg(&a.rg[g]); }, [](double v, int) { return v; });
     __syncthreads();
-    for (int h = t; h < nhalo; h += CGP_T) {
-      int ti, li, lj, kind;
-      halo_pos(h, ti, li, lj, kind);
-      double v;
-      if (kind == 0) v = __ldcg(&a.rg[pidx(P, li, lj) * 3 + l]);
-      else if (kind == 1) v = (l == 0) ? -T[ti + 1] : T[ti + 2];
-      else v = 0.0;
-      T[ti] = v;
-    }
-    __syncthreads();
+    wall_halo(l);
 
 #pragma unroll 1
     while (act) {
       // ---- phase A: ap <- f4 p - N4 p, sums r.r and p.ap                                        field.f90:392-413
       double sa[2] = {0.0, 0.0};
+      {
+        double up = T[i0 - tp], cc = T[i0];
 #pragma unroll
-      for (int k = 0, cx = cx0, cy = cy0; k < CGP_K; k++) {
-        const int e = t + k * CGP_T;
-        if (e < ncl) {
-          const int i = e + 2 * cy + tp + 1;
-          const double pc = T[i];
-          const double av = -T[i - tp] - T[i - 1] + f4 * pc - T[i + 1] - T[i + tp];
-          const double rr = r[k];
-          sa[0] = sa[0] + rr * rr;
-          sa[1] = sa[1] + pc * av;
-        }
-        cx += dr; cy += dq;
-        if (cx >= bw) { cx -= bw; cy++; }
-      }
-      allsum<2>(c, sa, s_red, s_tot);
-      sumr = sa[0];
-      const double alpha = sumr / sa[1];                                                          // field.f90:415
-      // ---- phase B: phi += alpha p, r -= alpha ap, sum of the new r.r                            field.f90:417-441
-      double sb1[1] = {0.0};
-#pragma unroll
-      for (int k = 0, cx = cx0, cy = cy0; k < CGP_K; k++) {
-        const int e = t + k * CGP_T;
-        if (e < ncl) {
-          const int i = e + 2 * cy + tp + 1;
-          const double pc = T[i];
-          const double av = -T[i - tp] - T[i - 1] + f4 * pc - T[i + 1] - T[i + tp];
-          phi[e] = phi[e] + alpha * pc;
-          const double rr = r[k] - alpha * av;
-          r[k] = rr;
-          sb1[0] = sb1[0] + rr * rr;
-          if (cx == 0 || cx == bw - 1 || cy == 0 || cy == bh - 1) {
-            const int li = x0 + cx, lj = y0 + cy;
-            a.rg[pidx(P, li, lj) * 3 + l] = rr;
-            if (P.nsize > 1) {
-              if (lj == 0) a.r_down[pidx(P, li, a.nyl_down) * 3 + l] = rr;
-              if (lj == P.nyl - 1) a.r_up[pidx(P, li, -1) * 3 + l] = rr;
-            }
+        for (int k = 0; k < K; k++) {
+          if (k < nrow) {
+            const int i = i0 + k * tp;
+            const double dn = T[i + tp];
+            const double av = -up - T[i - 1] + f4 * cc - T[i + 1] - dn;
+            const double rr = r[k];
+            sa[0] = sa[0] + rr * rr;
+            sa[1] = sa[1] + cc * av;
+            up = cc;
+            cc = dn;
           }
         }
-        cx += dr; cy += dq;
-        if (cx >= bw) { cx -= bw; cy++; }
       }
-      allsum<1>(c, sb1, s_red, s_tot);
+      allsum<2>(c, sa, s_red, [] {});
+      sumr = sa[0];
+      const double alpha = sumr / sa[1];                                                          // field.f90:415
+      // ---- phase B: r -= alpha ap, sum of the new r.r; phi += alpha p while the barrier gathers    field.f90:417-441
+      double sb1[1] = {0.0};
+      {
+        double up = T[i0 - tp], cc = T[i0];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          if (k < nrow) {
+            const int i = i0 + k * tp;
+            const double dn = T[i + tp];
+            const double av = -up - T[i - 1] + f4 * cc - T[i + 1] - dn;
+            const double rr = r[k] - alpha * av;
+            r[k] = rr;
+            sb1[0] = sb1[0] + rr * rr;
+            up = cc;
+            cc = dn;
+          }
+        }
+      }
+      publish();
+      allsum<1>(c, sb1, s_red, [&] {
+        // loads first, in two batches: one L2 round trip per batch instead of one per cell
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          double ph[(K + 1) / 2];
+#pragma unroll
+          for (int k = 0; k < (K + 1) / 2; k++) {
+            const int kk = h * ((K + 1) / 2) + k;
+            ph[k] = (kk < K && kk < nrow) ? phi[(size_t)kk * nthr] : 0.0;
+          }
+#pragma unroll
+          for (int k = 0; k < (K + 1) / 2; k++) {
+            const int kk = h * ((K + 1) / 2) + k;
+            if (kk < K && kk < nrow) phi[(size_t)kk * nthr] = ph[k] + alpha * T[i0 + kk * tp];
+          }
+        }
+      });
       // ---- loop control: the test uses the residual BEFORE this update                           field.f90:426-430,387
       ite++;
       if (ite >= 100) {
@@ -386,42 +424,44 @@ __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__
       if (!act) break;
       // ---- p <- r + beta p (field.f90:443-450), halo ring from the neighbours' new r and the old halo p
       const double beta = sb1[0] / sumr;
+      {
+        // the halo loads first: their L2 latency runs under the update of the own cells
+        double hb = 0.0, ht = 0.0;
+        if (has_bot) hb = __ldcg(&a.rg[g_bot + l]);
+        if (has_top) ht = __ldcg(&a.rg[g_top + l]);
 #pragma unroll
-      for (int k = 0, cx = cx0, cy = cy0; k < CGP_K; k++) {
-        const int e = t + k * CGP_T;
-        if (e < ncl) {
-          const int i = e + 2 * cy + tp + 1;
-          T[i] = r[k] + beta * T[i];
-        }
-        cx += dr; cy += dq;
-        if (cx >= bw) { cx -= bw; cy++; }
+        for (int k = 0; k < K; k++)
+          if (k < nrow) {
+            const int i = i0 + k * tp;
+            T[i] = r[k] + beta * T[i];
+          }
+        if (has_bot) T[i_bot] = hb + beta * T[i_bot];
+        if (has_top) T[i_top] = ht + beta * T[i_top];
+        if (first_col && kindl == 0)
+          for (int k = 0; k < nrow; k++) {
+            const int i = i0 + k * tp - 1;
+            T[i] = __ldcg(&a.rg[pidx(P, lil, y0 + cyb + k) * 3 + l]) + beta * T[i];
+          }
+        if (last_col && kindr == 0)
+          for (int k = 0; k < nrow; k++) {
+            const int i = i0 + k * tp + 1;
+            T[i] = __ldcg(&a.rg[pidx(P, lir, y0 + cyb + k) * 3 + l]) + beta * T[i];
+          }
       }
       __syncthreads();
-      for (int h = t; h < nhalo; h += CGP_T) {
-        int ti, li, lj, kind;
-        halo_pos(h, ti, li, lj, kind);
-        double v;
-        if (kind == 0) v = __ldcg(&a.rg[pidx(P, li, lj) * 3 + l]) + beta * T[ti];
-        else if (kind == 1) v = (l == 0) ? -T[ti + 1] : T[ti + 2];
-        else v = 0.0;
-        T[ti] = v;
-      }
-      __syncthreads();
+      wall_halo(l);
     }
     if (c.cta == 0 && t == 0) a.out[l] = ite;
   }
 
   // ---- df(l) <- phi on the interior                                                              field.f90:455-457
 #pragma unroll
-  for (int k = 0, cx = cx0, cy = cy0; k < CGP_K; k++) {
-    const int e = t + k * CGP_T;
-    if (e < ncl) {
-      const size_t o = pidx(P, x0 + cx, y0 + cy);
+  for (int k = 0; k < K; k++) {
+    if (k < nrow) {
+      const size_t o = pidx(P, li_own, y0 + cyb + k);
 #pragma unroll
-      for (int l = 0; l < 3; l++) a.df[o * 6 + l] = a.phipl[l * plane + pbase + e];
+      for (int l = 0; l < 3; l++) a.df[o * 6 + l] = a.phipl[l * plane + pbase + (size_t)k * nthr];
     }
-    cx += dr; cy += dq;
-    if (cx >= bw) { cx -= bw; cy++; }
   }
   if (c.cta == 0 && t == 0) {
     a.out[3] = stop;
@@ -429,46 +469,58 @@ __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__
   }
 }
 
-// Block decomposition of an nx x nyl slab over at most nsm CTAs: cbx x cby blocks with at most CGP_K * CGP_T cells each whose
-// tile (+ halo ring) fits `smem_max` bytes of shared memory.  Returns false if the slab is too large for the on-chip solver.
-bool cgp_plan(int nx, int nyl, int nsm, size_t smem_max, int *cbx_out, int *cby_out, size_t *smem_out) {
+// Block decomposition of an nx x nyl slab over at most nsm CTAs: cbx x cby blocks of bw x bh cells; a thread owns a vertical
+// run of rl <= CGP_K cells, bw * ceil(bh / rl) <= CGP_T threads, and the tile (+ halo ring) fits `smem_max` bytes of shared
+// memory.  Returns false if the slab is too large for the on-chip solver.
+bool cgp_plan(int nx, int nyl, int nsm, size_t smem_max, int *cbx_out, int *cby_out, int *rl_out, size_t *smem_out) {
   long long best = -1;
-  int bcx = 0, bcy = 0;
+  int bcx = 0, bcy = 0, brl = 0;
   size_t bsm = 0;
-  for (int cbx = 1; cbx <= nsm && cbx * 4 <= nx; cbx++)
+  if (nsm > 160) nsm = 160;  // GMAX of the kernel
+  for (int cbx = 1; cbx <= nsm && (cbx * 4 <= nx || cbx == 1); cbx++)
     for (int cby = 1; cbx * cby <= nsm && cby <= nyl; cby++) {
       const int bw = (nx + cbx - 1) / cbx, bh = (nyl + cby - 1) / cby;
-      const long long cells = (long long)bw * bh;
-      if (cells > (long long)CGP_K * CGP_T) continue;
+      if (bw > CGP_T || 2 * (bw + bh) > 3 * CGP_T) continue;
+      int ng = CGP_T / bw;
+      if (ng > bh) ng = bh;
+      const int rl = (bh + ng - 1) / ng;
+      if (rl > CGP_K) continue;
       const size_t sm = (size_t)(bw + 2) * (bh + 2) * sizeof(double);
       if (sm > smem_max) continue;
-      // fewest cells per CTA first; below one cell per thread more CTAs only make the barrier slower: then the fewest CTAs;
-      // ties: the shorter perimeter
-      const long long work = cells < CGP_T ? CGP_T : cells;
-      const long long score = work * 1000000LL + (cells < CGP_T ? (long long)cbx * cby * 1000 : 0) + (bw + bh);
+      // fewest cells per thread first; among equals the fewest CTAs (a cheaper barrier), then the shorter perimeter
+      const long long score = (long long)rl * 100000000LL + (long long)cbx * cby * 10000 + (bw + bh);
       if (best < 0 || score < best) {
         best = score;
         bcx = cbx;
         bcy = cby;
+        brl = rl;
         bsm = sm;
       }
     }
   if (best < 0) return false;
   *cbx_out = bcx;
   *cby_out = bcy;
+  *rl_out = brl;
   *smem_out = bsm;
   return true;
 }
 
 cudaError_t cgp_prepare(size_t smem) {
-  return cudaFuncSetAttribute(k_cg_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_cg_persist<CGP_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_cg_persist<CGP_KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_cg_persist<CGP_KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 cudaError_t launch_cg_persist(const DevParams &P, const CgpArgs &a, size_t smem, cudaStream_t st) {
   DevParams Pc = P;
   CgpArgs ac = a;
   void *args[] = {(void *)&Pc, (void *)&ac};
-  return cudaLaunchCooperativeKernel((const void *)k_cg_persist, dim3(a.cbx * a.cby), dim3(CGP_T), args, smem, st);
+  const void *fn = (a.rl <= CGP_KS)   ? (const void *)k_cg_persist<CGP_KS>
+                   : (a.rl <= CGP_KM) ? (const void *)k_cg_persist<CGP_KM>
+                                      : (const void *)k_cg_persist<CGP_K>;
+  return cudaLaunchCooperativeKernel(fn, dim3(a.cbx * a.cby), dim3(CGP_T), args, smem, st);
 }
 
 }  // namespace wm

@@ -92,7 +92,8 @@ void launch_update_uf(const DevParams &P, const FieldBufs &f, cudaStream_t st); 
 void launch_field_energy(const DevParams &P, const double *uf, double *partial, int nblocks, cudaStream_t st);
 // ---- persistent cooperative CG (cg_persist_kernel.cu): the three solves of cgm in one kernel, state on chip
 constexpr int CGP_T = 1024;   // threads per CTA, one CTA per SM
-constexpr int CGP_K = 14;     // cells per thread at most (r in registers): 148 x 14336 >= 4096 x 512
+constexpr int CGP_K = 16;     // cells per thread at most (r in registers): 4096 x 512 on 148 SMs takes 14, 16384 x 128 takes 15
+constexpr int CGP_KM = 14, CGP_KS = 8;  // further instantiations for slabs that need at most 14 / 8 cells per thread
 constexpr int CGP_MAXR = 8;   // ranks on the ring the in-kernel all-reduce supports
 struct CgpShared {            // one per rank, mapped by every other rank (CUDA IPC)
   unsigned long long flag[CGP_MAXR];  // flag[src] = last barrier sequence number rank src has published here
@@ -100,11 +101,12 @@ struct CgpShared {            // one per rank, mapped by every other rank (CUDA 
 };
 struct CgpArgs {
   int cbx, cby;               // block decomposition of the slab: cbx x cby CTAs
+  int rl;                     // cells per thread (a vertical run)
   double *df;                 // in: df(1:3) warm start (+ ghost rows of the ring neighbours); out: df(1:3) interior
   const double *gkl;          // right-hand side before the f5 scaling
   double *rg;                 // AoS3 padded: r of the blocks' perimeter cells, ghost rows written by the ring neighbours
   double *phipl, *bpl;        // 3 dense planes each: phi and b, cell e of CTA c at plane[l] + base(c) + e
-  double *partial;            // [2][G][4] partial sums of the CTAs
+  double *partial;            // [2][160] x (2 doubles): partial sums of the CTAs
   unsigned *bar;              // barrier counter, zero at launch
   int *abort;                 // set by a CTA whose wait timed out: everybody leaves
   int *out;                   // ite[3], stop, barriers
@@ -114,8 +116,10 @@ struct CgpArgs {
   CgpShared *sh[CGP_MAXR];    // every rank's block as mapped here (sh[nrank] = mine)
   double *r_up, *r_down;      // rg of nup / ndown as mapped here
   int nyl_down;               // rows of ndown: its upper ghost row is local row nyl_down
+  unsigned long long *trace;  // WM_CGTRACE: [G][4 barriers][4 events] global-timer stamps, else null
+  unsigned trace_seq;
 };
-bool cgp_plan(int nx, int nyl, int nsm, size_t smem_max, int *cbx, int *cby, size_t *smem);
+bool cgp_plan(int nx, int nyl, int nsm, size_t smem_max, int *cbx, int *cby, int *rl, size_t *smem);
 cudaError_t cgp_prepare(size_t smem);
 cudaError_t launch_cg_persist(const DevParams &P, const CgpArgs &a, size_t smem, cudaStream_t st);
 size_t cgctl_bytes();

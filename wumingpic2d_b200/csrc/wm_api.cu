@@ -103,7 +103,7 @@ struct wm_ctx {
   int cg_mode = 1;                       // WM_CG=0 selects the host loop of small kernels (k_cg_pap / k_cg_update2)
   bool cgp_ok = false;                   // the slab fits the on-chip solver on this device
   bool cgp_ring = false;                 // nsize > 1: the neighbours' arrays are mapped (CUDA IPC) on every rank
-  int cgp_cbx = 0, cgp_cby = 0, nsm = 0;
+  int cgp_cbx = 0, cgp_cby = 0, cgp_rl = 0, nsm = 0;
   int cgp_planned_nxa = -1;
   bool cgp_plan_ok = false;
   size_t cgp_smem = 0, cgp_smem_max = 0;
@@ -311,6 +311,7 @@ int cg_solve_persist(wm_ctx *c) {
   CgpArgs a{};
   a.cbx = c->cgp_cbx;
   a.cby = c->cgp_cby;
+  a.rl = c->cgp_rl;
   a.df = c->f.df;
   a.gkl = c->f.gkl;
   a.rg = c->f.r;
@@ -329,8 +330,42 @@ int cg_solve_persist(wm_ctx *c) {
   a.r_up = c->cgp_r_up;
   a.r_down = c->cgp_r_down;
   a.nyl_down = c->cgp_nyl_down;
+  static const char *tr = getenv("WM_CGTRACE");
+  unsigned long long *d_tr = nullptr;
+  const int G = a.cbx * a.cby;
+  if (tr && atoi(tr) > 0) {
+    CU(cudaMalloc(&d_tr, (size_t)G * 16 * sizeof(unsigned long long)));
+    CU(cudaMemset(d_tr, 0, (size_t)G * 16 * sizeof(unsigned long long)));
+    a.trace = d_tr;
+    a.trace_seq = (unsigned)atoi(tr);
+  }
   CU(cudaMemsetAsync(c->cgp_bar, 0, 2 * sizeof(unsigned), c->st));
   CU(launch_cg_persist(P, a, c->cgp_smem, c->st));
+  if (d_tr) {  // debugging aid: spread of the CTAs' arrival / release times at four consecutive barriers
+    std::vector<unsigned long long> h((size_t)G * 16);
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaMemcpy(h.data(), d_tr, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(cudaFree(d_tr));
+    unsigned long long t0 = ~0ull;
+    for (auto v : h) if (v && v < t0) t0 = v;
+    static int shown = 0;
+    if (shown++ < 3)
+      for (int b = 0; b < 4; b++) {
+        static const char *nm[4] = {"reduced", "arrived", "between done", "released"};
+        for (int e = 0; e < 4; e++) {
+          unsigned long long lo = ~0ull, hi = 0;
+          double mean = 0;
+          for (int g = 0; g < G; g++) {
+            const unsigned long long v = h[((size_t)g * 4 + b) * 4 + e];
+            lo = std::min(lo, v);
+            hi = std::max(hi, v);
+            mean += (double)(v - t0);
+          }
+          fprintf(stderr, "cgtrace barrier %u %-13s min %8.2f us mean %8.2f us max %8.2f us\n", a.trace_seq + b, nm[e],
+                  (lo - t0) * 1e-3, mean / G * 1e-3, (hi - t0) * 1e-3);
+        }
+      }
+  }
   CU(cudaMemcpyAsync(c->h_cgp_out, c->cgp_out, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
   c->cg_pending = true;
   c->launches++;
@@ -343,22 +378,23 @@ bool cg_persist_usable(wm_ctx *c) {
   if (!c->cg_mode || !c->cgp_ok) return false;
   if (c->P.nsize > 1 && !c->cgp_ring) return false;
   if (c->cgp_planned_nxa != c->nxa) {
-    int cbx, cby;
+    int cbx, cby, rl;
     size_t sm;
     const int nyl = c->P.nyl;
-    bool ok = cgp_plan(c->nxa, nyl, c->nsm, c->cgp_smem_max, &cbx, &cby, &sm);
+    bool ok = cgp_plan(c->nxa, nyl, c->nsm, c->cgp_smem_max, &cbx, &cby, &rl, &sm);
     if (ok && c->P.nsize > 1) {  // slabs hold ny / nsize rows, the first mod(ny, nsize) ranks one more
       const int ny = c->cfg.nyge - c->cfg.nygs + 1, base = ny / c->P.nsize;
-      int bx2, by2;
+      int bx2, by2, rl2;
       size_t sm2;
-      ok = cgp_plan(c->nxa, base, c->nsm, c->cgp_smem_max, &bx2, &by2, &sm2) &&
-           cgp_plan(c->nxa, base + (ny % c->P.nsize ? 1 : 0), c->nsm, c->cgp_smem_max, &bx2, &by2, &sm2);
+      ok = cgp_plan(c->nxa, base, c->nsm, c->cgp_smem_max, &bx2, &by2, &rl2, &sm2) &&
+           cgp_plan(c->nxa, base + (ny % c->P.nsize ? 1 : 0), c->nsm, c->cgp_smem_max, &bx2, &by2, &rl2, &sm2);
     }
     c->cgp_planned_nxa = c->nxa;
     c->cgp_plan_ok = ok;
     if (ok) {
       c->cgp_cbx = cbx;
       c->cgp_cby = cby;
+      c->cgp_rl = rl;
       c->cgp_smem = sm;
     }
   }
@@ -422,19 +458,28 @@ int cg_solve(wm_ctx *c) {
   return 0;
 }
 
-// everything of field__fdtd_i after ele_cur                                 field.f90:122-184
-int field_solve(wm_ctx *c) {
+// everything of field__fdtd_i after ele_cur, in two halves: up to the end of the CG solves (field.f90:122-149) ...
+int field_solve_pre(wm_ctx *c) {
   const DevParams P = fieldp(c);
   WM(bc_curre(c));
   launch_rhs(P, c->f, c->st);
   c->launches++;
   WM(cg_solve(c));
+  return 0;
+}
+// ... and from bc__dfield to the update of uf (field.f90:151-184)
+int field_solve_post(wm_ctx *c) {
+  const DevParams P = fieldp(c);
   WM(halo_copy(c, c->f.df, 6, 2, true));
   launch_efield(P, c->f, c->st);
   WM(halo_copy(c, c->f.df, 6, 2, true));
   launch_update_uf(P, c->f, c->st);
   c->launches += 2;
   return 0;
+}
+int field_solve(wm_ctx *c) {
+  WM(field_solve_pre(c));
+  return field_solve_post(c);
 }
 
 Pass1Args p1args(wm_ctx *c, const PartSoA &src, const PartSoA &dst, double delt_push) {
@@ -691,12 +736,12 @@ int wm_create(const wm_config *g, wm_ctx **out) {
     // persistent CG: one CTA per SM, the block's p tile in (opt-in) shared memory
     c->nsm = prop.multiProcessorCount;
     c->cgp_smem_max = prop.sharedMemPerBlockOptin > 4096 ? prop.sharedMemPerBlockOptin - 2048 : 0;  // s_red, s_tot are static
-    int cbx, cby;
+    int cbx, cby, rl;
     size_t sm;
-    c->cgp_ok = prop.cooperativeLaunch && cgp_plan(nx, nyl, c->nsm, c->cgp_smem_max, &cbx, &cby, &sm) &&
+    c->cgp_ok = prop.cooperativeLaunch && cgp_plan(nx, nyl, c->nsm, c->cgp_smem_max, &cbx, &cby, &rl, &sm) &&
                 cgp_prepare(c->cgp_smem_max) == cudaSuccess;
     (void)cudaGetLastError();
-    CU(cudaMalloc(&c->cgp_partial, (size_t)2 * c->nsm * 4 * sizeof(double)));
+    CU(cudaMalloc(&c->cgp_partial, (size_t)2 * 160 * 2 * sizeof(double)));
     CU(cudaMalloc(&c->cgp_bar, 2 * sizeof(unsigned)));
     CU(cudaMalloc(&c->cgp_out, 8 * sizeof(int)));
     CU(cudaMemset(c->cgp_out, 0, 8 * sizeof(int)));
@@ -1302,6 +1347,12 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
       // of field__fdtd_i only needs uj: the two run side by side, the sort on the second stream.  (NCCL calls stay
       // on the main stream, in program order.)
       WM(migrate(c, true));  // ring exchange of the leavers; arrivals are appended to their segments
+      // The persistent CG kernel takes every SM (one 1024-thread CTA each): a sort tail started before it would have to
+      // drain first.  So with k_place_rim (0.3 ms) the fork comes after the CG solves and the tail runs beside the
+      // streaming kernels that follow (bc__dfield, delta-E, uf update); the longer variants fork before the field solve.
+      const bool late_fork = rim && cg_persist_usable(c);
+      if (c->timing) CU(cudaEventRecord(c->ev[3], c->st));  // (ev[2], ev[3]) = migration
+      if (late_fork) WM(field_solve_pre(c));
       CU(cudaEventRecord(c->ev_fork, c->st));
       CU(cudaStreamWaitEvent(c->st2, c->ev_fork, 0));
       if (c->timing) CU(cudaEventRecord(c->ev_b[0], c->st2));
@@ -1313,9 +1364,11 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
       CU(cudaMemcpyAsync(c->h_ovf, c->ovfcnt, sizeof(int), cudaMemcpyDeviceToHost, c->st2));
       if (c->timing) CU(cudaEventRecord(c->ev_b[1], c->st2));
       CU(cudaEventRecord(c->ev_join, c->st2));
-      if (c->timing) CU(cudaEventRecord(c->ev[3], c->st));  // (ev[2], ev[3]) = migration
-      WM(field_solve(c));
-      if (c->timing) CU(cudaEventRecord(c->ev[4], c->st));  // (ev[3], ev[4]) = field solve, k_place running beside it
+      if (late_fork)
+        WM(field_solve_post(c));
+      else
+        WM(field_solve(c));
+      if (c->timing) CU(cudaEventRecord(c->ev[4], c->st));  // (ev[3], ev[4]) = field solve, the sort tail running beside (part of) it
       CU(cudaStreamWaitEvent(c->st, c->ev_join, 0));
     } else if (inplace) {
       // rest of field__fdtd_i
@@ -1420,14 +1473,15 @@ int wm_cg_path(wm_ctx *c, int32_t *path) {
   return 0;
 }
 
-int wm_cg_plan(int32_t nx, int32_t nyl, int32_t nsm, int64_t smem_max, int32_t out[3]) {
+int wm_cg_plan(int32_t nx, int32_t nyl, int32_t nsm, int64_t smem_max, int32_t out[4]) {
   if (!out) return fail("wm_cg_plan: null argument");
-  int cbx = 0, cby = 0;
+  int cbx = 0, cby = 0, rl = 0;
   size_t sm = 0;
-  if (!cgp_plan(nx, nyl, nsm, (size_t)smem_max, &cbx, &cby, &sm)) return fail("wm_cg_plan: the slab does not fit the on-chip solver");
+  if (!cgp_plan(nx, nyl, nsm, (size_t)smem_max, &cbx, &cby, &rl, &sm)) return fail("wm_cg_plan: the slab does not fit the on-chip solver");
   out[0] = cbx;
   out[1] = cby;
   out[2] = (int32_t)sm;
+  out[3] = rl;
   return 0;
 }
 
