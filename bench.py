@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--ppc", type=int, default=PPC)
     ap.add_argument("--ref-rows", type=int, default=256, help="rows of the CPU arm's sample (--impl reference)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-interval", type=int, default=50, help="also time wm_host_steps over this many steps per upload/download")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exact", action="store_true", help="bit-exact push arithmetic (WM_FLAG_EXACT_PUSH)")
@@ -331,7 +332,22 @@ def main():
             dt = allmax(time.perf_counter() - t0)
             e2e = {"value": n_total * args.e2e_steps / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
-                   "api": "wm_host_step(up, uf, np2, cumcnt): pinned host arrays in the reference's Fortran layout"}
+                   "api": "wm_host_step(up, uf, np2, cumcnt): pinned host arrays in the reference's Fortran layout",
+                   "note": "every step moves the whole state over PCIe: %.1f GB up, then the step, then %.1f GB down; the two "
+                           "transfers of one call cannot overlap (the step lies between them), so ~2 x 13 GB / 55 GB/s bounds "
+                           "it" % (h2d / 1e9, d2h / 1e9)}
+            # how the shim is meant to be used: host arrays refreshed every intvl_mom = 50 steps (WM_SYNC_INTERVAL=50)
+            if args.e2e_interval > 1:
+                barrier()
+                t0 = time.perf_counter()
+                ctx.host_steps(up, uf, np2, cum, args.e2e_interval)
+                barrier()
+                dti = allmax(time.perf_counter() - t0)
+                e2e["sync_interval_%d" % args.e2e_interval] = {
+                    "value": n_total * args.e2e_interval / dti, "unit": "particle-steps/s", "ms_per_step": 1e3 * dti / args.e2e_interval,
+                    "h2d_bytes_per_step": h2d // args.e2e_interval, "d2h_bytes_per_step": d2h // args.e2e_interval,
+                    "api": "wm_host_steps(up, uf, np2, cumcnt, %d): one upload, %d steps, one download (the shim's "
+                           "WM_SYNC_INTERVAL = intvl_mom of proj/weibel/config_sample.json)" % (args.e2e_interval, args.e2e_interval)}
             del up, uf, up_t, uf_t
         except Exception as ex:  # keep the resident number even if host memory is short
             e2e = {"value": None, "unit": "particle-steps/s", "error": str(ex)[:200]}

@@ -136,6 +136,10 @@ int wm_step(wm_ctx *ctx, int32_t nsteps);
 /* One full time step on host arrays: on entry `up` is cell-sorted with `cumcnt`
  * consistent (as after sort__bucket); on exit the same holds for the new state. */
 int wm_host_step(wm_ctx *ctx, double *up, double *uf, int32_t *np2, int32_t *cumcnt);
+/* The same over nsteps time steps with one upload before and one download after: what the Fortran shim does with
+ * WM_SYNC_INTERVAL = n (host arrays refreshed every n-th sort__bucket; the sample config's intvl_mom is 50, i.e. the driver
+ * looks at up/uf every 50 steps, proj/weibel/config_sample.json, proj/weibel/app.f90:109-126). */
+int wm_host_steps(wm_ctx *ctx, double *up, double *uf, int32_t *np2, int32_t *cumcnt, int32_t nsteps);
 /* particle__solv(gp,up,uf,cumcnt,nxs,nxe)   common/particle.f90:48 */
 int wm_host_particle__solv(wm_ctx *ctx, double *gp, const double *up, const double *uf,
                            const int32_t *cumcnt, const int32_t *np2);

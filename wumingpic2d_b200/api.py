@@ -50,7 +50,7 @@ EXPORTS = [
     "wm_particle_counts", "wm_particle__solv", "wm_field__ele_cur", "wm_boundary__curre",
     "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_boundary__injection",
     "wm_set_u_inject", "wm_set_xrange", "wm_append_particles", "wm_sort__bucket",
-    "wm_step", "wm_host_step", "wm_cg_path", "wm_cg_plan", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
+    "wm_step", "wm_host_step", "wm_host_steps", "wm_cg_path", "wm_cg_plan", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
     "wm_energy", "wm_gauss_residual", "wm_moments", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_ic_weibel", "wm_timing", "wm_synchronize", "wm_layout_rebuilds",
 ]
 
@@ -107,6 +107,7 @@ def load_library():
     lib.wm_set_xrange.argtypes = [P, C.c_int32, C.c_int32]
     lib.wm_append_particles.argtypes = [P, C.c_int32, C.c_int64, D]
     lib.wm_host_step.argtypes = [P, D, D, I32, I32]
+    lib.wm_host_steps.argtypes = [P, D, D, I32, I32, C.c_int32]
     lib.wm_host_particle__solv.argtypes = [P, D, D, D, I32, I32]
     lib.wm_host_sort__bucket.argtypes = [P, D, D, I32, I32]
     lib.wm_cg_iters.argtypes = [P, I32]
@@ -271,6 +272,9 @@ class Context:
     # ---- host-array (drop-in) calls
     def host_step(self, up, uf, np2, cumcnt):
         self._ck(self.lib.wm_host_step(self.h, _d(up), _d(uf), _i(np2), _i(cumcnt)))
+
+    def host_steps(self, up, uf, np2, cumcnt, nsteps):
+        self._ck(self.lib.wm_host_steps(self.h, _d(up), _d(uf), _i(np2), _i(cumcnt), nsteps))
 
     def host_particle__solv(self, gp, up, uf, cumcnt, np2):
         self._ck(self.lib.wm_host_particle__solv(self.h, _d(gp), _d(up), _d(uf), _i(cumcnt), _i(np2)))

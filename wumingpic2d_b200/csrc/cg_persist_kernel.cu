@@ -29,6 +29,7 @@
 // the global sums differs from the CPU path.
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -73,6 +74,7 @@ struct Ctx {
   const CgpArgs *a;
   int G, cta;
   unsigned nsync;  // barriers passed so far (uniform over the grid)
+  bool peer_writer;  // this CTA stores into the ring neighbours' ghost rows (its block touches the slab's first / last row)
 };
 
 // spin until pred() or abort / timeout
@@ -106,7 +108,7 @@ __device__ __forceinline__ void allsum(Ctx &c, double (&v)[NV], double *s_red, F
   if (lane == 0)
 #pragma unroll
     for (int k = 0; k < NV; k++) s_red[wid * 2 + k] = v[k];
-  if (a.nsize > 1) __threadfence_system();  // my stores into the neighbours' ghost rows
+  if (c.peer_writer) asm volatile("fence.acq_rel.sys;" ::: "memory");  // my stores into the neighbours' ghost rows
   __syncthreads();
   const unsigned seq = ++c.nsync;
   double2 *part = reinterpret_cast<double2 *>(a.partial) + (size_t)(seq & 1u) * GMAX;
@@ -121,8 +123,10 @@ __device__ __forceinline__ void allsum(Ctx &c, double (&v)[NV], double *s_red, F
     if (lane == 0) {
       trace(a, c.cta, seq, 0);
       part[c.cta] = make_double2(w[0], w[1]);
-      __threadfence();
-      atomicAdd(a.bar, 1u);
+      // release at gpu scope: the partial sums, and (through the CTA barrier above) every thread's perimeter stores, are
+      // visible to whoever acquires the counter.  (A release reduction, not __threadfence() + atomicAdd: the latter is a
+      // sequentially consistent fence, MEMBAR.SC, and costs about twice as much on the arrival path.)
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
       trace(a, c.cta, seq, 1);
     }
   }
@@ -156,10 +160,18 @@ __device__ __forceinline__ void allsum(Ctx &c, double (&v)[NV], double *s_red, F
       trace(a, c.cta, seq, 3);
     }
     __syncthreads();
-    double w[2];
-    sum_partials(w);
+    // one warp reads the partials (every warp of every CTA doing it made a hot spot of the few L2 lines that hold them)
+    if (wid == 0) {
+      double w[2];
+      sum_partials(w);
+      if (lane == 0) {
+        s_red[64] = w[0];
+        s_red[65] = w[1];
+      }
+    }
+    __syncthreads();
 #pragma unroll
-    for (int k = 0; k < NV; k++) v[k] = w[k];
+    for (int k = 0; k < NV; k++) v[k] = s_red[64 + k];
   } else {
     // ring: CTA 0 adds the slab's partials and publishes them to every rank (itself included); everybody waits for the
     // flags of all ranks in its own memory
@@ -175,19 +187,24 @@ __device__ __forceinline__ void allsum(Ctx &c, double (&v)[NV], double *s_red, F
           CgpShared *dst = a.sh[lane];
 #pragma unroll
           for (int k = 0; k < NV; k++) dst->xsum[slot][a.nrank][k] = w[k];
-          __threadfence_system();
-          st_release_sys(&dst->flag[a.nrank], gseq);
+          st_release_sys(&dst->flag[a.nrank], gseq);  // release.sys: orders the sums above and, cumulatively, the ghost rows
         }
       }
     }
     CgpShared *me = a.sh[a.nrank];
     if (t < a.nsize) spin_until(a, [&] { return ld_acquire_sys(&me->flag[t]) >= gseq; });
     __syncthreads();
-    double w[2] = {0.0, 0.0};
-    for (int q = 0; q < a.nsize; q++) {
+    if (t == 0) {
+      double w[2] = {0.0, 0.0};
+      for (int q = 0; q < a.nsize; q++) {
 #pragma unroll
-      for (int k = 0; k < NV; k++) w[k] += __ldcg(&me->xsum[slot][q][k]);
+        for (int k = 0; k < NV; k++) w[k] += __ldcg(&me->xsum[slot][q][k]);
+      }
+      s_red[64] = w[0];
+      s_red[65] = w[1];
     }
+    __syncthreads();
+    double w[2] = {s_red[64], s_red[65]};
 #pragma unroll
     for (int k = 0; k < NV; k++) v[k] = w[k];
   }
@@ -205,14 +222,51 @@ __device__ __forceinline__ double r_at(const double (&r)[K], int k) {
 }  // namespace
 
 // Thread layout: a block of bw x bh cells, bw * ng <= 1024 threads; thread (cx, g) owns the vertical run of rl = ceil(bh / ng)
-// cells (cx, g * rl ...) of one column, so the stencil slides down the column with three shared-memory loads per cell (the
-// shared-memory pipe bounds the compute phases: 8-byte loads are two wavefronts per warp).  The halo ring is served by the
+// cells (cx, g * rl ...) of one column.  The tile is stored COLUMN-major with an odd column pitch cp >= bh + 2: a thread's run,
+// the run of its left neighbour and the run of its right neighbour are three contiguous strips, so every shared-memory access
+// of the stencil is `base register + immediate` (no address arithmetic in the loops), the stencil slides down the column with
+// three loads per cell, and consecutive threads (consecutive columns) hit distinct banks.  The halo ring is served by the
 // threads next to it: the first / last thread of a column takes the cell below / above, the threads of the first / last column
 // the cells left / right of their rows.
+template <int K, bool GUARD>
+__device__ __forceinline__ void cg_phase_a(const double *q, const double *ql, const double *qr, int nrow, double f4, const double (&r)[K],
+                                           double (&sa)[2]) {
+  double up = q[-1], cc = q[0];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    if (!GUARD || k < nrow) {
+      const double dn = q[k + 1];
+      const double av = -up - ql[k] + f4 * cc - qr[k] - dn;      // ap <- f4 p - N4 p                 field.f90:395-405
+      const double rr = r[k];
+      sa[0] = sa[0] + rr * rr;
+      sa[1] = sa[1] + cc * av;
+      up = cc;
+      cc = dn;
+    }
+  }
+}
+template <int K, bool GUARD>
+__device__ __forceinline__ void cg_phase_b(const double *q, const double *ql, const double *qr, int nrow, double f4, double alpha,
+                                           double (&r)[K], double (&sb)[1]) {
+  double up = q[-1], cc = q[0];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    if (!GUARD || k < nrow) {
+      const double dn = q[k + 1];
+      const double av = -up - ql[k] + f4 * cc - qr[k] - dn;
+      const double rr = r[k] - alpha * av;                        // r <- r - alpha ap                 field.f90:421-424
+      r[k] = rr;
+      sb[0] = sb[0] + rr * rr;
+      up = cc;
+      cc = dn;
+    }
+  }
+}
+
 template <int K>
 __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__ DevParams P, const __grid_constant__ CgpArgs a) {
-  extern __shared__ __align__(16) double T[];  // p (phi during the set-up) of the block with its halo ring: (bw+2) x (bh+2)
-  __shared__ double s_red[32 * 2];
+  extern __shared__ __align__(16) double T[];  // p (phi during the set-up) of the block with its halo ring: (bw+2) columns x cp
+  __shared__ double s_red[32 * 2 + 2];
 
   const int t = threadIdx.x;
   Ctx c;
@@ -220,23 +274,27 @@ __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__
   c.G = gridDim.x;
   c.cta = blockIdx.x;
   c.nsync = 0;
+  c.peer_writer = false;
   const int bx = c.cta % a.cbx, by = c.cta / a.cbx;
   const int x0 = (int)((long long)bx * P.nx / a.cbx), x1 = (int)((long long)(bx + 1) * P.nx / a.cbx);
   const int y0 = (int)((long long)by * P.nyl / a.cby), y1 = (int)((long long)(by + 1) * P.nyl / a.cby);
-  const int bw = x1 - x0, bh = y1 - y0, tp = bw + 2;
+  const int bw = x1 - x0, bh = y1 - y0;
+  const int cp = a.cp;                        // column pitch of the tile (odd, >= rows of the tallest block + 2)
   const int rl = a.rl;                        // rows per thread
   const int ngr = (bh + rl - 1) / rl;         // row groups in this block
   const int nthr = bw * ngr;                  // threads that own cells
   const bool own = t < nthr;
   const int cx = own ? t % bw : 0, cyb = own ? (t / bw) * rl : 0;
   const int nrow = own ? min(rl, bh - cyb) : 0;              // cells of this thread: (cx, cyb .. cyb + nrow - 1)
-  const int i0 = (cyb + 1) * tp + cx + 1;                     // tile index of its first cell
+  double *const q = T + (cx + 1) * cp + (cyb + 1);            // its run; q[-1] / q[nrow]: the cells below / above
+  double *const ql = q - cp, *const qr = q + cp;              // the same rows of the columns left / right
+  const bool full = nrow == K;
   const size_t plane = (size_t)P.nx * P.nyl;
   const size_t pbase = (size_t)y0 * P.nx + (size_t)x0 * bh + t;  // dense packing: cell k of thread t at pbase + k * nthr
   const bool wall = P.bc != WM_BC_PERIODIC;
   const double f4 = P.f4;
   const int li_own = x0 + cx;
-  // ---- the halo cells this thread serves, as offsets into the AoS3 array rg (component 0) / tile indices
+  // ---- the halo cells this thread serves, as offsets into the AoS3 array rg (component 0)
   const bool has_bot = own && cyb == 0, has_top = own && cyb + nrow == bh;
   const bool first_col = own && cx == 0, last_col = own && cx == bw - 1;
   int ljb = y0 - 1, ljt = y0 + bh;  // rows below / above the block; on one rank the ring neighbour is this slab itself
@@ -245,12 +303,12 @@ __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__
     if (ljt >= P.nyl) ljt -= P.nyl;
   }
   const size_t g_bot = pidx(P, li_own, ljb) * 3, g_top = pidx(P, li_own, ljt) * 3;
-  const int i_bot = i0 - tp, i_top = i0 + nrow * tp;
   // left / right neighbours of the block's first / last column: the wrapped column, or a wall ghost (kind 1 / 2)
   int lil = x0 - 1, lir = x0 + bw, kindl = 0, kindr = 0;
   if (lil < 0) { if (wall) kindl = 1; else lil += P.nx; }
   if (lir >= P.nx) { if (wall) kindr = 2; else lir -= P.nx; }
   const bool slab_bot = P.nsize > 1 && y0 == 0, slab_top = P.nsize > 1 && y0 + bh == P.nyl;  // rows the ring neighbours need
+  c.peer_writer = slab_bot || slab_top;
 
   // r of the perimeter cells goes to the global array (and to the ring neighbours' ghost rows)
   auto publish_one = [&](int l, int cy, double rr) {
@@ -259,25 +317,25 @@ __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__
     if (slab_bot && cy == 0) a.r_down[pidx(P, li_own, a.nyl_down) * 3 + l] = rr;
     if (slab_top && cy == bh - 1) a.r_up[pidx(P, li_own, -1) * 3 + l] = rr;
   };
-  // the halo ring from get(global offset of component 0 of the cell) and mix(value, tile index): rows first, then columns
+  // the halo ring from get(global offset of component l of the cell) and mix(value, old tile value): rows first, then columns
   auto fill_halo = [&](int l, auto get, auto mix) {
     double hb = 0.0, ht = 0.0;
     if (has_bot) hb = get(g_bot + l);
     if (has_top) ht = get(g_top + l);
-    if (has_bot) T[i_bot] = mix(hb, i_bot);
-    if (has_top) T[i_top] = mix(ht, i_top);
+    if (has_bot) q[-1] = mix(hb, q[-1]);
+    if (has_top) q[nrow] = mix(ht, q[nrow]);
     if (first_col && kindl == 0)
-      for (int k = 0; k < nrow; k++) T[i0 + k * tp - 1] = mix(get(pidx(P, lil, y0 + cyb + k) * 3 + l), i0 + k * tp - 1);
+      for (int k = 0; k < nrow; k++) ql[k] = mix(get(pidx(P, lil, y0 + cyb + k) * 3 + l), ql[k]);
     if (last_col && kindr == 0)
-      for (int k = 0; k < nrow; k++) T[i0 + k * tp + 1] = mix(get(pidx(P, lir, y0 + cyb + k) * 3 + l), i0 + k * tp + 1);
+      for (int k = 0; k < nrow; k++) qr[k] = mix(get(pidx(P, lir, y0 + cyb + k) * 3 + l), qr[k]);
   };
   // wall ghosts from the block's own cells (after a barrier: the neighbour thread's column is read)   set_boundary_phi
   auto wall_halo = [&](int l) {
     if (!wall) return;
     if (first_col && kindl == 1)
-      for (int k = 0; k < nrow; k++) T[i0 + k * tp - 1] = (l == 0) ? -T[i0 + k * tp] : T[i0 + k * tp + 1];
+      for (int k = 0; k < nrow; k++) ql[k] = (l == 0) ? -q[k] : qr[k];
     if (last_col && kindr == 2)
-      for (int k = 0; k < nrow; k++) T[i0 + k * tp + 1] = 0.0;
+      for (int k = 0; k < nrow; k++) qr[k] = 0.0;
     __syncthreads();
   };
 
@@ -305,22 +363,21 @@ __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < K; k++)
-      if (k < nrow) T[i0 + k * tp] = phi[(size_t)k * nthr];
-    fill_halo(l, [&](size_t g) { return a.df[(g - l) * 2 + l]; }, [](double v, int) { return v; });
+      if (k < nrow) q[k] = phi[(size_t)k * nthr];
+    fill_halo(l, [&](size_t g) { return a.df[(g - l) * 2 + l]; }, [](double v, double) { return v; });
     __syncthreads();
     wall_halo(l);
     // ---- r <- b + N4 phi - f4 phi, sum b^2, sum r^2                                               field.f90:362-383
     double s[2] = {0.0, 0.0};
     {
-      double up = T[i0 - tp], cc = T[i0];
+      double up = q[-1], cc = q[0];
 #pragma unroll
       for (int k = 0; k < K; k++) {
         r[k] = 0.0;
         if (k < nrow) {
-          const int i = i0 + k * tp;
-          const double dn = T[i + tp];
+          const double dn = q[k + 1];
           const double b = bb[(size_t)k * nthr];
-          const double rr = b + up + T[i - 1] - f4 * cc + T[i + 1] + dn;
+          const double rr = b + up + ql[k] - f4 * cc + qr[k] + dn;
           r[k] = rr;
           s[0] = s[0] + b * b;
           s[1] = s[1] + rr * rr;
@@ -348,8 +405,8 @@ __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < K; k++)
-      if (k < nrow) T[i0 + k * tp] = r[k];
-    fill_halo(l, [&](size_t g) { return __ldcg(&a.rg[g]); }, [](double v, int) { return v; });
+      if (k < nrow) q[k] = r[k];
+    fill_halo(l, [&](size_t g) { return __ldcg(&a.rg[g]); }, [](double v, double) { return v; });
     __syncthreads();
     wall_halo(l);
 
@@ -357,43 +414,19 @@ __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__
     while (act) {
       // ---- phase A: ap <- f4 p - N4 p, sums r.r and p.ap                                        field.f90:392-413
       double sa[2] = {0.0, 0.0};
-      {
-        double up = T[i0 - tp], cc = T[i0];
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-          if (k < nrow) {
-            const int i = i0 + k * tp;
-            const double dn = T[i + tp];
-            const double av = -up - T[i - 1] + f4 * cc - T[i + 1] - dn;
-            const double rr = r[k];
-            sa[0] = sa[0] + rr * rr;
-            sa[1] = sa[1] + cc * av;
-            up = cc;
-            cc = dn;
-          }
-        }
-      }
+      if (full)
+        cg_phase_a<K, false>(q, ql, qr, nrow, f4, r, sa);
+      else
+        cg_phase_a<K, true>(q, ql, qr, nrow, f4, r, sa);
       allsum<2>(c, sa, s_red, [] {});
       sumr = sa[0];
       const double alpha = sumr / sa[1];                                                          // field.f90:415
       // ---- phase B: r -= alpha ap, sum of the new r.r; phi += alpha p while the barrier gathers    field.f90:417-441
       double sb1[1] = {0.0};
-      {
-        double up = T[i0 - tp], cc = T[i0];
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-          if (k < nrow) {
-            const int i = i0 + k * tp;
-            const double dn = T[i + tp];
-            const double av = -up - T[i - 1] + f4 * cc - T[i + 1] - dn;
-            const double rr = r[k] - alpha * av;
-            r[k] = rr;
-            sb1[0] = sb1[0] + rr * rr;
-            up = cc;
-            cc = dn;
-          }
-        }
-      }
+      if (full)
+        cg_phase_b<K, false>(q, ql, qr, nrow, f4, alpha, r, sb1);
+      else
+        cg_phase_b<K, true>(q, ql, qr, nrow, f4, alpha, r, sb1);
       publish();
       allsum<1>(c, sb1, s_red, [&] {
         // loads first, in two batches: one L2 round trip per batch instead of one per cell
@@ -408,7 +441,7 @@ __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__
 #pragma unroll
           for (int k = 0; k < (K + 1) / 2; k++) {
             const int kk = h * ((K + 1) / 2) + k;
-            if (kk < K && kk < nrow) phi[(size_t)kk * nthr] = ph[k] + alpha * T[i0 + kk * tp];
+            if (kk < K && kk < nrow) phi[(size_t)kk * nthr] = ph[k] + alpha * q[kk];
           }
         }
       });
@@ -431,22 +464,13 @@ __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__
         if (has_top) ht = __ldcg(&a.rg[g_top + l]);
 #pragma unroll
         for (int k = 0; k < K; k++)
-          if (k < nrow) {
-            const int i = i0 + k * tp;
-            T[i] = r[k] + beta * T[i];
-          }
-        if (has_bot) T[i_bot] = hb + beta * T[i_bot];
-        if (has_top) T[i_top] = ht + beta * T[i_top];
+          if (k < nrow) q[k] = r[k] + beta * q[k];
+        if (has_bot) q[-1] = hb + beta * q[-1];
+        if (has_top) q[nrow] = ht + beta * q[nrow];
         if (first_col && kindl == 0)
-          for (int k = 0; k < nrow; k++) {
-            const int i = i0 + k * tp - 1;
-            T[i] = __ldcg(&a.rg[pidx(P, lil, y0 + cyb + k) * 3 + l]) + beta * T[i];
-          }
+          for (int k = 0; k < nrow; k++) ql[k] = __ldcg(&a.rg[pidx(P, lil, y0 + cyb + k) * 3 + l]) + beta * ql[k];
         if (last_col && kindr == 0)
-          for (int k = 0; k < nrow; k++) {
-            const int i = i0 + k * tp + 1;
-            T[i] = __ldcg(&a.rg[pidx(P, lir, y0 + cyb + k) * 3 + l]) + beta * T[i];
-          }
+          for (int k = 0; k < nrow; k++) qr[k] = __ldcg(&a.rg[pidx(P, lir, y0 + cyb + k) * 3 + l]) + beta * qr[k];
       }
       __syncthreads();
       wall_halo(l);
@@ -477,15 +501,18 @@ bool cgp_plan(int nx, int nyl, int nsm, size_t smem_max, int *cbx_out, int *cby_
   int bcx = 0, bcy = 0, brl = 0;
   size_t bsm = 0;
   if (nsm > 160) nsm = 160;  // GMAX of the kernel
+  int fx = 0, fy = 0;        // WM_CGPLAN=cbx,cby forces a decomposition (experiments)
+  if (const char *v = getenv("WM_CGPLAN")) sscanf(v, "%d,%d", &fx, &fy);
   for (int cbx = 1; cbx <= nsm && (cbx * 4 <= nx || cbx == 1); cbx++)
     for (int cby = 1; cbx * cby <= nsm && cby <= nyl; cby++) {
       const int bw = (nx + cbx - 1) / cbx, bh = (nyl + cby - 1) / cby;
-      if (bw > CGP_T || 2 * (bw + bh) > 3 * CGP_T) continue;
+      if (fx > 0 && (cbx != fx || cby != fy)) continue;
+      if (bw > CGP_T) continue;
       int ng = CGP_T / bw;
       if (ng > bh) ng = bh;
       const int rl = (bh + ng - 1) / ng;
       if (rl > CGP_K) continue;
-      const size_t sm = (size_t)(bw + 2) * (bh + 2) * sizeof(double);
+      const size_t sm = (size_t)(bw + 2) * (size_t)((bh + 2) | 1) * sizeof(double);  // column-major tile, odd column pitch
       if (sm > smem_max) continue;
       // fewest cells per thread first; among equals the fewest CTAs (a cheaper barrier), then the shorter perimeter
       const long long score = (long long)rl * 100000000LL + (long long)cbx * cby * 10000 + (bw + bh);

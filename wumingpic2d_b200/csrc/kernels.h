@@ -102,6 +102,7 @@ struct CgpShared {            // one per rank, mapped by every other rank (CUDA 
 struct CgpArgs {
   int cbx, cby;               // block decomposition of the slab: cbx x cby CTAs
   int rl;                     // cells per thread (a vertical run)
+  int cp;                     // column pitch of the shared-memory tile: (rows of the tallest block + 2) | 1
   double *df;                 // in: df(1:3) warm start (+ ghost rows of the ring neighbours); out: df(1:3) interior
   const double *gkl;          // right-hand side before the f5 scaling
   double *rg;                 // AoS3 padded: r of the blocks' perimeter cells, ghost rows written by the ring neighbours

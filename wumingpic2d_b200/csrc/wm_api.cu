@@ -312,6 +312,7 @@ int cg_solve_persist(wm_ctx *c) {
   a.cbx = c->cgp_cbx;
   a.cby = c->cgp_cby;
   a.rl = c->cgp_rl;
+  a.cp = ((P.nyl + a.cby - 1) / a.cby + 2) | 1;
   a.df = c->f.df;
   a.gkl = c->f.gkl;
   a.rg = c->f.r;
@@ -1432,14 +1433,16 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
 }
 
 // ---------------------------------------------------------------- host-array (drop-in) calls
-int wm_host_step(wm_ctx *c, double *up, double *uf, int32_t *np2, int32_t *cumcnt) {
+int wm_host_steps(wm_ctx *c, double *up, double *uf, int32_t *np2, int32_t *cumcnt, int32_t nsteps) {
   WM(wm_upload_particles_sorted(c, up, np2, cumcnt));
   WM(wm_upload_field(c, uf));
-  WM(wm_step(c, 1));
+  WM(wm_step(c, nsteps));
   WM(wm_download_particles(c, up, np2, cumcnt));
   WM(wm_download_field(c, uf));
   return 0;
 }
+
+int wm_host_step(wm_ctx *c, double *up, double *uf, int32_t *np2, int32_t *cumcnt) { return wm_host_steps(c, up, uf, np2, cumcnt, 1); }
 
 int wm_host_particle__solv(wm_ctx *c, double *gp, const double *up, const double *uf, const int32_t *cumcnt, const int32_t *np2) {
   WM(wm_upload_particles_sorted(c, up, np2, cumcnt));
