@@ -50,9 +50,8 @@ enum {
 
 /* flags */
 enum {
-  WM_FLAG_EXACT_PUSH = 1, /* push arithmetic without FMA contraction, IEEE sqrt/div in the
+  WM_FLAG_EXACT_PUSH = 1  /* push arithmetic without FMA contraction, IEEE sqrt/div in the
                              reference's operation order: bit-identical to the CPU path   */
-  WM_FLAG_DETERMINISTIC = 2 /* reserved */
 };
 
 /* All scalars the reference passes to particle__init (common/particle.f90:18),
@@ -149,6 +148,9 @@ int wm_host_sort__bucket(wm_ctx *ctx, double *gp_out, const double *up_in, int32
 
 /* ---- diagnostics ------------------------------------------------------------------- */
 int wm_cg_iters(wm_ctx *ctx, int32_t out[3]);  /* CG iterations of the last solve, l=1..3 */
+/* FP64 vector peak of the device in TFLOP/s, measured with a DFMA loop (2 flop each) and CUDA events: the denominator of the
+ * FP64-pipe utilisation reported for the particle kernel. */
+int wm_fp64_peak(wm_ctx *ctx, double *tflops);
 /* Which implementation of cgm (common/field.f90:319-461) the next field solve uses: 0 = host loop of small kernels with NCCL
  * all-reduces / halo exchanges per iteration, 1 = one persistent cooperative kernel (one rank), 2 = the persistent kernel
  * with the ring exchange and the all-reduce done in the kernel over CUDA-IPC mapped peer memory.  WM_CG=0 forces 0. */

@@ -6,13 +6,15 @@ import pytest
                                     (40, 19), (8, 2), (5, 3), (208, 150), (4097, 511)])
 def test_plan_covers_the_slab(nx, nyl):
     """Every BASELINE slab (config 1: 256 x 64 per rank; 2: 4096 x 512; 3: 2048 x 512; 4: 16384 x 128) fits: at most 148 CTAs,
-    at most CGP_K x CGP_T = 14336 cells and 225 KB of shared memory per CTA, blocks at least 4 cells wide (wall rule)."""
+    a thread owns a vertical run of at most CGP_K = 16 cells, columns x row groups <= 1024 threads, the column-major tile
+    (odd column pitch) fits 225 KB of shared memory, blocks at least 4 cells wide (wall rule)."""
     import wumingpic2d_b200.api as A
-    cbx, cby, smem = A.cg_plan(nx, nyl)
+    cbx, cby, smem, rl = A.cg_plan(nx, nyl)
     assert 1 <= cbx * cby <= 148
     bw, bh = -(-nx // cbx), -(-nyl // cby)
-    assert bw * bh <= 14 * 1024
-    assert (bw + 2) * (bh + 2) * 8 == smem <= 227 * 1024 - 2048
+    assert 1 <= rl <= 16
+    assert bw * -(-bh // rl) <= 1024
+    assert (bw + 2) * ((bh + 2) | 1) * 8 == smem <= 227 * 1024 - 2048
     assert nx // cbx >= 4 or cbx == 1
     assert nyl // cby >= 1
 
@@ -20,6 +22,6 @@ def test_plan_covers_the_slab(nx, nyl):
 def test_plan_rejects_what_does_not_fit():
     import wumingpic2d_b200.api as A
     with pytest.raises(A.WmError):
-        A.cg_plan(2048, 2048)       # 4.2 M cells > 148 x 14336: the host-loop CG takes over
+        A.cg_plan(2048, 2048)       # 4.2 M cells > 148 x 1024 x 16: the host-loop CG takes over
     with pytest.raises(A.WmError):
         A.cg_plan(4096, 512, nsm=64)

@@ -50,7 +50,7 @@ EXPORTS = [
     "wm_particle_counts", "wm_particle__solv", "wm_field__ele_cur", "wm_boundary__curre",
     "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_boundary__injection",
     "wm_set_u_inject", "wm_set_xrange", "wm_append_particles", "wm_sort__bucket",
-    "wm_step", "wm_host_step", "wm_host_steps", "wm_cg_path", "wm_cg_plan", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
+    "wm_step", "wm_host_step", "wm_host_steps", "wm_cg_path", "wm_cg_plan", "wm_fp64_peak", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
     "wm_energy", "wm_gauss_residual", "wm_moments", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_ic_weibel", "wm_timing", "wm_synchronize", "wm_layout_rebuilds",
 ]
 
@@ -112,6 +112,7 @@ def load_library():
     lib.wm_host_sort__bucket.argtypes = [P, D, D, I32, I32]
     lib.wm_cg_iters.argtypes = [P, I32]
     lib.wm_cg_path.argtypes = [P, I32]
+    lib.wm_fp64_peak.argtypes = [P, D]
     lib.wm_cg_plan.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, I32]
     lib.wm_energy.argtypes = [P, D]
     lib.wm_gauss_residual.argtypes = [P, C.POINTER(C.c_double)]
@@ -287,6 +288,11 @@ class Context:
         out = (C.c_int32 * 3)()
         self._ck(self.lib.wm_cg_iters(self.h, out))
         return list(out)
+
+    def fp64_peak(self):
+        v = C.c_double()
+        self._ck(self.lib.wm_fp64_peak(self.h, C.byref(v)))
+        return v.value
 
     def cg_path(self):
         v = C.c_int32()

@@ -601,6 +601,23 @@ __global__ void __launch_bounds__(256) k_field_energy(const DevParams P, const d
   }
 }
 
+// ---- measured FP64 peak: 8 independent DFMA chains per thread, 16 warps per SM x 4 CTAs: the pipe's own rate
+//      ("to be measured by the builder with a DFMA loop")
+__global__ void __launch_bounds__(512) k_fp64_peak(double *out, int n, double a, double b) {
+  double v[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < n; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(v[i]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += v[i];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+void launch_fp64_peak(double *out, int nblocks, int n, cudaStream_t st) { k_fp64_peak<<<nblocks, 512, 0, st>>>(out, n, 0.999, 1e-3); }
+
 // ---------------------------------------------------------------- launch wrappers
 // grid of the reducing CG kernels: RED_BLOCKS by default (4 per SM); WM_CGBLOCKS overrides it up to the allocated maximum
 static int cg_blocks() {

@@ -37,10 +37,14 @@ int fail(const char *fmt, ...) {
     cudaError_t e_ = (x);                                                                      \
     if (e_ != cudaSuccess) return fail("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #x); \
   } while (0)
+// (a failure inside an open ncclGroupStart() must close the group before returning: ncclGroupEnd() is harmless otherwise)
 #define NC(x)                                                                                  \
   do {                                                                                         \
     ncclResult_t e_ = (x);                                                                     \
-    if (e_ != ncclSuccess) return fail("NCCL error %s at %s:%d (%s)", ncclGetErrorString(e_), __FILE__, __LINE__, #x); \
+    if (e_ != ncclSuccess) {                                                                   \
+      (void)ncclGroupEnd();                                                                    \
+      return fail("NCCL error %s at %s:%d (%s)", ncclGetErrorString(e_), __FILE__, __LINE__, #x); \
+    }                                                                                          \
   } while (0)
 #define WM(x)               \
   do {                      \
@@ -147,8 +151,8 @@ int alloc_particles(wm_ctx *c, long long need) {
     return fail("particle capacity %lld exceeded (need %lld); recreate the context with a larger wm_config.capacity", c->P.cap, need);
   }
   // slots per species: every cell segment carries slack (wm_internal.h cell_capacity); by
-  // Cauchy-Schwarz sum_c cap(n_c) <= need + 8 ncell + slack sqrt(2 ncell need)
-  auto bound = [&](float sl) { return (double)need + 8.0 * c->P.ncell + (double)sl * std::sqrt(2.0 * c->P.ncell * (double)need); };
+  // Cauchy-Schwarz sum_c cap(n_c) <= need + 12 ncell + slack sqrt(2 ncell need)
+  auto bound = [&](float sl) { return (double)need + 12.0 * c->P.ncell + (double)sl * std::sqrt(2.0 * c->P.ncell * (double)need); };  // cell_capacity adds up to 4 + ceil + 7
   long long cap = c->cfg.capacity > 0 ? c->cfg.capacity : (long long)std::ceil(1.1 * bound(c->slack)) + 4096;
   if (cap < need) return fail("wm_config.capacity %lld < particles per species %lld", cap, need);
   while (c->slack > 0.f && bound(c->slack) > (double)cap) c->slack = (c->slack > 0.5f) ? c->slack * 0.5f : 0.f;
@@ -624,7 +628,19 @@ extern "C" {
 const char *wm_last_error(void) { return g_err.c_str(); }
 int wm_version(void) { return 100; }
 
+static int wm_create_impl(const wm_config *g, wm_ctx **out, wm_ctx **partial);
 int wm_create(const wm_config *g, wm_ctx **out) {
+  wm_ctx *partial = nullptr;
+  const int e = wm_create_impl(g, out, &partial);
+  if (e && partial) {  // a failed allocation half way: give everything back (wm_destroy copes with null members)
+    const std::string keep = g_err;
+    wm_destroy(partial);
+    g_err = keep;
+    if (out) *out = nullptr;
+  }
+  return e;
+}
+static int wm_create_impl(const wm_config *g, wm_ctx **out, wm_ctx **partial) {
   if (!g || !out) return fail("wm_create: null argument");
   *out = nullptr;
   if (g->ndim != 6) return fail("wm_create: ndim must be 6 (x,y,ux,uy,uz,id)");
@@ -641,6 +657,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("wm_create: no CUDA device available (this library has no CPU fallback)");
   wm_ctx *c = new wm_ctx();
+  *partial = c;
   c->cfg = *g;
   if (const char *v = getenv("WM_SLACK")) c->slack = (float)atof(v);
   if (const char *v = getenv("WM_INPLACE")) c->inplace = atoi(v) != 0;
@@ -658,11 +675,8 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   CU(cudaSetDevice(c->dev));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, c->dev));
-  if (prop.major < 10) {
-    const int d = c->dev;
-    delete c;
-    return fail("wm_create: device %d is sm_%d%d; this library is built for sm_100a only", d, prop.major, prop.minor);
-  }
+  if (prop.major < 10)
+    return fail("wm_create: device %d is sm_%d%d; this library is built for sm_100a only", c->dev, prop.major, prop.minor);
   DevParams &P = c->P;
   P.nx = nx;
   P.nyl = nyl;
@@ -770,6 +784,7 @@ int wm_create(const wm_config *g, wm_ctx **out) {
   CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (auto &e : c->ev_call) CU(cudaEventCreate(&e));
   *out = c;
+  *partial = nullptr;
   return 0;
 }
 
@@ -797,9 +812,9 @@ int wm_destroy(wm_ctx *c) {
   cudaFree(c->cgp_bar);
   cudaFree(c->cgp_out);
   cudaFreeHost(c->h_cgp_out);
-  for (auto &e : c->ev_b) cudaEventDestroy(e);
-  cudaEventDestroy(c->ev_fork);
-  cudaEventDestroy(c->ev_join);
+  for (auto &e : c->ev_b) if (e) cudaEventDestroy(e);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   cudaFree(c->cnt_tail);
   cudaFree(c->tight);
   cudaFree(c->ovf);
@@ -811,11 +826,12 @@ int wm_destroy(wm_ctx *c) {
   cudaFreeHost(c->h_err);
   cudaFreeHost(c->h_cg);
   cudaFreeHost(c->h_cnt);
-  for (auto &e : c->ev_cg) cudaEventDestroy(e);
-  for (auto &e : c->ev) cudaEventDestroy(e);
-  for (auto &e : c->ev_call) cudaEventDestroy(e);
-  cudaStreamDestroy(c->st);
-  cudaStreamDestroy(c->st2);
+  for (auto &e : c->ev_cg) if (e) cudaEventDestroy(e);
+  for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+  for (auto &e : c->ev_call) if (e) cudaEventDestroy(e);
+  if (c->st) cudaStreamDestroy(c->st);
+  if (c->st2) cudaStreamDestroy(c->st2);
+  (void)cudaGetLastError();
   delete c;
   return 0;
 }
@@ -1308,8 +1324,15 @@ static int rebuild_layout(wm_ctx *c, int novf) {
   return 0;
 }
 
+static int wm_step_impl(wm_ctx *c, int32_t nsteps);
 int wm_step(wm_ctx *c, int32_t nsteps) {
-  WM(need_state(c, ST_SORTED, "wm_step"));
+  const int e = wm_step_impl(c, nsteps);
+  // a step that bailed out half way leaves the stores inconsistent: nothing but a fresh upload may follow
+  if (e && c && c->state == ST_SORTED && e != 2) c->state = ST_EMPTY;
+  return e;
+}
+static int wm_step_impl(wm_ctx *c, int32_t nsteps) {
+  if (need_state(c, ST_SORTED, "wm_step")) return 2;  // wrong state on entry: nothing was touched
   c->accl_valid = false;
   WM(set_device(c));
   const DevParams &P = c->P;
@@ -1467,6 +1490,30 @@ int wm_cg_iters(wm_ctx *c, int32_t out[3]) {
     WM(cg_collect(c));
   }
   for (int l = 0; l < 3; l++) out[l] = c->cg_ite[l];
+  return 0;
+}
+
+// FP64 vector peak of this device, measured: a DFMA loop (8 independent chains per thread, 64 warps per SM) timed with CUDA
+// events; flop = 2 per DFMA.  The denominator for the FP64-pipe figures of the fused particle kernel.
+int wm_fp64_peak(wm_ctx *c, double *tflops) {
+  if (!c || !tflops) return fail("wm_fp64_peak: null argument");
+  WM(set_device(c));
+  const int nb = c->nsm * 4, n = 1 << 15;
+  double *out = nullptr;
+  CU(cudaMalloc(&out, (size_t)nb * 512 * sizeof(double)));
+  launch_fp64_peak(out, nb, 1 << 10, c->st);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    CU(cudaEventRecord(c->ev_call[0], c->st));
+    launch_fp64_peak(out, nb, n, c->st);
+    CU(cudaEventRecord(c->ev_call[1], c->st));
+    CU(cudaEventSynchronize(c->ev_call[1]));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, c->ev_call[0], c->ev_call[1]));
+    best = std::min(best, ms);
+  }
+  CU(cudaFree(out));
+  *tflops = 2.0 * 8.0 * (double)n * 512.0 * nb / (best * 1e-3) / 1e12;
   return 0;
 }
 
@@ -1662,9 +1709,10 @@ int wm_ic_weibel(wm_ctx *c, uint64_t seed, int32_t n0, double vti, double vte, d
   if (n >= (1LL << 31) - 1) return fail("wm_ic_weibel: too many particles per species for one GPU");
   WM(alloc_particles(c, n));
   WM(ensure_migration_buffers(c, n));
+  if ((long long)cell_capacity(n0, c->slack) * P.ncell > P.cap)  // before anything is written (the kernel was queued first)
+    return fail("wm_ic_weibel: particle capacity %lld too small for %d cells x %d slots (segment slack)", P.cap, P.ncell, cell_capacity(n0, c->slack));
   WM(fill_dead(c, c->cur));
   launch_ic_weibel(P, c->soa[c->cur], c->cstart[c->cur], c->cnt[c->cur], seed, n0, vti, vte, t_ani, c->slack, c->st);
-  if ((long long)cell_capacity(n0, c->slack) * P.ncell > P.cap) return fail("wm_ic_weibel: particle capacity too small for the segment slack");
   // uniform field Bz = b0 (app.f90:388-399), df = 0
   const size_t ng = (size_t)P.pitch * (P.nyl + 4);
   std::vector<double> h(ng * 6, 0.0);
