@@ -183,6 +183,27 @@ int wm_moments(wm_ctx *ctx, double *mom);
  * test oracle; Box-Muller in device libm, so velocities agree to a few ulp only). */
 int wm_ic_weibel(wm_ctx *ctx, uint64_t seed, int32_t n0, double vti, double vte, double t_ani, double b0);
 
+/* ---- the applications' particle sources and initial conditions, generated on the device ------
+ * The distributions are the reference's, formula by formula; the random numbers come from the counter-based generator of
+ * wm_ic_weibel (the reference seeds from OS entropy and is not reproducible, utils/wuming_utils.f90:38-55). */
+/* Harris current sheet of proj/reconnection/app.f90:368-456: By = b0 tanh((x-x0)/lcs) + localized perturbation e1, nbg
+ * background pairs per cell between the walls + ncs*2*lcs sheet pairs per row with the sech^2 profile, drifts from jz/density.
+ * lcs in cells (the app's lcs*c/wpi), vti / vte as the app defines them (sigma*sqrt(2)). */
+int wm_ic_harris(wm_ctx *ctx, uint64_t seed, int32_t nbg, int32_t ncs, double lcs, double vti, double vte, double b0,
+                 double rtemp, double e1);
+/* Initial state of proj/shock/app.f90:406-470: n0 pairs per cell evenly spaced over the cells nxs+1..nxe-1 (the reference's
+ * cumcnt, app.f90:341-344; its positions start one cell further left, see gen_kernels.cu), Maxwellian boosted by the
+ * velocity profile, uniform B (b0, theta_bn, phi_bn in radians) with the motional E; sets the active range to nxs..nxe.
+ * wm_config.capacity must be set (the box fills up). */
+int wm_ic_shock(wm_ctx *ctx, uint64_t seed, int32_t n0, int32_t nxe, double v0, double vti, double vte, double b0,
+                double theta_bn, double phi_bn, double l_damp_ini);
+/* inject() (proj/shock/app.f90:685-850) and relocate() (:611-680) of the shock driver on the device, with the parameters of
+ * wm_ic_shock: new particles are appended to their cells' segments, the upstream field columns refreshed; relocate also moves
+ * nxe (wm_xrange tells where it is).  Call them where the driver does: after sort__bucket (proj/shock/app.f90:119-125). */
+int wm_shock_inject(wm_ctx *ctx, uint64_t seed, int32_t it);
+int wm_shock_relocate(wm_ctx *ctx, uint64_t seed, int32_t it);
+int wm_xrange(wm_ctx *ctx, int32_t out[2]);
+
 /* ---- measurement hooks ----------------------------------------------------------- */
 /* device milliseconds (CUDA events on the context's stream) accumulated by wm_step since the
  * last reset: [0] the fused push+deposit+boundary kernel alone, [1] field solve,

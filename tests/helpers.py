@@ -215,3 +215,55 @@ def em_wave_in_plasma_setup(m, nx=32, wpe=0.1, e0=1e-3):
     om_scheme = (np.arctan(s_ * (1 - g)) + np.arctan(s_ * g)) / dt
     om_text = np.sqrt(wpe ** 2 + (c * k) ** 2)
     return prm, w, uf, om_scheme, om_text
+
+
+def harris_params(nx, ny, nbg, ncs, nranks=1, mass_ratio=16.0, alpha=2.0, rtemp=0.2, lcs=0.5, cfl=0.5):
+    """Physical set-up of proj/reconnection/app.f90:292-311 (constants c = delx = 1, gfac = 0.501, cfl = 0.5 of
+    app.f90:64-68) as a parameter dict for the oracle / Context: adds vti, vte, b0, lcs_cells, n0 = nbg + ncs, and
+    np = n0 * nx (app.f90:249)."""
+    import math
+    c, delx, gfac = 1.0, 1.0, 0.501
+    r = [mass_ratio, 1.0]
+    delt = cfl * delx / c
+    vte = math.sqrt(rtemp) * c / (math.sqrt(1 + rtemp) * alpha)
+    vti = vte * math.sqrt(r[1] / r[0]) / math.sqrt(rtemp)
+    wpe = vte / delx / math.sqrt(2.0)
+    wpi = wpe * math.sqrt(r[1] / r[0])
+    wge = wpe / alpha
+    wgi = wge / mass_ratio
+    n0 = nbg + ncs
+    q = [+math.sqrt(r[0] / (4 * math.pi * n0 / delx ** 2)) * wpi, -math.sqrt(r[1] / (4 * math.pi * n0 / delx ** 2)) * wpe]
+    b0 = r[0] * c / q[0] * wgi
+    return dict(nx=nx, ny=ny, nranks=nranks, n0=n0, np=n0 * nx, nsp=2, delx=delx, delt=delt, c=c, gfac=gfac, q=q, r=r, b0=b0,
+                vti=vti, vte=vte, t_ani=1.0, nxgs=2, nygs=2, bc=O.BC_RECONNECTION, nbg=nbg, ncs=ncs, rtemp=rtemp,
+                lcs_cells=lcs * c / wpi)
+
+
+def shock_params(nx, ny, n0, nranks=1, u_inject=0.4, mass_ratio=1.0, sigma_e=0.1, omega_pe=0.1, v_the=0.05, v_thi=0.05,
+                 theta_bn=90.0, phi_bn=90.0, l_damp_ini=10.0, cap_factor=5.0):
+    """Physical set-up of proj/shock/app.f90:317-334 (c = delx = 1, cfl = 1, gfac = 0.501): u0 = -|u_inject|, v0 = u0 / gam0,
+    charges scaled by gam0, b0 from sigma_e; np = n_ppc * nx * 5 (app.f90:277)."""
+    import math
+    c, delx, gfac, cfl = 1.0, 1.0, 0.501, 1.0
+    delt = cfl * delx / c
+    u0 = -abs(u_inject)
+    gam0 = math.sqrt(1 + u0 * u0 / (c * c))
+    v0 = u0 / gam0
+    wpe = omega_pe
+    wge = omega_pe * math.sqrt(sigma_e)
+    wpi = wpe / math.sqrt(mass_ratio)
+    wgi = wge / mass_ratio
+    r = [mass_ratio, 1.0]
+    q = [+math.sqrt(gam0 * r[0] / (4 * math.pi * n0 / delx ** 2)) * wpi, -math.sqrt(gam0 * r[1] / (4 * math.pi * n0 / delx ** 2)) * wpe]
+    b0 = r[0] * c / q[0] * wgi * gam0
+    return dict(nx=nx, ny=ny, nranks=nranks, n0=n0, np=int(n0 * nx * cap_factor), nsp=2, delx=delx, delt=delt, c=c, gfac=gfac,
+                q=q, r=r, b0=b0, vti=v_thi, vte=v_the, t_ani=1.0, nxgs=2, nygs=2, bc=O.BC_SHOCK, u0=u0, v0=v0,
+                theta=math.radians(theta_bn), phi=math.radians(phi_bn), l_damp=l_damp_ini)
+
+
+def load_state_into_oracle(w, up, np2, cumcnt, uf, rank=0):
+    """A sorted device state (download_particles + download_field) becomes the oracle's state (up, gp, np2, cumcnt, uf)."""
+    for which, a in ((O.UP, up), (O.GP, up), (O.NP2, np2), (O.CUMCNT, cumcnt), (O.UF, uf)):
+        dst = w.array(rank, which)
+        assert dst.shape == a.shape, (which, dst.shape, a.shape)
+        dst[...] = a

@@ -50,7 +50,7 @@ EXPORTS = [
     "wm_particle_counts", "wm_particle__solv", "wm_field__ele_cur", "wm_boundary__curre",
     "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_boundary__injection",
     "wm_set_u_inject", "wm_set_xrange", "wm_append_particles", "wm_sort__bucket",
-    "wm_step", "wm_host_step", "wm_host_steps", "wm_cg_path", "wm_cg_plan", "wm_fp64_peak", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
+    "wm_step", "wm_host_step", "wm_host_steps", "wm_cg_path", "wm_cg_plan", "wm_fp64_peak", "wm_ic_harris", "wm_ic_shock", "wm_shock_inject", "wm_shock_relocate", "wm_xrange", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
     "wm_energy", "wm_gauss_residual", "wm_moments", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_ic_weibel", "wm_timing", "wm_synchronize", "wm_layout_rebuilds",
 ]
 
@@ -121,6 +121,11 @@ def load_library():
     lib.wm_mom_calc__nvt.argtypes = [P, D]
     lib.wm_boundary__mom.argtypes = [P, D]
     lib.wm_ic_weibel.argtypes = [P, C.c_uint64, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]
+    lib.wm_ic_harris.argtypes = [P, C.c_uint64, C.c_int32, C.c_int32] + [C.c_double] * 6
+    lib.wm_ic_shock.argtypes = [P, C.c_uint64, C.c_int32, C.c_int32] + [C.c_double] * 7
+    lib.wm_shock_inject.argtypes = [P, C.c_uint64, C.c_int32]
+    lib.wm_shock_relocate.argtypes = [P, C.c_uint64, C.c_int32]
+    lib.wm_xrange.argtypes = [P, I32]
     lib.wm_timing.argtypes = [P, D, C.POINTER(C.c_int64), C.c_int32]
     lib.wm_layout_rebuilds.argtypes = [P, C.POINTER(C.c_int64)]
     _lib = lib
@@ -325,6 +330,20 @@ class Context:
 
     def ic_weibel(self, seed, n0, vti, vte, t_ani, b0):
         self._ck(self.lib.wm_ic_weibel(self.h, seed, n0, vti, vte, t_ani, b0))
+
+    def ic_harris(self, seed, nbg, ncs, lcs, vti, vte, b0, rtemp, e1=0.12):
+        self._ck(self.lib.wm_ic_harris(self.h, seed, nbg, ncs, lcs, vti, vte, b0, rtemp, e1))
+
+    def ic_shock(self, seed, n0, nxe, v0, vti, vte, b0, theta_bn, phi_bn, l_damp_ini):
+        self._ck(self.lib.wm_ic_shock(self.h, seed, n0, nxe, v0, vti, vte, b0, theta_bn, phi_bn, l_damp_ini))
+
+    def shock_inject(self, seed, it): self._ck(self.lib.wm_shock_inject(self.h, seed, it))
+    def shock_relocate(self, seed, it): self._ck(self.lib.wm_shock_relocate(self.h, seed, it))
+
+    def xrange(self):
+        out = (C.c_int32 * 2)()
+        self._ck(self.lib.wm_xrange(self.h, out))
+        return out[0], out[1]
 
     def rebuilds(self):
         n = C.c_int64()

@@ -15,7 +15,8 @@ void launch_pass2(const DevParams &P, const PartSoA &src, const PartSoA &dst, co
                   cudaStream_t st);
 int scan_scratch_ints(int n);
 // exclusive scan of cell_capacity(in[c], sl): sl = 0 gives the tight offsets (cumcnt), sl > 0 the segment offsets
-int launch_scan(const int *in, int *out, int *scratch, int n, float sl, cudaStream_t st);
+// floor_n: with slack, a cell is laid out as if it held at least floor_n particles (cells a moving source will fill)
+int launch_scan(const int *in, int *out, int *scratch, int n, float sl, cudaStream_t st, int floor_n = 0);
 void launch_incoming_tag(const DevParams &P, const double *rec, int n, int isp, const int *spv, int *gcnt, int *rank,
                          unsigned *err, cudaStream_t st);
 void launch_incoming_scatter(const DevParams &P, const double *rec, int n, int isp, const int *spv, const int *cstart_new,
@@ -33,7 +34,8 @@ void launch_relayout_soa(const DevParams &P, const PartSoA &src, const int *csta
                          const int *cstart_dst, size_t so, unsigned *err, cudaStream_t st);
 void launch_incoming_append(const DevParams &P, const double *rec, int n, int isp, const int *cstart, int *cnt_tail,
                             const PartSoA &dst, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
-                            cudaStream_t st);
+                            cudaStream_t st, const int *n_dev = nullptr);
+void launch_check_counts(const int *cnt, int n, const int lim[4], unsigned *err, cudaStream_t st);
 // in-place sort: append the records staged by k_fused<INPLACE> to their new segments, retire vacated slots;
 // rim_only: k_fused_sm<TAIL> served the tile's own cells, only the window rim is left (k_place_rim)
 void launch_place(const DevParams &P, const double *stage, const uint32_t *tag, const PartSoA &dst, const int *cstart,
@@ -55,6 +57,26 @@ void launch_charge_density(const DevParams &P, const PartSoA &src, const int *cs
 void launch_gauss(const DevParams &P, const double *uf, const double *rho, unsigned long long *out, cudaStream_t st);
 void launch_moments(const DevParams &P, const PartSoA &src, PView<double> keyx, const int *cstart, double *mom,
                     cudaStream_t st);
+
+// ---- generators of the applications' particle sources and initial fields (gen_kernels.cu)
+struct GenParams {
+  int nxgs, nygs, nxg, nyg;        // global grid: first cell, cells
+  double delx, delt, c;
+  double q[WM_NSP_MAX];
+  double vti, vte, b0;
+  // Harris sheet (proj/reconnection)
+  int nbg, ncs;
+  long long npr, ibg;              // pairs per row, of which background
+  double lcs, rtemp, e1;
+  // shock (proj/shock)
+  int n0, it;
+  double v0, theta, phi, l_damp;
+};
+void launch_gen_harris(const DevParams &P, const GenParams &g, uint64_t seed, double *stage0, double *stage1, double *uf,
+                       cudaStream_t st);
+void launch_gen_shock(const DevParams &P, const GenParams &g, uint64_t seed, int kind, int nxe, const int *rowoff, double *stage0,
+                      double *stage1, cudaStream_t st);
+void launch_field_shock(const DevParams &P, const GenParams &g, int kind, int nxe, double *uf, cudaStream_t st);
 
 // ---- fields
 struct FieldBufs {

@@ -512,12 +512,12 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
   return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partial(const int *__restrict__ in, int *__restrict__ bsum, int n, float sl) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partial(const int *__restrict__ in, int *__restrict__ bsum, int n, float sl, int floor_n) {
   const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int s = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++)
-    if (base + k < n) s += cell_capacity(in[base + k], sl);
+    if (base + k < n) s += cell_capacity(sl > 0.f ? max(in[base + k], floor_n) : in[base + k], sl);
   int tot;
   block_exclusive_scan(s, &tot);
   if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
@@ -542,12 +542,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_bsums(int *bsum, int nb) 
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const int *__restrict__ in, const int *__restrict__ bsum,
-                                                             int *__restrict__ out, int n, float sl) {
+                                                             int *__restrict__ out, int n, float sl, int floor_n) {
   const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS], s = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
-    v[k] = (base + k < n) ? cell_capacity(in[base + k], sl) : 0;
+    v[k] = (base + k < n) ? cell_capacity(sl > 0.f ? max(in[base + k], floor_n) : in[base + k], sl) : 0;
     s += v[k];
   }
   int tot;
@@ -931,10 +931,20 @@ __global__ void k_relayout_soa(const DevParams P, const PartSoA src, const int *
 
 // in-place sort: records arriving from a neighbour rank (or from the overflow list after a rebuild
 // is NOT needed: see wm_api.cu) are appended at the tail of their cell's segment
-__global__ void k_incoming_append(const DevParams P, const double *__restrict__ rec, int n, int isp,
+// n_dev != nullptr: the number of records is *n_dev (a count that arrived with the records); more than n is an error (the
+// message was sized from the previous step's count and got truncated)
+__global__ void k_incoming_append(const DevParams P, const double *__restrict__ rec, int n, const int *__restrict__ n_dev, int isp,
                                   const int *__restrict__ cstart, int *cnt_tail, const PartSoA dst, double *ovf, int *ovfsp,
                                   int *ovfcnt, int ovfcap, unsigned *err) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) {
+    const int m = *n_dev;
+    if (m > n) {
+      if (s == 0) atomicOr(err, ERR_SENDBUF);
+    } else {
+      n = m;
+    }
+  }
   if (s >= n) return;
   const double *r = rec + (size_t)s * 6;
   const int li = __double2int_rz(r[0]) - P.nxgs, lj = __double2int_rz(r[1]) - P.nys;
@@ -1258,12 +1268,12 @@ void launch_pass2(const DevParams &P, const PartSoA &src, const PartSoA &dst, co
 
 int scan_scratch_ints(int n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
 
-int launch_scan(const int *in, int *out, int *scratch, int n, float sl, cudaStream_t st) {
+int launch_scan(const int *in, int *out, int *scratch, int n, float sl, cudaStream_t st, int floor_n) {
   const int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
   if (nb > SCAN_TILE) return 1;
-  k_scan_partial<<<nb, SCAN_THREADS, 0, st>>>(in, scratch, n, sl);
+  k_scan_partial<<<nb, SCAN_THREADS, 0, st>>>(in, scratch, n, sl, floor_n);
   k_scan_bsums<<<1, SCAN_THREADS, 0, st>>>(scratch, nb);
-  k_scan_final<<<nb, SCAN_THREADS, 0, st>>>(in, scratch, out, n, sl);
+  k_scan_final<<<nb, SCAN_THREADS, 0, st>>>(in, scratch, out, n, sl, floor_n);
   return 0;
 }
 
@@ -1295,9 +1305,17 @@ void launch_relayout_soa(const DevParams &P, const PartSoA &src, const int *csta
 }
 void launch_incoming_append(const DevParams &P, const double *rec, int n, int isp, const int *cstart, int *cnt_tail,
                             const PartSoA &dst, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
-                            cudaStream_t st) {
+                            cudaStream_t st, const int *n_dev) {
   if (n > 0)
-    k_incoming_append<<<(n + 255) / 256, 256, 0, st>>>(P, rec, n, isp, cstart, cnt_tail, dst, ovf, ovfsp, ovfcnt, ovfcap, err);
+    k_incoming_append<<<(n + 255) / 256, 256, 0, st>>>(P, rec, n, n_dev, isp, cstart, cnt_tail, dst, ovf, ovfsp, ovfcnt, ovfcap, err);
+}
+// the sender's side of the same check: more leavers than the message holds
+__global__ void k_check_counts(const int *__restrict__ cnt, int n, int lim0, int lim1, int lim2, int lim3, unsigned *err) {
+  const int lim[4] = {lim0, lim1, lim2, lim3};
+  if (threadIdx.x < n && cnt[threadIdx.x] > lim[threadIdx.x]) atomicOr(err, ERR_SENDBUF);
+}
+void launch_check_counts(const int *cnt, int n, const int lim[4], unsigned *err, cudaStream_t st) {
+  k_check_counts<<<1, 32, 0, st>>>(cnt, n, lim[0], lim[1], lim[2], lim[3], err);
 }
 void launch_place(const DevParams &P, const double *stage, const uint32_t *tag, const PartSoA &dst, const int *cstart,
                   int *cnt_new, const int *tilebase, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -73,6 +74,11 @@ struct wm_ctx {
   int *ovfsp = nullptr, *ovfcnt = nullptr, *ovfrank = nullptr, *h_ovf = nullptr;
   int ovfcap = 0;
   float slack = 6.0f;                    // segment slack in std deviations of the count change (WM_SLACK)
+  int cell_floor = 0;                    // every segment is laid out for at least this many particles (shock: upstream cells fill up)
+  GenParams gen{};                       // parameters of the device-side particle sources (wm_ic_shock -> wm_shock_inject / _relocate)
+  int *d_rowoff = nullptr;               // [nyl + 1] per-row record offsets of a generator call
+  double *gen_stage = nullptr;           // records of one inject / relocate call, both species
+  long long gen_stage_cap = 0;
   bool inplace = true;                   // WM_INPLACE=0 selects the tag + scatter sort for wm_step
   bool cg3 = false;                      // WM_CG3=1: three-kernel CG iteration (k_cg_ap, k_cg_update, k_cg_pupdate)
   bool rimplace = true;                  // k_place_rim after k_fused_sm<TAIL> (WM_RIMPLACE=0: the general k_place)
@@ -89,6 +95,8 @@ struct wm_ctx {
   int *in_rank = nullptr;                      // [2*nsp*sendcap]
   int *h_cnt = nullptr;                        // pinned [4*nsp]
   int n_in[2][WM_NSP_MAX] = {{0}};
+  bool mig_prev = false;                       // h_cnt holds the counts of the previous step's exchange
+  int mig_fast = 1;                            // WM_MIGSYNC=1 keeps the count-then-payload protocol with its host round trip
   // fields
   FieldBufs f{};
   double *rowtmp = nullptr;  // 2 ghost rows x 6 comps (multi-rank fold)
@@ -525,6 +533,43 @@ int migrate(wm_ctx *c, bool inplace = false) {
   if (P.nsize == 1) return 0;
   if (!c->comm) return fail("nsize > 1 but wm_comm_init has not been called");
   const int nsp = P.nsp;
+  if (inplace && c->mig_fast && c->mig_prev && nsp <= 2) {
+    // No host round trip: the counts travel WITH the payload in one NCCL group.  A message is sized from the count the same
+    // channel carried in the previous step (both ends know it: the sender sent it, the receiver got it in the header), twice
+    // that + 4096 records; the counts of this step are checked on the device (a truncated message is an error, not a loss)
+    // and copied to the host behind the kernels for the next step's sizes (wm_step synchronises at the end of every step).
+    int ms[4], mr[4];  // [dir * nsp + isp]: send down / up, receive from nup (their down-going) / ndown (their up-going)
+    for (int k = 0; k < 2 * nsp; k++) {
+      ms[k] = (int)std::min<long long>(c->sendcap, 2LL * c->h_cnt[k] + 4096);
+      mr[k] = (int)std::min<long long>(c->sendcap, 2LL * c->h_cnt[2 * nsp + k] + 4096);
+    }
+    for (int k = 2 * nsp; k < 4; k++) ms[k] = mr[k] = 0;
+    NC(ncclGroupStart());
+    NC(ncclSend(c->sendcnt, nsp, ncclInt, c->ndown, c->comm, c->st));
+    NC(ncclSend(c->sendcnt + nsp, nsp, ncclInt, c->nup, c->comm, c->st));
+    NC(ncclRecv(c->recvcnt, nsp, ncclInt, c->nup, c->comm, c->st));
+    NC(ncclRecv(c->recvcnt + nsp, nsp, ncclInt, c->ndown, c->comm, c->st));
+    for (int isp = 0; isp < nsp; isp++) {
+      const size_t off = (size_t)isp * c->sendcap * 6;
+      NC(ncclSend(c->send[0] + off, (size_t)ms[isp] * 6, ncclDouble, c->ndown, c->comm, c->st));
+      NC(ncclSend(c->send[1] + off, (size_t)ms[nsp + isp] * 6, ncclDouble, c->nup, c->comm, c->st));
+      NC(ncclRecv(c->recv[0] + off, (size_t)mr[isp] * 6, ncclDouble, c->nup, c->comm, c->st));
+      NC(ncclRecv(c->recv[1] + off, (size_t)mr[nsp + isp] * 6, ncclDouble, c->ndown, c->comm, c->st));
+    }
+    NC(ncclGroupEnd());
+    launch_check_counts(c->sendcnt, 2 * nsp, ms, c->d_err, c->st);
+    for (int d = 0; d < 2; d++)
+      for (int isp = 0; isp < nsp; isp++) {
+        const size_t off = (size_t)isp * c->sendcap;
+        launch_incoming_append(P, c->recv[d] + off * 6, mr[d * nsp + isp], isp, c->cstart[c->cur], c->cnt_tail, c->soa[c->cur], c->ovf,
+                               c->ovfsp, c->ovfcnt, c->ovfcap, c->d_err, c->st, c->recvcnt + d * nsp + isp);
+        c->launches++;
+      }
+    c->launches++;
+    CU(cudaMemcpyAsync(c->h_cnt, c->sendcnt, 2 * nsp * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(c->h_cnt + 2 * nsp, c->recvcnt, 2 * nsp * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    return 0;
+  }
   // counts first (MPI_SENDRECV of cnt, :174,:183)
   NC(ncclGroupStart());
   NC(ncclSend(c->sendcnt, nsp, ncclInt, c->ndown, c->comm, c->st));
@@ -551,6 +596,7 @@ int migrate(wm_ctx *c, bool inplace = false) {
     c->n_in[1][isp] = rd;
   }
   NC(ncclGroupEnd());
+  c->mig_prev = inplace;  // h_cnt = {send down, send up, recv from nup, recv from ndown} of this step
   for (int d = 0; d < 2; d++)
     for (int isp = 0; isp < nsp; isp++) {
       const size_t off = (size_t)isp * c->sendcap;
@@ -582,7 +628,7 @@ int scatter_arrivals(wm_ctx *c, int dstbuf) {
 int scan_counts(wm_ctx *c, int dstbuf) {
   for (int isp = 0; isp < c->P.nsp; isp++) {
     if (launch_scan(c->gcnt + (size_t)isp * c->P.ncell, c->cstart[dstbuf] + (size_t)isp * (c->P.ncell + 1), c->scan_scratch,
-                    c->P.ncell, c->slack, c->st))
+                    c->P.ncell, c->slack, c->st, c->cell_floor))
       return fail("grid too large for the prefix scan");
     c->launches += 3;
   }
@@ -666,6 +712,7 @@ static int wm_create_impl(const wm_config *g, wm_ctx **out, wm_ctx **partial) {
   if (const char *v = getenv("WM_CG3")) c->cg3 = atoi(v) != 0;
   if (const char *v = getenv("WM_OVERLAP")) c->overlap = atoi(v) != 0;
   if (const char *v = getenv("WM_CG")) c->cg_mode = atoi(v);
+  if (const char *v = getenv("WM_MIGSYNC")) c->mig_fast = atoi(v) == 0;
   if (g->flags & WM_FLAG_EXACT_PUSH) c->inplace = false;  // the exact path keeps the reference's two-pass structure
   if (g->device >= 0) {
     c->dev = g->device;
@@ -808,6 +855,8 @@ int wm_destroy(wm_ctx *c) {
     cudaFree(p);
   for (int k = 0; k < c->cgp_nopen; k++) cudaIpcCloseMemHandle(c->cgp_ipc_open[k]);
   cudaFree(c->cgp_sh_mine);
+  cudaFree(c->d_rowoff);
+  cudaFree(c->gen_stage);
   cudaFree(c->cgp_partial);
   cudaFree(c->cgp_bar);
   cudaFree(c->cgp_out);
@@ -955,19 +1004,10 @@ static int stage_rows_h2d(wm_ctx *c, const double *up, const int32_t *np2, doubl
   return 0;
 }
 
-int wm_upload_particles(wm_ctx *c, const double *up, const int32_t *np2) {
-  if (!c || !up || !np2) return fail("wm_upload_particles: null argument");
-  c->accl_valid = false;
-  WM(set_device(c));
-  long long n[WM_NSP_MAX];
-  WM(count_host(c, np2, n));
-  long long nmax = 0;
-  for (int isp = 0; isp < c->P.nsp; isp++) nmax = std::max(nmax, n[isp]);
-  WM(alloc_particles(c, nmax));
-  WM(ensure_migration_buffers(c, nmax));
+// tight AoS records in `stage` (species 0 first, then species 1), any order -> the cell-sorted store: sort__bucket on the device
+// (histogram by global atomics, prefix scan into segments with slack, scatter)                 common/sort.f90:36-82
+static int bucket_stage(wm_ctx *c, double *stage, const long long n[WM_NSP_MAX], const char *who) {
   const DevParams &P = c->P;
-  double *stage = c->pbuf[c->cur ^ 1];
-  WM(stage_rows_h2d(c, up, np2, stage, n));
   WM(zero_sort_state(c));
   int *rank = reinterpret_cast<int *>(c->tag);
   long long off = 0;
@@ -982,9 +1022,25 @@ int wm_upload_particles(wm_ctx *c, const double *up, const int32_t *np2) {
     launch_incoming_scatter(P, stage + off * 6, (int)n[isp], isp, nullptr, c->cstart[c->cur], rank + off, c->soa[c->cur], c->d_err, c->st);
     off += n[isp];
   }
-  WM(check_errors(c, "wm_upload_particles"));
+  c->launches += 2 * P.nsp;
+  WM(check_errors(c, who));
   c->state = ST_SORTED;
   return 0;
+}
+
+int wm_upload_particles(wm_ctx *c, const double *up, const int32_t *np2) {
+  if (!c || !up || !np2) return fail("wm_upload_particles: null argument");
+  c->accl_valid = false;
+  WM(set_device(c));
+  long long n[WM_NSP_MAX];
+  WM(count_host(c, np2, n));
+  long long nmax = 0;
+  for (int isp = 0; isp < c->P.nsp; isp++) nmax = std::max(nmax, n[isp]);
+  WM(alloc_particles(c, nmax));
+  WM(ensure_migration_buffers(c, nmax));
+  double *stage = c->pbuf[c->cur ^ 1];
+  WM(stage_rows_h2d(c, up, np2, stage, n));
+  return bucket_stage(c, stage, n, "wm_upload_particles");
 }
 
 int wm_upload_particles_sorted(wm_ctx *c, const double *up, const int32_t *np2, const int32_t *cumcnt) {
@@ -1722,6 +1778,204 @@ int wm_ic_weibel(wm_ctx *c, uint64_t seed, int32_t n0, double vti, double vte, d
   CU(cudaStreamSynchronize(c->st));
   CU(cudaGetLastError());
   c->state = ST_SORTED;
+  return 0;
+}
+
+// ---------------------------------------------------------------- device-side particle sources
+static void gen_common(wm_ctx *c, GenParams &g) {
+  g.nxgs = c->cfg.nxgs;
+  g.nygs = c->cfg.nygs;
+  g.nxg = c->cfg.nxge - c->cfg.nxgs + 1;
+  g.nyg = c->cfg.nyge - c->cfg.nygs + 1;
+  g.delx = c->cfg.delx;
+  g.delt = c->cfg.delt;
+  g.c = c->cfg.c;
+  for (int s = 0; s < WM_NSP_MAX; s++) g.q[s] = c->cfg.q[s];
+}
+
+int wm_ic_harris(wm_ctx *c, uint64_t seed, int32_t nbg, int32_t ncs, double lcs, double vti, double vte, double b0, double rtemp,
+                 double e1) {
+  if (!c) return fail("wm_ic_harris: null context");
+  if (c->P.nsp != 2) return fail("wm_ic_harris: two species (ions, electrons) expected");
+  if (nbg < 0 || ncs < 0 || !(lcs > 0)) return fail("wm_ic_harris: bad arguments");
+  c->accl_valid = false;
+  WM(set_device(c));
+  const DevParams &P = c->P;
+  GenParams g{};
+  gen_common(c, g);
+  g.nbg = nbg;
+  g.ncs = ncs;
+  g.lcs = lcs;
+  g.vti = vti;
+  g.vte = vte;
+  g.b0 = b0;
+  g.rtemp = rtemp;
+  g.e1 = e1;
+  g.npr = (long long)nbg * (g.nxg - 1) + (long long)(ncs * 2 * lcs);  // np2 = nbg*(nxge-nxgs) + ncs*2*lcs   app.f90:313
+  g.ibg = (long long)nbg * (g.nxg - 3);                               // ibg = nbg*(nxge-nxgs-2)            app.f90:422
+  const long long n = g.npr * P.nyl;
+  if (g.npr > c->cfg.np) return fail("wm_ic_harris: %lld particles per row > np = %d", g.npr, c->cfg.np);
+  if (n >= (1LL << 31) - 1) return fail("wm_ic_harris: too many particles per species for one GPU");
+  WM(alloc_particles(c, n));
+  WM(ensure_migration_buffers(c, n));
+  if (2 * n > (long long)P.cap * P.nsp) return fail("wm_ic_harris: capacity too small for the staging area");
+  double *stage = c->pbuf[c->cur ^ 1];
+  launch_gen_harris(P, g, seed, stage, stage + n * 6, c->f.uf, c->st);
+  const size_t ng = (size_t)P.pitch * (P.nyl + 4);
+  CU(cudaMemsetAsync(c->f.df, 0, ng * 6 * sizeof(double), c->st));
+  c->launches += 2;
+  const long long nn[WM_NSP_MAX] = {n, n};
+  return bucket_stage(c, stage, nn, "wm_ic_harris");
+}
+
+static int gen_rowoff(wm_ctx *c, const std::vector<int> &cnt, int *total) {
+  std::vector<int> off(cnt.size() + 1, 0);
+  for (size_t k = 0; k < cnt.size(); k++) off[k + 1] = off[k] + cnt[k];
+  *total = off.back();
+  if (!c->d_rowoff) CU(cudaMalloc(&c->d_rowoff, (size_t)(c->P.nyl + 1) * sizeof(int)));
+  CU(cudaMemcpyAsync(c->d_rowoff, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
+  CU(cudaStreamSynchronize(c->st));  // `off` goes out of scope
+  return 0;
+}
+
+int wm_ic_shock(wm_ctx *c, uint64_t seed, int32_t n0, int32_t nxe, double v0, double vti, double vte, double b0, double theta_bn,
+                double phi_bn, double l_damp_ini) {
+  if (!c) return fail("wm_ic_shock: null context");
+  if (c->P.bc != WM_BC_SHOCK || c->P.nsp != 2) return fail("wm_ic_shock: needs a WM_BC_SHOCK context with two species");
+  if (n0 < 1 || nxe - c->cfg.nxgs < 4 || nxe > c->cfg.nxge || !(std::fabs(v0) < c->cfg.c)) return fail("wm_ic_shock: bad arguments");
+  c->accl_valid = false;
+  WM(set_device(c));
+  const DevParams &P = c->P;
+  GenParams &g = c->gen;
+  g = GenParams{};
+  gen_common(c, g);
+  g.n0 = n0;
+  g.it = 0;
+  g.v0 = v0;
+  g.vti = vti;
+  g.vte = vte;
+  g.b0 = b0;
+  g.theta = theta_bn;
+  g.phi = phi_bn;
+  g.l_damp = l_damp_ini;
+  const int npr = n0 * (nxe - c->cfg.nxgs - 1);  // np2 = n0*(nxe-nxs-1)   proj/shock/app.f90:330
+  const long long n = (long long)npr * P.nyl;
+  if (!c->cfg.capacity) return fail("wm_ic_shock: set wm_config.capacity (the box fills up: the reference sizes rows for n_ppc*nx*5 particles)");
+  c->cell_floor = n0;  // upstream cells are laid out for the density they are going to hold
+  WM(alloc_particles(c, n));
+  WM(ensure_migration_buffers(c, (long long)n0 * P.nx * P.nyl));
+  std::vector<int> cnt(P.nyl, npr);
+  int total = 0;
+  WM(gen_rowoff(c, cnt, &total));
+  double *stage = c->pbuf[c->cur ^ 1];
+  launch_field_shock(P, g, 0, nxe, c->f.uf, c->st);
+  launch_gen_shock(P, g, seed, 0, nxe, c->d_rowoff, stage, stage + n * 6, c->st);
+  const size_t ng = (size_t)P.pitch * (P.nyl + 4);
+  CU(cudaMemsetAsync(c->f.df, 0, ng * 6 * sizeof(double), c->st));
+  c->launches += 2;
+  const long long nn[WM_NSP_MAX] = {n, n};
+  WM(bucket_stage(c, stage, nn, "wm_ic_shock"));
+  WM(wm_set_xrange(c, c->cfg.nxgs, nxe));
+  return 0;
+}
+
+// records of one inject / relocate call -> their cells' segments (as wm_append_particles, without the host copy)
+static int gen_append(wm_ctx *c, int total, const char *who) {
+  const DevParams &P = c->P;
+  CU(cudaMemsetAsync(c->ovfcnt, 0, sizeof(int), c->st));
+  for (int isp = 0; isp < 2; isp++)
+    launch_incoming_append(P, c->gen_stage + (size_t)isp * total * 6, total, isp, c->cstart[c->cur], c->cnt[c->cur], c->soa[c->cur],
+                           c->ovf, c->ovfsp, c->ovfcnt, c->ovfcap, c->d_err, c->st);
+  launch_clamp_counts(P, c->cstart[c->cur], c->cnt[c->cur], c->st);
+  c->launches += 3;
+  CU(cudaMemcpyAsync(c->h_ovf, c->ovfcnt, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  WM(check_errors(c, who));
+  if (*c->h_ovf > 0) WM(rebuild_layout(c, *c->h_ovf));
+  return 0;
+}
+
+static int gen_stage_reserve(wm_ctx *c, long long records) {
+  if (records <= c->gen_stage_cap) return 0;
+  if (c->gen_stage) CU(cudaFree(c->gen_stage));
+  c->gen_stage = nullptr;
+  c->gen_stage_cap = records + records / 4 + 1024;
+  CU(cudaMalloc(&c->gen_stage, (size_t)c->gen_stage_cap * 2 * 6 * sizeof(double)));
+  return 0;
+}
+
+// inject() of proj/shock/app.f90:685-850 on the device: n0 |v0| delt delx ny particles per species enter through the right-hand
+// boundary (the fractional part by a random number), spread evenly over all rows of the ring with the remainder on random
+// rows; new upstream field values in the columns nxe - 1, nxe.  `it` = time step (keys the random numbers and the ids).
+int wm_shock_inject(wm_ctx *c, uint64_t seed, int32_t it) {
+  WM(need_state(c, ST_SORTED, "wm_shock_inject"));
+  if (c->P.bc != WM_BC_SHOCK || c->gen.n0 < 1) return fail("wm_shock_inject: call wm_ic_shock first");
+  WM(set_device(c));
+  const DevParams &P = c->P;
+  GenParams g = c->gen;
+  g.it = it;
+  const int nxe = c->cfg.nxgs + c->nxa - 1;
+  const int ny = g.nyg;
+  // (1) total over the system, (2)+(3) equal shares, remainders on random rows: one level here (rows of the whole ring),
+  // which gives every row floor or floor + 1 particles like the reference's two-level split
+  auto h64 = [](uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+  };
+  const double pflux = g.n0 * std::fabs(g.v0) * g.delt * g.delx * ny;
+  int nginj = (int)pflux;
+  const double u = ((double)(h64(seed ^ h64((uint64_t)it * 2 + 1)) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  if (u < pflux - (int)pflux) nginj++;
+  const int base = nginj / ny, rem = nginj % ny;
+  // the `rem` rows with the smallest hash get one more
+  std::vector<std::pair<uint64_t, int>> key(ny);
+  for (int j = 0; j < ny; j++) key[j] = {h64(seed ^ h64(((uint64_t)it << 20) + (uint64_t)j + 77)), j};
+  std::vector<int> extra(ny, 0);
+  if (rem) {
+    std::nth_element(key.begin(), key.begin() + rem, key.end());
+    for (int k = 0; k < rem; k++) extra[key[k].second] = 1;
+  }
+  std::vector<int> cnt(P.nyl);
+  for (int lj = 0; lj < P.nyl; lj++) cnt[lj] = base + extra[P.nys - g.nygs + lj];
+  int total = 0;
+  WM(gen_rowoff(c, cnt, &total));
+  launch_field_shock(P, g, 1, nxe, c->f.uf, c->st);
+  c->launches++;
+  if (total == 0) return 0;
+  WM(gen_stage_reserve(c, total));
+  launch_gen_shock(P, g, seed, 2, nxe, c->d_rowoff, c->gen_stage, c->gen_stage + (size_t)total * 6, c->st);
+  c->launches++;
+  return gen_append(c, total, "wm_shock_inject");
+}
+
+// relocate() of proj/shock/app.f90:611-680 on the device: the box grows by one column (nxe + 1) unless it is at nxge, n0 new
+// pairs per row in the cell nxe - 1, upstream fields in the columns nxe - 1, nxe; the active range follows (wm_set_xrange).
+int wm_shock_relocate(wm_ctx *c, uint64_t seed, int32_t it) {
+  WM(need_state(c, ST_SORTED, "wm_shock_relocate"));
+  if (c->P.bc != WM_BC_SHOCK || c->gen.n0 < 1) return fail("wm_shock_relocate: call wm_ic_shock first");
+  WM(set_device(c));
+  const DevParams &P = c->P;
+  int nxe = c->cfg.nxgs + c->nxa - 1;
+  if (nxe == c->cfg.nxge) return 0;  // app.f90:619
+  nxe++;
+  GenParams g = c->gen;
+  g.it = it;
+  std::vector<int> cnt(P.nyl, g.n0);
+  int total = 0;
+  WM(gen_rowoff(c, cnt, &total));
+  WM(gen_stage_reserve(c, total));
+  launch_gen_shock(P, g, seed, 1, nxe, c->d_rowoff, c->gen_stage, c->gen_stage + (size_t)total * 6, c->st);
+  launch_field_shock(P, g, 1, nxe, c->f.uf, c->st);
+  c->launches += 2;
+  WM(wm_set_xrange(c, c->cfg.nxgs, nxe));
+  return gen_append(c, total, "wm_shock_relocate");
+}
+
+int wm_xrange(wm_ctx *c, int32_t out[2]) {
+  if (!c || !out) return fail("wm_xrange: null argument");
+  out[0] = c->cfg.nxgs;
+  out[1] = c->cfg.nxgs + c->nxa - 1;
   return 0;
 }
 
