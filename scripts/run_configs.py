@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--small", action="store_true", help="1/8 of the slab (quick check)")
     ap.add_argument("--ppc", type=int, default=32, help="shock: particles per cell and species upstream")
+    ap.add_argument("--capf", type=float, default=8.0, help="shock: device slots per species = capf x n0 x nx x rows")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -84,7 +85,7 @@ def main():
         prm = shock_params(nx, rows * world, n0, nranks=world, u_inject=40.0, sigma_e=0.1, v_the=0.01, v_thi=0.01, l_damp_ini=100.0)
         nys = 2 + rank * rows
         ctx = wm.Context.from_params(prm, nys=nys, nye=nys + rows - 1, nrank=rank, nsize=world, device=local, bc=wm.WM_BC_SHOCK,
-                                     capacity=int(n0 * nx * rows * 3.2))
+                                     capacity=int(n0 * nx * rows * args.capf))
     if world > 1:
         ids = [ctx.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)

@@ -52,6 +52,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ int ld_volatile(const int *p) {
   int v;
   asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -75,6 +83,9 @@ struct Ctx {
   int G, cta;
   unsigned nsync;  // barriers passed so far (uniform over the grid)
   bool peer_writer;  // this CTA stores into the ring neighbours' ghost rows (its block touches the slab's first / last row)
+  bool w_up, w_down; // ... into nup's lower ghost row / ndown's upper ghost row
+  bool r_up, r_down; // this CTA reads the slab's upper / lower ghost row
+  int bx;
 };
 
 // spin until pred() or abort / timeout
@@ -108,9 +119,16 @@ __device__ __forceinline__ void allsum(Ctx &c, double (&v)[NV], double *s_red, F
   if (lane == 0)
 #pragma unroll
     for (int k = 0; k < NV; k++) s_red[wid * 2 + k] = v[k];
-  if (c.peer_writer) asm volatile("fence.acq_rel.sys;" ::: "memory");  // my stores into the neighbours' ghost rows
   __syncthreads();
   const unsigned seq = ++c.nsync;
+  // Ring: this CTA's stores into a neighbour's ghost row are released by ONE flag per CTA in the neighbour's memory, off the
+  // critical path of the sums (thread 32: warp 1, while warp 0 reduces).  st.release.sys is cumulative over the stores the
+  // CTA barrier above has ordered before it.
+  if (c.peer_writer && t == 32) {
+    const unsigned long long gs = a.seq0 + seq;
+    if (c.w_up) st_release_sys(&a.sh[a.nup]->halo_flag[0][c.bx], gs);      // nup's row nys-1 comes "from its ndown"
+    if (c.w_down) st_release_sys(&a.sh[a.ndown]->halo_flag[1][c.bx], gs);  // ndown's row nye+1 comes "from its nup"
+  }
   double2 *part = reinterpret_cast<double2 *>(a.partial) + (size_t)(seq & 1u) * GMAX;
   if (wid == 0) {
     double w[2] = {0.0, 0.0};
@@ -173,9 +191,12 @@ __device__ __forceinline__ void allsum(Ctx &c, double (&v)[NV], double *s_red, F
 #pragma unroll
     for (int k = 0; k < NV; k++) v[k] = s_red[64 + k];
   } else {
-    // ring: CTA 0 adds the slab's partials and publishes them to every rank (itself included); everybody waits for the
-    // flags of all ranks in its own memory
+    // ring: CTA 0 adds the slab's partials and publishes them to every rank (itself included) as "LL" words: each half of a
+    // double travels in one 8-byte store together with the low 32 bits of the barrier's sequence number, so the data IS the
+    // flag (8-byte stores are single-copy atomic): no release fence, one NVLink trip.  Everybody polls the words in its own
+    // memory.
     const unsigned long long gseq = a.seq0 + seq;
+    const unsigned seq32 = (unsigned)gseq;
     const int slot = (int)(gseq & 3ull);
     if (c.cta == 0) {
       if (t == 0) spin_until(a, [&] { return ld_acquire_gpu(a.bar) >= target; });
@@ -184,27 +205,38 @@ __device__ __forceinline__ void allsum(Ctx &c, double (&v)[NV], double *s_red, F
         double w[2];
         sum_partials(w);
         if (lane < a.nsize) {
-          CgpShared *dst = a.sh[lane];
+          unsigned long long *dst = &a.sh[lane]->ll[slot][a.nrank][0];
 #pragma unroll
-          for (int k = 0; k < NV; k++) dst->xsum[slot][a.nrank][k] = w[k];
-          st_release_sys(&dst->flag[a.nrank], gseq);  // release.sys: orders the sums above and, cumulatively, the ghost rows
+          for (int k = 0; k < NV; k++) {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(w[k]);
+            st_relaxed_sys(dst + 2 * k, (b & 0xffffffffull) | ((unsigned long long)seq32 << 32));
+            st_relaxed_sys(dst + 2 * k + 1, (b >> 32) | ((unsigned long long)seq32 << 32));
+          }
         }
       }
     }
     CgpShared *me = a.sh[a.nrank];
-    if (t < a.nsize) spin_until(a, [&] { return ld_acquire_sys(&me->flag[t]) >= gseq; });
-    __syncthreads();
-    if (t == 0) {
-      double w[2] = {0.0, 0.0};
-      for (int q = 0; q < a.nsize; q++) {
-#pragma unroll
-        for (int k = 0; k < NV; k++) w[k] += __ldcg(&me->xsum[slot][q][k]);
-      }
-      s_red[64] = w[0];
-      s_red[65] = w[1];
+    unsigned *halves = reinterpret_cast<unsigned *>(s_red + 66);  // [rank][2 * NV]
+    if (t < a.nsize * 2 * NV) {
+      const int q = t / (2 * NV), j = t - q * 2 * NV;
+      const unsigned long long *src = &me->ll[slot][q][j];
+      unsigned long long wv = 0;
+      spin_until(a, [&] { wv = ld_relaxed_sys(src); return (unsigned)(wv >> 32) == seq32; });
+      halves[t] = (unsigned)wv;
     }
+    // the ghost rows this CTA reads: one flag per boundary CTA of the neighbour that owns them
+    if (c.r_down && t >= 64 && t < 64 + a.cbx_down) spin_until(a, [&] { return ld_acquire_sys(&me->halo_flag[0][t - 64]) >= gseq; });
+    if (c.r_up && t >= 256 && t < 256 + a.cbx_up) spin_until(a, [&] { return ld_acquire_sys(&me->halo_flag[1][t - 256]) >= gseq; });
     __syncthreads();
-    double w[2] = {s_red[64], s_red[65]};
+    double w[2] = {0.0, 0.0};
+    for (int q = 0; q < a.nsize; q++) {  // rank order: the same sums on every rank
+#pragma unroll
+      for (int k = 0; k < NV; k++) {
+        const unsigned lo = halves[q * 2 * NV + 2 * k], hi = halves[q * 2 * NV + 2 * k + 1];
+        w[k] += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+      }
+    }
+    __syncthreads();  // `halves` is reused by the next barrier
 #pragma unroll
     for (int k = 0; k < NV; k++) v[k] = w[k];
   }
@@ -266,7 +298,7 @@ __device__ __forceinline__ void cg_phase_b(const double *q, const double *ql, co
 template <int K>
 __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__ DevParams P, const __grid_constant__ CgpArgs a) {
   extern __shared__ __align__(16) double T[];  // p (phi during the set-up) of the block with its halo ring: (bw+2) columns x cp
-  __shared__ double s_red[32 * 2 + 2];
+  __shared__ double s_red[32 * 2 + 2 + CGP_MAXR * 2];  // warp sums, the totals, the halves of the ranks' sums
 
   const int t = threadIdx.x;
   Ctx c;
@@ -274,7 +306,8 @@ __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__
   c.G = gridDim.x;
   c.cta = blockIdx.x;
   c.nsync = 0;
-  c.peer_writer = false;
+  c.peer_writer = c.w_up = c.w_down = c.r_up = c.r_down = false;
+  c.bx = 0;
   const int bx = c.cta % a.cbx, by = c.cta / a.cbx;
   const int x0 = (int)((long long)bx * P.nx / a.cbx), x1 = (int)((long long)(bx + 1) * P.nx / a.cbx);
   const int y0 = (int)((long long)by * P.nyl / a.cby), y1 = (int)((long long)(by + 1) * P.nyl / a.cby);
@@ -309,6 +342,11 @@ __global__ void __launch_bounds__(CGP_T, 1) k_cg_persist(const __grid_constant__
   if (lir >= P.nx) { if (wall) kindr = 2; else lir -= P.nx; }
   const bool slab_bot = P.nsize > 1 && y0 == 0, slab_top = P.nsize > 1 && y0 + bh == P.nyl;  // rows the ring neighbours need
   c.peer_writer = slab_bot || slab_top;
+  c.w_up = slab_top;
+  c.w_down = slab_bot;
+  c.r_down = slab_bot;  // the block that touches the slab's first row reads the ghost row below it, written by ndown
+  c.r_up = slab_top;
+  c.bx = bx;
 
   // r of the perimeter cells goes to the global array (and to the ring neighbours' ghost rows)
   auto publish_one = [&](int l, int cy, double rr) {

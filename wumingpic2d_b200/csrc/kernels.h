@@ -34,7 +34,7 @@ void launch_relayout_soa(const DevParams &P, const PartSoA &src, const int *csta
                          const int *cstart_dst, size_t so, unsigned *err, cudaStream_t st);
 void launch_incoming_append(const DevParams &P, const double *rec, int n, int isp, const int *cstart, int *cnt_tail,
                             const PartSoA &dst, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
-                            cudaStream_t st, const int *n_dev = nullptr);
+                            cudaStream_t st, const int *n_dev = nullptr, const int *cntb = nullptr);
 void launch_check_counts(const int *cnt, int n, const int lim[4], unsigned *err, cudaStream_t st);
 // in-place sort: append the records staged by k_fused<INPLACE> to their new segments, retire vacated slots;
 // rim_only: k_fused_sm<TAIL> served the tile's own cells, only the window rim is left (k_place_rim)
@@ -43,12 +43,19 @@ void launch_place(const DevParams &P, const double *stage, const uint32_t *tag, 
                   bool rim_only, cudaStream_t st);
 // does launch_fused_sm(variant) place the in-tile cell changers itself?
 bool fused_sm_has_tail(int variant);
-void launch_clamp_counts(const DevParams &P, const int *cstart, int *cnt, cudaStream_t st);
+void launch_clamp_counts(const DevParams &P, const int *cstart, int *cnt, cudaStream_t st, const int *cntb = nullptr);
+void launch_mark_gaps(const DevParams &P, PView<double> x, const int *cstart, const int *cnt, cudaStream_t st);
+void launch_nbr_max(const DevParams &P, const int *in, int *out, int r, cudaStream_t st);
 void launch_mark_dead(const DevParams &P, PView<double> x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st);
 // fused push + deposit + boundaries that moves cell changers itself (no tags, no scatter pass)
 void launch_fused_inplace(const DevParams &P, const Pass1Args &a, cudaStream_t st);
 // k_fused<INPLACE> with the deposit split into stayers (21 sums, in the loop) and movers (queued, drained per cell) (fused5_kernel.cu)
 void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaStream_t st);
+// push + deposit + boundaries + sort with direct placement of the cell changers: reads a.src, writes a.dst (fused6_kernel.cu)
+void launch_fused_dp(const DevParams &P, const Pass1Args &a, cudaStream_t st);
+void launch_place_rim2(const DevParams &P, const uint32_t *tag, const PartSoA &dst, const int *cstart, int *cnt_new, const int *cntb_new,
+                       double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err, cudaStream_t st);
+void launch_normalize(const DevParams &P, const PartSoA &st_, const int *cstart, int *cnt, int *cntb, cudaStream_t st);
 void launch_kinetic(const DevParams &P, const PartSoA &src, const int *cstart, int isp, double *partial, int nblocks,
                     cudaStream_t st);
 // diagnostic: discrete Gauss law residual of the sorted store against uf (periodic x).  rho: 2 planes of (nyl + 2) rows; the
@@ -118,8 +125,9 @@ constexpr int CGP_K = 16;     // cells per thread at most (r in registers): 4096
 constexpr int CGP_KM = 14, CGP_KS = 8;  // further instantiations for slabs that need at most 14 / 8 cells per thread
 constexpr int CGP_MAXR = 8;   // ranks on the ring the in-kernel all-reduce supports
 struct CgpShared {            // one per rank, mapped by every other rank (CUDA IPC)
-  unsigned long long flag[CGP_MAXR];  // flag[src] = last barrier sequence number rank src has published here
-  double xsum[4][CGP_MAXR][4];        // [sequence & 3][src][value]: rank src's sums of that barrier
+  unsigned long long ll[4][CGP_MAXR][4];   // [sequence & 3][src][2 x value]: (half of a double | sequence << 32) words
+  unsigned long long halo_flag[2][160];    // [0]: ndown's CTA bx has stored its part of my row nys-1 for barrier (value);
+                                           // [1]: nup's CTA bx ... of my row nye+1
 };
 struct CgpArgs {
   int cbx, cby;               // block decomposition of the slab: cbx x cby CTAs
@@ -139,6 +147,8 @@ struct CgpArgs {
   CgpShared *sh[CGP_MAXR];    // every rank's block as mapped here (sh[nrank] = mine)
   double *r_up, *r_down;      // rg of nup / ndown as mapped here
   int nyl_down;               // rows of ndown: its upper ghost row is local row nyl_down
+  int nup, ndown;             // ring neighbours
+  int cbx_up, cbx_down;       // blocks in x of nup's / ndown's decomposition (one halo flag each)
   unsigned long long *trace;  // WM_CGTRACE: [G][4 barriers][4 events] global-timer stamps, else null
   unsigned trace_seq;
 };

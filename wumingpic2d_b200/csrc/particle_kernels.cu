@@ -935,7 +935,7 @@ __global__ void k_relayout_soa(const DevParams P, const PartSoA src, const int *
 // message was sized from the previous step's count and got truncated)
 __global__ void k_incoming_append(const DevParams P, const double *__restrict__ rec, int n, const int *__restrict__ n_dev, int isp,
                                   const int *__restrict__ cstart, int *cnt_tail, const PartSoA dst, double *ovf, int *ovfsp,
-                                  int *ovfcnt, int ovfcap, unsigned *err) {
+                                  int *ovfcnt, int ovfcap, unsigned *err, const int *__restrict__ cntb) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) {
     const int m = *n_dev;
@@ -955,7 +955,8 @@ __global__ void k_incoming_append(const DevParams P, const double *__restrict__ 
   const int cell = lj * P.nx + li;
   const int *cs = cstart + (size_t)isp * (P.ncell + 1);
   const int pos = atomicAdd(&cnt_tail[(size_t)isp * P.ncell + cell], 1);
-  if (pos < cs[cell + 1] - cs[cell]) {
+  // (cntb: the back of the segment holds the arrivals of the last fused pass, k_fused_dp)
+  if (pos < cs[cell + 1] - cs[cell] - (cntb ? cntb[(size_t)isp * P.ncell + cell] : 0)) {
     const size_t o = (size_t)isp * P.cap + cs[cell] + pos;
     dst.x[o] = r[0];
     dst.y[o] = r[1];
@@ -1236,6 +1237,31 @@ __global__ void k_clamp_counts(const DevParams P, const int *__restrict__ cstart
     if (cnt[wk] > capc) cnt[wk] = capc;
   }
 }
+// layout rebuild: the slots behind the live particles of every segment become dead (instead of a memset of the whole store)
+__global__ void k_mark_gaps(const DevParams P, PView<double> x, const int *__restrict__ cstart, const int *__restrict__ cnt) {
+  const long long n = (long long)P.nsp * P.ncell;
+  const int lane = threadIdx.x & 31;
+  for (long long wk = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wk < n; wk += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int isp = (int)(wk / P.ncell), cell = (int)(wk - (long long)isp * P.ncell);
+    const int *cs = cstart + (size_t)isp * (P.ncell + 1);
+    const size_t so = (size_t)isp * P.cap;
+    for (int p = cs[cell] + cnt[wk] + lane; p < cs[cell + 1]; p += 32) x[so + p] = dead_x();
+  }
+}
+void launch_mark_gaps(const DevParams &P, PView<double> x, const int *cstart, const int *cnt, cudaStream_t st) {
+  k_mark_gaps<<<148 * 16, 256, 0, st>>>(P, x, cstart, cnt);
+}
+// out[c] = max of in over the cells c-r .. c+r of the same row: segments sized for the densest neighbour survive a moving
+// density front (shock) for ~r / front speed steps instead of one
+__global__ void k_nbr_max(const DevParams P, const int *__restrict__ in, int *__restrict__ out, int r) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < P.ncell; c += gridDim.x * blockDim.x) {
+    const int lj = c / P.nx, li = c - lj * P.nx;
+    int m = 0;
+    for (int d = max(li - r, 0); d <= min(li + r, P.nx - 1); d++) m = max(m, in[lj * P.nx + d]);
+    out[c] = m;
+  }
+}
+void launch_nbr_max(const DevParams &P, const int *in, int *out, int r, cudaStream_t st) { k_nbr_max<<<148 * 8, 256, 0, st>>>(P, in, out, r); }
 void launch_clamp_counts(const DevParams &P, const int *cstart, int *cnt, cudaStream_t st) {
   k_clamp_counts<<<148 * 8, 256, 0, st>>>(P, cstart, cnt);
 }
@@ -1305,9 +1331,9 @@ void launch_relayout_soa(const DevParams &P, const PartSoA &src, const int *csta
 }
 void launch_incoming_append(const DevParams &P, const double *rec, int n, int isp, const int *cstart, int *cnt_tail,
                             const PartSoA &dst, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
-                            cudaStream_t st, const int *n_dev) {
+                            cudaStream_t st, const int *n_dev, const int *cntb) {
   if (n > 0)
-    k_incoming_append<<<(n + 255) / 256, 256, 0, st>>>(P, rec, n, n_dev, isp, cstart, cnt_tail, dst, ovf, ovfsp, ovfcnt, ovfcap, err);
+    k_incoming_append<<<(n + 255) / 256, 256, 0, st>>>(P, rec, n, n_dev, isp, cstart, cnt_tail, dst, ovf, ovfsp, ovfcnt, ovfcap, err, cntb);
 }
 // the sender's side of the same check: more leavers than the message holds
 __global__ void k_check_counts(const int *__restrict__ cnt, int n, int lim0, int lim1, int lim2, int lim3, unsigned *err) {

@@ -69,11 +69,17 @@ struct wm_ctx {
   int *cstart[2] = {nullptr, nullptr};   // [nsp][ncell+1] segment offsets of store b
   int *cnt[2] = {nullptr, nullptr};      // [nsp][ncell]   live particles per segment of store b
   int *cnt_tail = nullptr;               // [nsp][ncell]   append cursors of the in-place sort
+  // k_fused_dp ("ping-pong" stores, direct placement): a segment holds cnt particles at its front and cntb at its back; the
+  // pass reads store `cur` and writes the other one; has_back = the current state has back ranges (k_normalize removes them)
+  int *cntb[2] = {nullptr, nullptr}, *cntb_tail = nullptr;
+  bool has_back = false;
   int *tight = nullptr;                  // [nsp][ncell+1] scratch: exclusive scan of cnt (= cumcnt + row bases)
   double *ovf = nullptr;                 // in-place sort overflow list
   int *ovfsp = nullptr, *ovfcnt = nullptr, *ovfrank = nullptr, *h_ovf = nullptr;
   int ovfcap = 0;
   float slack = 6.0f;                    // segment slack in std deviations of the count change (WM_SLACK)
+  int nbr_r = 0;                         // segments sized for the densest cell within nbr_r cells in x (adaptive: frequent rebuilds)
+  long long nstep = 0, last_rebuild_step = -1000000;
   int cell_floor = 0;                    // every segment is laid out for at least this many particles (shock: upstream cells fill up)
   GenParams gen{};                       // parameters of the device-side particle sources (wm_ic_shock -> wm_shock_inject / _relocate)
   int *d_rowoff = nullptr;               // [nyl + 1] per-row record offsets of a generator call
@@ -82,7 +88,7 @@ struct wm_ctx {
   bool inplace = true;                   // WM_INPLACE=0 selects the tag + scatter sort for wm_step
   bool cg3 = false;                      // WM_CG3=1: three-kernel CG iteration (k_cg_ap, k_cg_update, k_cg_pupdate)
   bool rimplace = true;                  // k_place_rim after k_fused_sm<TAIL> (WM_RIMPLACE=0: the general k_place)
-  int sm = 1;                            // stayer/mover split deposit (k_fused_sm); WM_SM=0 selects k_fused<INPLACE>
+  int sm = 5;                            // 5: k_fused_dp (direct placement); 1: k_fused_sm<TAIL> + k_place_rim; 0: k_fused<INPLACE> (WM_SM)
   long long rebuilds = 0;
   int cur = 0;
   int *gcnt = nullptr, *tilebase = nullptr, *scan_scratch = nullptr;
@@ -128,7 +134,7 @@ struct wm_ctx {
   void *cgp_ipc_open[CGP_MAXR + 2] = {nullptr};  // mappings to close at destroy
   int cgp_nopen = 0;
   double *cgp_r_up = nullptr, *cgp_r_down = nullptr;
-  int cgp_nyl_down = 0;
+  int cgp_nyl_down = 0, cgp_nyl_up = 0;
   // comm
   ncclComm_t comm = nullptr;
   int nup = 0, ndown = 0;
@@ -174,9 +180,12 @@ int alloc_particles(wm_ctx *c, long long need) {
     carve(c->soa[b], c->pbuf[b], cap, nsp);
     CU(cudaMalloc(&c->cstart[b], (size_t)nsp * (c->P.ncell + 1) * sizeof(int)));
     CU(cudaMalloc(&c->cnt[b], (size_t)nsp * c->P.ncell * sizeof(int)));
+    CU(cudaMalloc(&c->cntb[b], (size_t)nsp * c->P.ncell * sizeof(int)));
+    CU(cudaMemset(c->cntb[b], 0, (size_t)nsp * c->P.ncell * sizeof(int)));
     CU(cudaMemset(c->pbuf[b], 0xFF, (size_t)cap * nsp * 6 * sizeof(double)));  // every slot dead (x = all-ones NaN)
   }
   CU(cudaMalloc(&c->cnt_tail, (size_t)nsp * c->P.ncell * sizeof(int)));
+  CU(cudaMalloc(&c->cntb_tail, (size_t)nsp * c->P.ncell * sizeof(int)));
   CU(cudaMalloc(&c->tight, (size_t)nsp * (c->P.ncell + 1) * sizeof(int)));
   c->ovfcap = (int)std::min<long long>(std::max<long long>(need / 64, 1 << 16), 1 << 24);
   CU(cudaMalloc(&c->ovf, (size_t)c->ovfcap * 6 * sizeof(double)));
@@ -343,6 +352,16 @@ int cg_solve_persist(wm_ctx *c) {
   a.r_up = c->cgp_r_up;
   a.r_down = c->cgp_r_down;
   a.nyl_down = c->cgp_nyl_down;
+  a.nup = c->nup;
+  a.ndown = c->ndown;
+  a.cbx_up = a.cbx_down = a.cbx;
+  if (P.nsize > 1) {  // the neighbours' decompositions follow from their row counts (the same rule on every rank)
+    int cby, rl;
+    size_t sm;
+    if (!cgp_plan(c->nxa, c->cgp_nyl_up, c->nsm, c->cgp_smem_max, &a.cbx_up, &cby, &rl, &sm) ||
+        !cgp_plan(c->nxa, c->cgp_nyl_down, c->nsm, c->cgp_smem_max, &a.cbx_down, &cby, &rl, &sm))
+      return fail("cg_solve_persist: a ring neighbour's slab does not fit the on-chip solver");
+  }
   static const char *tr = getenv("WM_CGTRACE");
   unsigned long long *d_tr = nullptr;
   const int G = a.cbx * a.cby;
@@ -501,7 +520,9 @@ Pass1Args p1args(wm_ctx *c, const PartSoA &src, const PartSoA &dst, double delt_
   a.dst = dst;
   a.cstart = c->cstart[c->cur];
   a.cnt = c->cnt[c->cur];
+  a.cntb = c->cntb[c->cur];
   a.cnt_tail = c->cnt_tail;
+  a.cntb_new = c->cntb_tail;
   a.ovf = c->ovf;
   a.ovfsp = c->ovfsp;
   a.ovfcnt = c->ovfcnt;
@@ -528,8 +549,12 @@ int zero_sort_state(wm_ctx *c) {
 
 // ring exchange of the leavers packed by the BOUND pass, then rank the arrivals
 // boundary_periodic.f90:173-189
-int migrate(wm_ctx *c, bool inplace = false) {
+int migrate(wm_ctx *c, bool inplace = false, bool dp = false) {
   const DevParams &P = c->P;
+  // append cursors of the arrivals: the in-place sort's cnt_tail, or (k_fused_dp) the front counts of the new store, limited by
+  // its back ranges
+  int *const cursor = dp ? c->cnt[c->cur] : c->cnt_tail;
+  const int *const backs = dp ? c->cntb[c->cur] : nullptr;
   if (P.nsize == 1) return 0;
   if (!c->comm) return fail("nsize > 1 but wm_comm_init has not been called");
   const int nsp = P.nsp;
@@ -561,8 +586,8 @@ int migrate(wm_ctx *c, bool inplace = false) {
     for (int d = 0; d < 2; d++)
       for (int isp = 0; isp < nsp; isp++) {
         const size_t off = (size_t)isp * c->sendcap;
-        launch_incoming_append(P, c->recv[d] + off * 6, mr[d * nsp + isp], isp, c->cstart[c->cur], c->cnt_tail, c->soa[c->cur], c->ovf,
-                               c->ovfsp, c->ovfcnt, c->ovfcap, c->d_err, c->st, c->recvcnt + d * nsp + isp);
+        launch_incoming_append(P, c->recv[d] + off * 6, mr[d * nsp + isp], isp, c->cstart[c->cur], cursor, c->soa[c->cur], c->ovf,
+                               c->ovfsp, c->ovfcnt, c->ovfcap, c->d_err, c->st, c->recvcnt + d * nsp + isp, backs);
         c->launches++;
       }
     c->launches++;
@@ -601,8 +626,8 @@ int migrate(wm_ctx *c, bool inplace = false) {
     for (int isp = 0; isp < nsp; isp++) {
       const size_t off = (size_t)isp * c->sendcap;
       if (inplace)  // append at the tail of the destination segments of the current store
-        launch_incoming_append(P, c->recv[d] + off * 6, c->n_in[d][isp], isp, c->cstart[c->cur], c->cnt_tail, c->soa[c->cur],
-                               c->ovf, c->ovfsp, c->ovfcnt, c->ovfcap, c->d_err, c->st);
+        launch_incoming_append(P, c->recv[d] + off * 6, c->n_in[d][isp], isp, c->cstart[c->cur], cursor, c->soa[c->cur],
+                               c->ovf, c->ovfsp, c->ovfcnt, c->ovfcap, c->d_err, c->st, nullptr, backs);
       else
         launch_incoming_tag(P, c->recv[d] + off * 6, c->n_in[d][isp], isp, nullptr, c->gcnt,
                             c->in_rank + (size_t)d * nsp * c->sendcap + off, c->d_err, c->st);
@@ -627,8 +652,14 @@ int scatter_arrivals(wm_ctx *c, int dstbuf) {
 // new layout of store `dstbuf` from the destination-cell counts in gcnt: cnt = gcnt, cstart = scan of capacities
 int scan_counts(wm_ctx *c, int dstbuf) {
   for (int isp = 0; isp < c->P.nsp; isp++) {
-    if (launch_scan(c->gcnt + (size_t)isp * c->P.ncell, c->cstart[dstbuf] + (size_t)isp * (c->P.ncell + 1), c->scan_scratch,
-                    c->P.ncell, c->slack, c->st, c->cell_floor))
+    const int *in = c->gcnt + (size_t)isp * c->P.ncell;
+    if (c->nbr_r > 0 && c->slack > 0.f) {  // capacity from the densest cell within nbr_r cells in x (c->tight is scratch here)
+      int *tmp = c->tight + (size_t)isp * (c->P.ncell + 1);
+      launch_nbr_max(c->P, in, tmp, c->nbr_r, c->st);
+      c->launches++;
+      in = tmp;
+    }
+    if (launch_scan(in, c->cstart[dstbuf] + (size_t)isp * (c->P.ncell + 1), c->scan_scratch, c->P.ncell, c->slack, c->st, c->cell_floor))
       return fail("grid too large for the prefix scan");
     c->launches += 3;
   }
@@ -652,12 +683,29 @@ int fill_dead(wm_ctx *c, int buf) {
   return 0;
 }
 
-int need_state(wm_ctx *c, State s, const char *who) {
+// k_fused_dp leaves the arrivals of a step at the back of their segments; everything but the next k_fused_dp wants one range
+int normalize(wm_ctx *c) {
+  if (!c->has_back) return 0;
+  CU(cudaSetDevice(c->dev));
+  launch_normalize(c->P, c->soa[c->cur], c->cstart[c->cur], c->cnt[c->cur], c->cntb[c->cur], c->st);
+  c->launches++;
+  c->has_back = false;
+  return 0;
+}
+// the state after an upload / initial condition / layout rebuild has no back ranges
+int reset_back(wm_ctx *c, int buf) {
+  CU(cudaMemsetAsync(c->cntb[buf], 0, (size_t)c->P.nsp * c->P.ncell * sizeof(int), c->st));
+  c->has_back = false;
+  return 0;
+}
+
+int need_state(wm_ctx *c, State s, const char *who, bool keep_back = false) {
   if (!c) return fail("%s: null context", who);
   if (c->state != s) {
     static const char *nm[] = {"EMPTY", "SORTED", "PUSHED", "BOUNDED"};
     return fail("%s: particle state is %s, expected %s (call order of proj/weibel/app.f90:100-107)", who, nm[c->state], nm[s]);
   }
+  if (!keep_back) return normalize(c);
   return 0;
 }
 
@@ -844,6 +892,7 @@ int wm_destroy(wm_ctx *c) {
     cudaFree(c->pbuf[b]);
     cudaFree(c->cstart[b]);
     cudaFree(c->cnt[b]);
+    cudaFree(c->cntb[b]);
     cudaFree(c->send[b]);
     cudaFree(c->recv[b]);
   }
@@ -865,6 +914,7 @@ int wm_destroy(wm_ctx *c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   cudaFree(c->cnt_tail);
+  cudaFree(c->cntb_tail);
   cudaFree(c->tight);
   cudaFree(c->ovf);
   cudaFree(c->ovfsp);
@@ -933,6 +983,7 @@ static int ring_map_peers(wm_ctx *c) {
         ok = open(all[c->ndown].r, reinterpret_cast<void **>(&c->cgp_r_down));
     }
     c->cgp_nyl_down = all[c->ndown].nyl;
+    c->cgp_nyl_up = all[c->nup].nyl;
   }
   // everybody or nobody
   int *d_ok = reinterpret_cast<int *>(d_all);
@@ -1017,6 +1068,7 @@ static int bucket_stage(wm_ctx *c, double *stage, const long long n[WM_NSP_MAX],
   }
   WM(scan_counts(c, c->cur));
   WM(fill_dead(c, c->cur));
+  WM(reset_back(c, c->cur));
   off = 0;
   for (int isp = 0; isp < P.nsp; isp++) {
     launch_incoming_scatter(P, stage + off * 6, (int)n[isp], isp, nullptr, c->cstart[c->cur], rank + off, c->soa[c->cur], c->d_err, c->st);
@@ -1078,6 +1130,7 @@ int wm_upload_particles_sorted(wm_ctx *c, const double *up, const int32_t *np2, 
   CU(cudaMemcpyAsync(c->gcnt, hc.data(), hc.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
   WM(scan_counts(c, c->cur));
   WM(fill_dead(c, c->cur));
+  WM(reset_back(c, c->cur));
   long long off = 0;
   for (int isp = 0; isp < P.nsp; isp++) {
     launch_relayout_from_aos(P, stage + off * 6, n[isp], c->tight + (size_t)isp * (P.ncell + 1),
@@ -1185,6 +1238,7 @@ int wm_particle_counts(wm_ctx *c, int64_t *n) {
     for (int isp = 0; isp < c->P.nsp; isp++) n[isp] = 0;
     return 0;
   }
+  WM(normalize(c));
   WM(scan_tight(c));
   for (int isp = 0; isp < c->P.nsp; isp++) {
     int v = 0;
@@ -1363,18 +1417,51 @@ int wm_sort__bucket(wm_ctx *c) {
 // parked records), order-preserving copy into the other store, then the parked records.
 static int rebuild_layout(wm_ctx *c, int novf) {
   const DevParams &P = c->P;
+  WM(normalize(c));
   const int dst = c->cur ^ 1;
+  WM(reset_back(c, dst));
   if (novf > c->ovfcap) return fail("in-place sort: %d records overflowed their segments, list holds %d", novf, c->ovfcap);
   launch_clamp_counts(P, c->cstart[c->cur], c->cnt[c->cur], c->st);  // the surplus of a full segment is in the overflow list
   CU(cudaMemcpyAsync(c->gcnt, c->cnt[c->cur], (size_t)P.nsp * P.ncell * sizeof(int), cudaMemcpyDeviceToDevice, c->st));
   launch_incoming_tag(P, c->ovf, novf, 0, c->ovfsp, c->gcnt, c->ovfrank, c->d_err, c->st);
-  WM(scan_counts(c, dst));
-  WM(fill_dead(c, dst));
+  // A moving density front (the shock) overflows the Poisson slack of the cells just ahead of it step after step: when
+  // rebuilds come in quick succession, size the segments for the densest cell of their neighbourhood in x
+  // ... and when that is not enough (filaments that compress by tens of per cent within a few steps), widen the slack itself
+  if (c->nstep - c->last_rebuild_step < 4) {
+    if (c->nbr_r < 8)
+      c->nbr_r = c->nbr_r ? 2 * c->nbr_r : 4;
+    else if (c->slack < 40.f)
+      c->slack *= 1.5f;
+  }
+  c->last_rebuild_step = c->nstep;
+  for (;;) {  // the new layout must fit the store: drop the neighbourhood sizing, then the slack, before giving up
+    WM(scan_counts(c, dst));
+    int tot[WM_NSP_MAX] = {0, 0};
+    for (int isp = 0; isp < P.nsp; isp++)
+      CU(cudaMemcpyAsync(&tot[isp], c->cstart[dst] + (size_t)isp * (P.ncell + 1) + P.ncell, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if ((long long)std::max(tot[0], tot[1]) <= P.cap) break;
+    if (c->slack > 6.f) {
+      c->slack = std::max(6.f, c->slack / 1.5f);
+    } else if (c->nbr_r > 0) {
+      c->nbr_r /= 2;
+      if (c->nbr_r < 4) c->nbr_r = 0;
+    } else if (c->cell_floor > 0) {
+      c->cell_floor /= 2;
+    } else if (c->slack > 0.5f) {
+      c->slack *= 0.5f;
+    } else {
+      return fail("memory over: the particle store (%lld slots per species) cannot hold the segments any more; raise wm_config.capacity "
+                  "(cf. boundary_periodic.f90:231-234)", P.cap);
+    }
+  }
   for (int isp = 0; isp < P.nsp; isp++)
     launch_relayout_soa(P, c->soa[c->cur], c->cstart[c->cur] + (size_t)isp * (P.ncell + 1), c->soa[dst],
                         c->cstart[dst] + (size_t)isp * (P.ncell + 1), (size_t)isp * P.cap, c->d_err, c->st);
   launch_incoming_scatter(P, c->ovf, novf, 0, c->ovfsp, c->cstart[dst], c->ovfrank, c->soa[dst], c->d_err, c->st);
-  c->launches += 2 + P.nsp;
+  // dead marks behind the live particles of every segment (a memset of the whole store cost more than the copy itself)
+  launch_mark_gaps(P, c->soa[dst].x, c->cstart[dst], c->cnt[dst], c->st);
+  c->launches += 3 + P.nsp;
   c->cur = dst;
   c->rebuilds++;
   return 0;
@@ -1388,7 +1475,7 @@ int wm_step(wm_ctx *c, int32_t nsteps) {
   return e;
 }
 static int wm_step_impl(wm_ctx *c, int32_t nsteps) {
-  if (need_state(c, ST_SORTED, "wm_step")) return 2;  // wrong state on entry: nothing was touched
+  if (need_state(c, ST_SORTED, "wm_step", true)) return 2;  // wrong state on entry: nothing was touched
   c->accl_valid = false;
   WM(set_device(c));
   const DevParams &P = c->P;
@@ -1396,7 +1483,9 @@ static int wm_step_impl(wm_ctx *c, int32_t nsteps) {
   const int mode = M_PUSH | M_DEPOSIT | M_BOUND | ((c->cfg.flags & WM_FLAG_EXACT_PUSH) ? M_EXACT : 0);
   const bool inplace = c->inplace && !(c->cfg.flags & WM_FLAG_EXACT_PUSH);
   // k_fused_sm<TAIL> places the in-tile cell changers and retires the vacated slots itself: k_place_rim for the rest
-  const bool rim = inplace && c->sm && fused_sm_has_tail(c->sm) && c->rimplace;
+  const bool dp = inplace && c->sm == 5;  // k_fused_dp: store `cur` -> the other store, cell changers placed directly
+  const bool rim = inplace && !dp && c->sm && fused_sm_has_tail(c->sm) && c->rimplace;
+  if (!dp) WM(normalize(c));
   if (P.bc == WM_BC_SHOCK) {
     if (!c->u_inject_set) return fail("wm_step: WM_BC_SHOCK needs wm_set_u_inject(u0) first (bc__injection, proj/shock/app.f90:113)");
     if (!(c->cfg.flags & WM_FLAG_EXACT_PUSH) && !(inplace && c->sm))
@@ -1408,12 +1497,18 @@ static int wm_step_impl(wm_ctx *c, int32_t nsteps) {
     // particle__solv + ele_cur + bc__particle_x/y + (histogram | move of the cell changers) in one pass, in place
     launch_tmpf(fieldp(c), c->f.uf, c->f.tmpf, c->st);
     CU(cudaMemsetAsync(c->f.uj, 0, ng * 3 * sizeof(double), c->st));
-    WM(zero_sort_state(c));
+    if (dp) {  // (no destination-cell counters: only the leavers' counters)
+      if (P.nsize > 1) CU(cudaMemsetAsync(c->sendcnt, 0, 2 * WM_NSP_MAX * sizeof(int), c->st));
+    } else {
+      WM(zero_sort_state(c));
+    }
     if (inplace) CU(cudaMemsetAsync(c->ovfcnt, 0, sizeof(int), c->st));
     const PartSoA &a = c->soa[c->cur];
     if (c->timing) CU(cudaEventRecord(c->ev[1], c->st));
     if (c->cfg.flags & WM_FLAG_EXACT_PUSH)
       launch_pass1(mode, P, p1args(c, a, a, P.delt), c->st);
+    else if (dp)
+      launch_fused_dp(P, p1args(c, a, c->soa[c->cur ^ 1], P.delt), c->st);
     else if (inplace && c->sm)
       launch_fused_sm(P, p1args(c, a, c->soa[c->cur ^ 1], P.delt), c->sm, c->st);
     else if (inplace)
@@ -1422,7 +1517,39 @@ static int wm_step_impl(wm_ctx *c, int32_t nsteps) {
       launch_fused(P, p1args(c, a, a, P.delt), c->st);
     c->launches += 2;
     if (c->timing) CU(cudaEventRecord(c->ev[2], c->st));
-    if (inplace && c->overlap) {
+    if (dp) {
+      // The pass has written the other store: stayers at the front of their segments (counts in cnt_tail), arrivals from
+      // cells of the same tile at the back (counts in cntb_tail).  That store is the current one from here on; the segment
+      // offsets are the same, so the offset arrays swap with the stores.
+      const int d = c->cur ^ 1;
+      std::swap(c->cstart[0], c->cstart[1]);
+      std::swap(c->cnt[d], c->cnt_tail);
+      std::swap(c->cntb[d], c->cntb_tail);
+      c->cur = d;
+      c->has_back = true;
+      WM(migrate(c, true, true));  // ring exchange of the leavers; arrivals are appended behind the stayers
+      if (c->timing) CU(cudaEventRecord(c->ev[3], c->st));  // (ev[2], ev[3]) = migration
+      const bool late_fork = c->overlap && cg_persist_usable(c);
+      if (late_fork) WM(field_solve_pre(c));
+      cudaStream_t ps = c->overlap ? c->st2 : c->st;
+      if (c->overlap) {
+        CU(cudaEventRecord(c->ev_fork, c->st));
+        CU(cudaStreamWaitEvent(c->st2, c->ev_fork, 0));
+      }
+      if (c->timing) CU(cudaEventRecord(c->ev_b[0], ps));
+      // arrivals from other tiles' cells (the window rim: 1.8 % of the particles) behind the stayers of their new cells
+      launch_place_rim2(P, c->tag, c->soa[d], c->cstart[d], c->cnt[d], c->cntb[d], c->ovf, c->ovfsp, c->ovfcnt, c->ovfcap, c->d_err, ps);
+      c->launches++;
+      CU(cudaMemcpyAsync(c->h_ovf, c->ovfcnt, sizeof(int), cudaMemcpyDeviceToHost, ps));
+      if (c->timing) CU(cudaEventRecord(c->ev_b[1], ps));
+      if (c->overlap) CU(cudaEventRecord(c->ev_join, c->st2));
+      if (late_fork)
+        WM(field_solve_post(c));
+      else
+        WM(field_solve(c));
+      if (c->timing) CU(cudaEventRecord(c->ev[4], c->st));
+      if (c->overlap) CU(cudaStreamWaitEvent(c->st, c->ev_join, 0));
+    } else if (inplace && c->overlap) {
       // The rest of the sort (migration, k_place_rim -- or k_place + k_mark_dead on the variant paths) only needs what the fused pass left behind, the rest
       // of field__fdtd_i only needs uj: the two run side by side, the sort on the second stream.  (NCCL calls stay
       // on the main stream, in program order.)
@@ -1486,7 +1613,7 @@ static int wm_step_impl(wm_ctx *c, int32_t nsteps) {
       float t[5];
       for (int k = 0; k < 5; k++) CU(cudaEventElapsedTime(&t[k], c->ev[k], c->ev[k + 1]));
       c->ms[0] += t[1];
-      if (inplace && c->overlap) {
+      if (dp || (inplace && c->overlap)) {
         float tb;
         CU(cudaEventElapsedTime(&tb, c->ev_b[0], c->ev_b[1]));
         c->ms[1] += t[3];         // field solve
@@ -1498,6 +1625,7 @@ static int wm_step_impl(wm_ctx *c, int32_t nsteps) {
         c->ms[3] += t[4];
       }
     }
+    c->nstep++;
     if (inplace && *c->h_ovf > 0) WM(rebuild_layout(c, *c->h_ovf));
   }
   CU(cudaEventRecord(c->ev_call[1], c->st));
@@ -1768,6 +1896,7 @@ int wm_ic_weibel(wm_ctx *c, uint64_t seed, int32_t n0, double vti, double vte, d
   if ((long long)cell_capacity(n0, c->slack) * P.ncell > P.cap)  // before anything is written (the kernel was queued first)
     return fail("wm_ic_weibel: particle capacity %lld too small for %d cells x %d slots (segment slack)", P.cap, P.ncell, cell_capacity(n0, c->slack));
   WM(fill_dead(c, c->cur));
+  WM(reset_back(c, c->cur));
   launch_ic_weibel(P, c->soa[c->cur], c->cstart[c->cur], c->cnt[c->cur], seed, n0, vti, vte, t_ani, c->slack, c->st);
   // uniform field Bz = b0 (app.f90:388-399), df = 0
   const size_t ng = (size_t)P.pitch * (P.nyl + 4);
@@ -1885,8 +2014,8 @@ static int gen_append(wm_ctx *c, int total, const char *who) {
   CU(cudaMemsetAsync(c->ovfcnt, 0, sizeof(int), c->st));
   for (int isp = 0; isp < 2; isp++)
     launch_incoming_append(P, c->gen_stage + (size_t)isp * total * 6, total, isp, c->cstart[c->cur], c->cnt[c->cur], c->soa[c->cur],
-                           c->ovf, c->ovfsp, c->ovfcnt, c->ovfcap, c->d_err, c->st);
-  launch_clamp_counts(P, c->cstart[c->cur], c->cnt[c->cur], c->st);
+                           c->ovf, c->ovfsp, c->ovfcnt, c->ovfcap, c->d_err, c->st, nullptr, c->cntb[c->cur]);
+  launch_clamp_counts(P, c->cstart[c->cur], c->cnt[c->cur], c->st, c->cntb[c->cur]);
   c->launches += 3;
   CU(cudaMemcpyAsync(c->h_ovf, c->ovfcnt, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   WM(check_errors(c, who));
@@ -1907,7 +2036,7 @@ static int gen_stage_reserve(wm_ctx *c, long long records) {
 // boundary (the fractional part by a random number), spread evenly over all rows of the ring with the remainder on random
 // rows; new upstream field values in the columns nxe - 1, nxe.  `it` = time step (keys the random numbers and the ids).
 int wm_shock_inject(wm_ctx *c, uint64_t seed, int32_t it) {
-  WM(need_state(c, ST_SORTED, "wm_shock_inject"));
+  WM(need_state(c, ST_SORTED, "wm_shock_inject", true));  // (the appends know about the back ranges)
   if (c->P.bc != WM_BC_SHOCK || c->gen.n0 < 1) return fail("wm_shock_inject: call wm_ic_shock first");
   WM(set_device(c));
   const DevParams &P = c->P;
@@ -1952,7 +2081,7 @@ int wm_shock_inject(wm_ctx *c, uint64_t seed, int32_t it) {
 // relocate() of proj/shock/app.f90:611-680 on the device: the box grows by one column (nxe + 1) unless it is at nxge, n0 new
 // pairs per row in the cell nxe - 1, upstream fields in the columns nxe - 1, nxe; the active range follows (wm_set_xrange).
 int wm_shock_relocate(wm_ctx *c, uint64_t seed, int32_t it) {
-  WM(need_state(c, ST_SORTED, "wm_shock_relocate"));
+  WM(need_state(c, ST_SORTED, "wm_shock_relocate", true));
   if (c->P.bc != WM_BC_SHOCK || c->gen.n0 < 1) return fail("wm_shock_relocate: call wm_ic_shock first");
   WM(set_device(c));
   const DevParams &P = c->P;

@@ -97,8 +97,10 @@ __host__ __device__ inline int cell_capacity(int n, float sl) {
 struct Pass1Args {
   PartSoA src, dst;         // dst == src for the in-place fused pass
   const int *cstart;        // [nsp][ncell+1] segment offsets (capacity)
-  const int *cnt;           // [nsp][ncell]   live particles per segment
-  int *cnt_tail;            // [nsp][ncell]   in-place sort: append cursors (start = cnt)
+  const int *cnt;           // [nsp][ncell]   live particles per segment (k_fused_dp: at the front of the segment)
+  const int *cntb;          // [nsp][ncell]   k_fused_dp: particles at the back of the segment (arrivals of the last step)
+  int *cnt_tail;            // [nsp][ncell]   in-place sort: append cursors (start = cnt); k_fused_dp: front counts of the new store
+  int *cntb_new;            // [nsp][ncell]   k_fused_dp: back counts of the new store
   double *ovf;              // in-place sort: records that did not fit their segment [ovfcap][6], isp in ovfsp
   int *ovfsp;
   int *ovfcnt;
