@@ -297,13 +297,14 @@ def main():
         fp64_pipe = tj.get("fp64_pipe_pct_of_peak")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_pass1<PUSH|DEPOSIT|BOUND> (exact)" if args.exact else ("k_fused_sm (push + Esirkepov deposit split into stayers/movers + particle boundaries + in-place cell sort: stayers compacted, in-tile cell changers appended to their new segments; one pass)" if os.environ.get("WM_SM", "1") != "0" else "k_fused<INPLACE>"),
+    roofline = {"bound": "hbm", "kernel": "k_pass1<PUSH|DEPOSIT|BOUND> (exact)" if args.exact else {"5": "k_fused_dp (push + Esirkepov deposit split into stayers/movers + particle boundaries + cell sort with direct placement: every record written once into the other store; one pass)", "1": "k_fused_sm<TAIL> (push + Esirkepov deposit split into stayers/movers + particle boundaries + in-place cell sort: stayers compacted, in-tile cell changers appended to their new segments by the CTA's tail; one pass)", "0": "k_fused<INPLACE>"}.get(os.environ.get("WM_SM", "1"), "k_fused_sm variant"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_kind, "alg_bytes_per_particle": ALG_BYTES_PASS1, "ms_per_launch": ms_pass1,
                 "fp64_pipe_pct_of_peak_ncu": fp64_pipe,
-                "note": ("alg_bytes_per_particle counts the push pass only (48 B read + 48 B written, SURVEY 8d); since r01t the "
-                         "kernel also appends the cell changers that stay in their tile to their new segments (sort work, "
-                         "about 13 B/particle more traffic, not counted): compare whole_step across rounds, not this frac"),
+                "note": ("alg_bytes_per_particle = 48 B read + 48 B written per particle (SURVEY 8d); the kernel also does the sort "
+                         "of 98 % of the particles (stayers compacted in place, in-tile cell changers staged and appended by the "
+                         "CTA's tail: about 13 B/particle more traffic, not counted), which SURVEY 8d books as another 96 B: "
+                         "compare whole_step across rounds as well"),
                 "whole_step": {"alg_bytes_per_particle_step": ALG_BYTES_STEP,
                                "achieved": ALG_BYTES_STEP * n_local / (allmax(ms[4]) / args.steps * 1e-3) / 1e9,
                                "frac": ALG_BYTES_STEP * n_local / (allmax(ms[4]) / args.steps * 1e-3) / 1e9 / peak}}

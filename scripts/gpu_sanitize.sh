@@ -16,6 +16,9 @@ run() {  # name tool env... -- kind steps
 run memcheck_weibel memcheck -- weibel 3
 run racecheck_weibel racecheck -- weibel 2
 run synccheck_weibel synccheck -- weibel 2
+run racecheck_sm5 racecheck WM_SM=5 -- weibel 2
+run memcheck_sm5 memcheck WM_SM=5 -- weibel 3
+run memcheck_sm5_slack memcheck WM_SM=5 WM_SLACK=0.4 -- weibel 3
 run racecheck_sm3 racecheck WM_SM=3 -- weibel 2
 run memcheck_sm3 memcheck WM_SM=3 -- weibel 2
 run memcheck_slack memcheck WM_SLACK=0.4 -- weibel 3

@@ -283,7 +283,8 @@ def test_call_order_is_enforced(warm):
 
 @pytest.mark.parametrize("env", [{"WM_INPLACE": "0"}, {"WM_SLACK": "0.4"}, {"WM_SLACK": "12"}, {"WM_SM": "0"},
                                  {"WM_CG3": "1", "WM_CG": "0"}, {"WM_CG": "0"}, {"WM_OVERLAP": "0"}, {"WM_SM": "3"}, {"WM_RIMPLACE": "0"},
-                                 {"WM_SM": "3", "WM_SLACK": "0.4"}])
+                                 {"WM_SM": "3", "WM_SLACK": "0.4"}, {"WM_SM": "5"}, {"WM_SM": "5", "WM_SLACK": "0.4"},
+                                 {"WM_SM": "5", "WM_OVERLAP": "0"}, {"WM_SLACK": "0.4", "WM_OVERLAP": "0"}])
 def test_sort_variants_match_oracle(env, monkeypatch):
     """wm_step with (a) the tag + scatter sort, (b) the in-place sort with so little segment slack that
     segments overflow and the layout is rebuilt nearly every step, (c) generous slack, (d) k_fused<INPLACE> (65
@@ -291,8 +292,9 @@ def test_sort_variants_match_oracle(env, monkeypatch):
     the persistent cooperative kernel, (f) everything on one
     stream, (g) k_fused_sm without its in-tile tail (every cell changer through k_place + k_mark_dead), (h) the tail
     with the general k_place instead of k_place_rim, (i) = (g) with overflowing segments: per-cell counts bit-exact and
-    particles/fields within tolerance in every case.  (The default path -- k_fused_sm<TAIL> + k_place_rim -- is what
-    every other test runs; (b) drives its overflow branch.)"""
+    particles/fields within tolerance in every case; (j) k_fused_dp (WM_SM=5: ping-pong stores, cell changers placed directly,
+    k_place_rim2 for the window rim, k_normalize before every download) with and without overflows.  (The default path --
+    k_fused_sm<TAIL> + k_place_rim -- is what every other test runs; (b) drives its overflow branch.)"""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     prm, w = make_world(40, 24, 16)

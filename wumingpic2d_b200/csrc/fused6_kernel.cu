@@ -746,8 +746,12 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_dp(const DevParams P, const 
   // ---- the tile's cells: how many arrivals their back ranges received (the front counts were written by their owners)
   for (int e = tid; e < P.nsp * TX * TY; e += FT) {
     const int isp = e / (TX * TY), r = e - isp * (TX * TY), cy = r / TX, cx = r - cy * TX;
-    if (cy < th && cx < tw)
-      a.cntb_new[(size_t)isp * P.ncell + (size_t)(lj0 + cy) * P.nx + (li0 + cx)] = s_arr[isp * WIN + (cy + 1) * WINX + (cx + 1)];
+    if (cy < th && cx < tw) {
+      // (arrivals that found the segment full -- the highest ranks -- went to the overflow list)
+      const int *scs = &s_cs[(isp * TY + cy) * (TX + 1) + cx];
+      a.cntb_new[(size_t)isp * P.ncell + (size_t)(lj0 + cy) * P.nx + (li0 + cx)] =
+          min(s_arr[isp * WIN + (cy + 1) * WINX + (cx + 1)], max(scs[1] - scs[0] - s_nold[e], 0));
+    }
   }
 }
 

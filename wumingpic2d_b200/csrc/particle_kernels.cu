@@ -1228,12 +1228,13 @@ __global__ void k_mark_dead(const DevParams P, const PView<double> x, const int 
 }
 
 // counts that ran past their segment's capacity (the surplus went to the overflow list): clamp
-__global__ void k_clamp_counts(const DevParams P, const int *__restrict__ cstart, int *cnt) {
+__global__ void k_clamp_counts(const DevParams P, const int *__restrict__ cstart, int *cnt, const int *__restrict__ cntb) {
   const long long n = (long long)P.nsp * P.ncell;
   for (long long wk = (long long)blockIdx.x * blockDim.x + threadIdx.x; wk < n; wk += (long long)gridDim.x * blockDim.x) {
     const int isp = (int)(wk / P.ncell), cell = (int)(wk - (long long)isp * P.ncell);
     const int *cs = cstart + (size_t)isp * (P.ncell + 1);
-    const int capc = cs[cell + 1] - cs[cell];
+    const int full = cs[cell + 1] - cs[cell];
+    const int capc = full - (cntb ? min(cntb[wk], full) : 0);  // (k_fused_dp: the back of the segment is taken)
     if (cnt[wk] > capc) cnt[wk] = capc;
   }
 }
@@ -1262,8 +1263,8 @@ __global__ void k_nbr_max(const DevParams P, const int *__restrict__ in, int *__
   }
 }
 void launch_nbr_max(const DevParams &P, const int *in, int *out, int r, cudaStream_t st) { k_nbr_max<<<148 * 8, 256, 0, st>>>(P, in, out, r); }
-void launch_clamp_counts(const DevParams &P, const int *cstart, int *cnt, cudaStream_t st) {
-  k_clamp_counts<<<148 * 8, 256, 0, st>>>(P, cstart, cnt);
+void launch_clamp_counts(const DevParams &P, const int *cstart, int *cnt, cudaStream_t st, const int *cntb) {
+  k_clamp_counts<<<148 * 8, 256, 0, st>>>(P, cstart, cnt, cntb);
 }
 
 // ---------------------------------------------------------------- launch wrappers

@@ -88,7 +88,8 @@ struct wm_ctx {
   bool inplace = true;                   // WM_INPLACE=0 selects the tag + scatter sort for wm_step
   bool cg3 = false;                      // WM_CG3=1: three-kernel CG iteration (k_cg_ap, k_cg_update, k_cg_pupdate)
   bool rimplace = true;                  // k_place_rim after k_fused_sm<TAIL> (WM_RIMPLACE=0: the general k_place)
-  int sm = 5;                            // 5: k_fused_dp (direct placement); 1: k_fused_sm<TAIL> + k_place_rim; 0: k_fused<INPLACE> (WM_SM)
+  int sm = 1;                            // 1: k_fused_sm<TAIL> + k_place_rim (default); 5: k_fused_dp (ping-pong stores, direct placement:
+                                         // measured slower, kept as a tested variant); 0: k_fused<INPLACE> (WM_SM)
   long long rebuilds = 0;
   int cur = 0;
   int *gcnt = nullptr, *tilebase = nullptr, *scan_scratch = nullptr;
