@@ -77,6 +77,8 @@ typedef struct wm_ctx wm_ctx;
 
 const char *wm_last_error(void);
 int wm_version(void);
+/* hash of the sources the library was built from (the host layer refuses a binary that does not match the tree) */
+const char *wm_source_hash(void);
 
 /* ---- life cycle ------------------------------------------------------------------ */
 /* the six *__init calls of proj/weibel/app.f90:331-347 */

@@ -162,3 +162,13 @@ def test_oracle_shock_injection(nranks):
     assert np.array_equal(ids, i1) and np.abs(rec - r1).max() <= 1e-12
     assert np.abs(w.global_field() - w1.global_field()).max() <= 1e-13
     w.close(); w1.close()
+
+
+def test_library_is_built_from_this_tree():
+    """The .so is git-ignored and travels with the tree: load_library() refuses a binary whose compiled-in source hash
+    (wm_source_hash) differs from the hash of csrc/ + include/ as they are now."""
+    import wumingpic2d_b200 as wm
+    from wumingpic2d_b200.build import source_hash
+    lib = wm.load_library()
+    assert lib.wm_source_hash().decode() == source_hash()
+    assert lib.wm_version() >= 200

@@ -44,7 +44,7 @@ def library_path():
 _lib = None
 
 EXPORTS = [
-    "wm_last_error", "wm_version", "wm_create", "wm_destroy", "wm_comm_unique_id", "wm_comm_init",
+    "wm_last_error", "wm_version", "wm_source_hash", "wm_create", "wm_destroy", "wm_comm_unique_id", "wm_comm_init",
     "wm_upload_particles", "wm_upload_particles_sorted", "wm_upload_field", "wm_download_particles",
     "wm_download_gp", "wm_download_field", "wm_download_current", "wm_download_dfield",
     "wm_particle_counts", "wm_particle__solv", "wm_field__ele_cur", "wm_boundary__curre",
@@ -85,6 +85,13 @@ def load_library():
     lib = C.CDLL(path)
     P, D, I32 = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)
     lib.wm_last_error.restype = C.c_char_p
+    lib.wm_source_hash.restype = C.c_char_p
+    if not os.environ.get("WM_SKIP_HASH_CHECK"):
+        from .build import source_hash
+        built, tree = lib.wm_source_hash().decode(), source_hash()
+        if built != tree:
+            raise WmError("%s was built from other sources (binary %s, tree %s): rebuild with `python -m wumingpic2d_b200.build`"
+                          % (path, built, tree))
     lib.wm_create.argtypes = [C.POINTER(WmConfig), C.POINTER(P)]
     lib.wm_destroy.argtypes = [P]
     lib.wm_comm_unique_id.argtypes = [C.c_void_p]

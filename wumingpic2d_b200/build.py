@@ -17,20 +17,40 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 UNITS = [("fused_kernel.cu", []), ("fused5_kernel.cu", []), ("fused6_kernel.cu", []), ("particle_kernels.cu", []), ("gen_kernels.cu", []), ("field_kernels.cu", ["-fmad=false"]), ("cg_persist_kernel.cu", ["-fmad=false"]), ("wm_api.cu", [])]
 
 
+def source_hash():
+    """sha256 over the sources the library is built from (csrc/*.cu, csrc/*.h, include/wumingpic2d.h), first 16 hex digits.
+    It is compiled into the library (wm_source_hash) and checked by load_library(): the .so is git-ignored and travels with
+    the tree, so a stale binary must fail loudly instead of silently testing yesterday's kernels."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".h")) and f != "wm_source_hash.h")
+    files.append(os.path.join(os.path.dirname(HERE), "include", "wumingpic2d.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def _newer(a, b):
     return not os.path.exists(b) or os.path.getmtime(a) > os.path.getmtime(b)
 
 
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    hdrs = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".h")]
+    stamp = os.path.join(CSRC, "wm_source_hash.h")  # generated, git-ignored: only wm_api.cu includes it
+    line = '#define WM_SOURCE_HASH "%s"\n' % source_hash()
+    if not os.path.exists(stamp) or open(stamp).read() != line:
+        with open(stamp, "w") as f:
+            f.write(line)
+    hdrs = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".h") and h != "wm_source_hash.h"]
     hdrs.append(os.path.join(os.path.dirname(HERE), "include", "wumingpic2d.h"))
     objs, rebuilt = [], False
     os.makedirs(os.path.join(HERE, "_obj"), exist_ok=True)
     for src, extra in UNITS:
         s = os.path.join(CSRC, src)
         o = os.path.join(HERE, "_obj", src.replace(".cu", ".o"))
-        if force or _newer(s, o) or any(_newer(h, o) for h in hdrs):
+        if force or _newer(s, o) or any(_newer(h, o) for h in hdrs) or (src == "wm_api.cu" and _newer(stamp, o)):
             cmd = [nvcc] + ARCH + COMMON + extra + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             with open(o + ".log", "w") as f:
