@@ -882,10 +882,12 @@ int field_fdtd_i(orc_world *w) {
       }
   }
   bc_dfield(w);          // :173
-  for (Rank &k : w->R) { // :176-184
-    const size_t n = k.uf.size();
+  for (Rank &k : w->R) { // :176-184: uf += df over nxs-2..nxe+2 (the active range of the call), nys-2..nye+2
+    V v{w, &k};
 #pragma omp parallel for
-    for (size_t s = 0; s < n; s++) k.uf[s] = k.uf[s] + k.df[s];
+    for (int j = k.nys - 2; j <= k.nye + 2; j++)
+      for (int i = nxs - 2; i <= nxe + 2; i++)
+        for (int ieq = 1; ieq <= 6; ieq++) k.uf[v.F6(ieq, i, j)] = k.uf[v.F6(ieq, i, j)] + k.df[v.F6(ieq, i, j)];
   }
   return 0;
 }

@@ -352,6 +352,44 @@ def test_persistent_cg_many_blocks(kind):
     w.close()
 
 
+def test_benchmark_strip_matches_oracle():
+    """The benchmark's own initial condition and row length against the oracle: a 4096 x 8-row strip of BASELINE configs[1]
+    (64 ppc x 2 species, 4.2 M particles: 256 tiles wide, tiles at both slab edges, the mover-queue drain path at 64 ppc).
+    The device generates the IC itself (wm_ic_weibel, what bench.py times) and must agree with the oracle's generator to
+    a few ulp; then both start from the oracle's state: counts bit-exact, particles by ID / fields <= 1e-12 after one
+    step, <= 1e-10 after three."""
+    import wumingpic2d_b200 as wm
+    prm = O.weibel_params(4096, 8, 64, cap_factor=1.25)
+    w = O.World(prm, fast=False)
+    w.ic_weibel(20260117)
+    s = oracle_state(w)
+    c = ctx_for(prm)
+    c.ic_weibel(20260117, 64, prm["vti"], prm["vte"], prm["t_ani"], prm["b0"])
+    up, np2, cum = c.download_particles()
+    assert np.array_equal(cum, s["cumcnt"]) and np.array_equal(np2, s["np2"])
+    a, b = flatten_by_id(up, np2), flatten_by_id(s["up"], s["np2"])
+    assert np.array_equal(a[0], b[0])
+    ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+    assert ex <= 1e-15 and eu <= 1e-12, (ex, eu)       # positions identical, Box-Muller in device libm: a few ulp
+    c.upload_particles_sorted(s["up"], s["np2"], s["cumcnt"])
+    c.upload_field(s["uf"])
+    for it in range(3):
+        w.step(1)
+        c.step(1)
+        assert c.cg_iters() == w.cg_iters()
+        up, np2, cum = c.download_particles()
+        assert np.array_equal(cum, w.array(0, O.CUMCNT)), "per-cell counts must be bit-exact (step %d)" % it
+        a, b = flatten_by_id(up, np2), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
+        assert np.array_equal(a[0], b[0])
+        ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+        tol = TOL if it == 0 else 1e-10
+        assert ex <= tol and eu <= tol, (it, ex, eu)
+        assert rel_to_max(c.download_field(), w.array(0, O.UF)).max() <= tol
+        assert rel_to_max(c.download_current(), w.array(0, O.UJ)).max() <= tol
+    assert c.rebuilds() == 0
+    c.close(); w.close()
+
+
 def test_langmuir_oscillation_on_device():
     """A known answer for the CUDA path itself, not through the oracle: cold uniform plasma, heavy ions, electrons on a
     quiet lattice with ux = v0 sin(k x) (the oracle is only the container of the initial condition).  260 wm_step on the

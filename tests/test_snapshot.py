@@ -174,3 +174,35 @@ def test_metadata_writer_reproduces_the_reference_fixture(tmp_path):
                 assert list(mine[sec][name]) == list(rec), (sec, name)
             assert mine[sec][name] == rec, (sec, name, mine[sec][name], rec)
     assert os.path.getsize(base + ".raw") == gold["dataset"]["mom"]["offset"] + gold["dataset"]["mom"]["size"]
+
+
+@pytest.mark.gpu
+def test_compare_with_reference_run_script(tmp_path):
+    """scripts/compare_with_reference_run.py -- the script a maintainer with gfortran + MPI runs on two restart snapshots of
+    the real reference binary -- end to end, with the oracle standing in for the Fortran code: a 2-rank run writes a snapshot
+    at step 3, is restarted from it (df = 0, rows re-bucketed, proj/weibel/app.f90:349-353), runs one step and writes the
+    second snapshot; the script must load the first, advance the device and find parity with the second."""
+    import subprocess
+    import sys
+    from wumingpic2d_b200 import snapshot as S
+    prm, w0 = make_world(24, 16, 6, nranks=2, steps=3)
+    cfg = dict(_cfg(prm), np=prm["np"])
+    b1 = str(tmp_path / "0000003_restart")
+    S.write_restart(b1, 3, prm["nxgs"], prm["nxgs"] + prm["nx"] - 1, cfg, [w0.array(r, O.UP).copy() for r in range(2)],
+                    [w0.array(r, O.NP2).copy() for r in range(2)], [w0.array(r, O.UF).copy() for r in range(2)])
+    w = O.World(prm)                       # the restarted run
+    for r in range(2):
+        w.array(r, O.GP)[...] = w0.array(r, O.UP)
+        w.array(r, O.NP2)[...] = w0.array(r, O.NP2)
+        w.array(r, O.UF)[...] = w0.array(r, O.UF)
+    w.sort_bucket()
+    w.step(1)
+    b2 = str(tmp_path / "0000004_restart")
+    S.write_restart(b2, 4, prm["nxgs"], prm["nxgs"] + prm["nx"] - 1, cfg, [w.array(r, O.UP).copy() for r in range(2)],
+                    [w.array(r, O.NP2).copy() for r in range(2)], [w.array(r, O.UF).copy() for r in range(2)])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "compare_with_reference_run.py"), b1, b2],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "PARITY WITH THE REFERENCE BINARY: ok" in r.stdout and "bit-exact: True" in r.stdout
+    w.close(); w0.close()

@@ -564,9 +564,15 @@ __global__ void k_efield(const DevParams P, const double *__restrict__ uf, const
 }
 
 // uf += df over the whole padded array                                        field.f90:176-184
-__global__ void k_update_uf(double *__restrict__ uf, const double *__restrict__ df, long long n) {
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
-    uf[t] = uf[t] + df[t];
+// over the columns nxs-2 .. nxe+2 of the ACTIVE range (P.nx = nxe - nxs + 1 here) and all rows incl. ghosts, as the reference
+// loops: beyond a shock box that has not grown to nxge yet, uf is left alone
+__global__ void k_update_uf(const DevParams P, double *__restrict__ uf, const double *__restrict__ df) {
+  const long long w = (long long)(P.nx + 4) * 6, n = w * (P.nyl + 4);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / w, e = t - row * w;
+    const size_t o = (size_t)row * P.pitch * 6 + e;
+    uf[o] = uf[o] + df[o];
+  }
 }
 
 // sum B^2, sum E^2 over the interior (app.f90:521-528): partial[block*2 + {0:B,1:E}]
@@ -700,8 +706,8 @@ void launch_efield(const DevParams &P, const FieldBufs &f, cudaStream_t st) {
   k_efield<<<gblocks((long long)P.ncell), 256, 0, st>>>(P, f.uf, f.uj, f.df);
 }
 void launch_update_uf(const DevParams &P, const FieldBufs &f, cudaStream_t st) {
-  const long long n = (long long)P.pitch * (P.nyl + 4) * 6;
-  k_update_uf<<<gblocks(n), 256, 0, st>>>(f.uf, f.df, n);
+  const long long n = (long long)(P.nx + 4) * (P.nyl + 4) * 6;
+  k_update_uf<<<gblocks(n), 256, 0, st>>>(P, f.uf, f.df);
 }
 void launch_field_energy(const DevParams &P, const double *uf, double *partial, int nblocks, cudaStream_t st) {
   k_field_energy<<<nblocks, 256, 0, st>>>(P, uf, partial);
