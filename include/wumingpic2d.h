@@ -91,6 +91,15 @@ int wm_destroy(wm_ctx *ctx);
 int wm_comm_unique_id(void *id128);
 int wm_comm_init(wm_ctx *ctx, const void *id128);
 
+/* In-process transport for nsize > 1 without a second GPU: N contexts of ONE process on one device, each driven by its own
+ * host thread, exchange through device-to-device copies and a host rendezvous instead of NCCL (same call sites, same
+ * semantics: all ranks make the same calls in the same order).  The CG runs as the host loop here (N persistent kernels on one
+ * device cannot wait for each other).  For tests of the ring path on a one-GPU box and for several slabs per GPU. */
+typedef struct wm_loopback wm_loopback;
+int wm_loopback_create(int32_t nsize, wm_loopback **out);
+int wm_loopback_destroy(wm_loopback *group);
+int wm_comm_init_loopback(wm_ctx *ctx, wm_loopback *group);
+
 /* ---- residency: the only points where host arrays are read / written -------------- */
 /* `up` need not be sorted: rows are taken as lists of np2(j,isp) records and bucket-
  * sorted on the device exactly like sort__bucket (common/sort.f90:36). */

@@ -4,5 +4,5 @@ include/wumingpic2d.h; the product is wumingpic2d_b200/libwumingpic2d.so (CUDA, 
 There is no CPU fallback: loading fails loudly if the library has not been built, and every
 call fails if no B200-class device is present.
 """
-from .api import (Context, WmConfig, WmError, load_library, library_path,  # noqa: F401
+from .api import (Context, LoopbackGroup, WmConfig, WmError, load_library, library_path,  # noqa: F401
                   WM_BC_PERIODIC, WM_BC_RECONNECTION, WM_BC_SHOCK, WM_FLAG_EXACT_PUSH)

@@ -50,7 +50,7 @@ EXPORTS = [
     "wm_particle_counts", "wm_particle__solv", "wm_field__ele_cur", "wm_boundary__curre",
     "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_boundary__injection",
     "wm_set_u_inject", "wm_set_xrange", "wm_append_particles", "wm_sort__bucket",
-    "wm_step", "wm_host_step", "wm_host_steps", "wm_cg_path", "wm_cg_plan", "wm_fp64_peak", "wm_ic_harris", "wm_ic_shock", "wm_shock_inject", "wm_shock_relocate", "wm_xrange", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
+    "wm_step", "wm_host_step", "wm_host_steps", "wm_loopback_create", "wm_loopback_destroy", "wm_comm_init_loopback", "wm_cg_path", "wm_cg_plan", "wm_fp64_peak", "wm_ic_harris", "wm_ic_shock", "wm_shock_inject", "wm_shock_relocate", "wm_xrange", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
     "wm_energy", "wm_gauss_residual", "wm_moments", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_ic_weibel", "wm_timing", "wm_synchronize", "wm_layout_rebuilds",
 ]
 
@@ -96,6 +96,9 @@ def load_library():
     lib.wm_destroy.argtypes = [P]
     lib.wm_comm_unique_id.argtypes = [C.c_void_p]
     lib.wm_comm_init.argtypes = [P, C.c_void_p]
+    lib.wm_loopback_create.argtypes = [C.c_int32, C.POINTER(P)]
+    lib.wm_loopback_destroy.argtypes = [P]
+    lib.wm_comm_init_loopback.argtypes = [P, P]
     lib.wm_upload_particles.argtypes = [P, D, I32]
     lib.wm_upload_particles_sorted.argtypes = [P, D, I32, I32]
     lib.wm_upload_field.argtypes = [P, D]
@@ -161,6 +164,23 @@ def _i(a):
         return None
     assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class LoopbackGroup:
+    """The in-process transport for several ranks on one device (wm_loopback_create): every rank's Context is attached with
+    Context.comm_init_loopback(group) and driven by its own host thread."""
+
+    def __init__(self, nsize):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        if self.lib.wm_loopback_create(nsize, C.byref(self.h)):
+            raise WmError(self.lib.wm_last_error().decode())
+        self.nsize = nsize
+
+    def close(self):
+        if getattr(self, "h", None) and self.h:
+            self.lib.wm_loopback_destroy(self.h)
+            self.h = None
 
 
 class Context:
@@ -305,6 +325,9 @@ class Context:
         v = C.c_double()
         self._ck(self.lib.wm_fp64_peak(self.h, C.byref(v)))
         return v.value
+
+    def comm_init_loopback(self, group):
+        self._ck(self.lib.wm_comm_init_loopback(self.h, group.h))
 
     def cg_path(self):
         v = C.c_int32()

@@ -607,6 +607,23 @@ __global__ void __launch_bounds__(256) k_field_energy(const DevParams P, const d
   }
 }
 
+__global__ void k_sum_ranks(const RankPtrs rp, int nranks, int n, int is_double, double *out) {
+  const int k = threadIdx.x;
+  if (k >= n) return;
+  if (is_double) {
+    double s = 0.0;
+    for (int q = 0; q < nranks; q++) s += static_cast<const volatile double *>(rp.p[q])[k];
+    out[k] = s;
+  } else {
+    int m = static_cast<const volatile int *>(rp.p[0])[k];
+    for (int q = 1; q < nranks; q++) m = min(m, static_cast<const volatile int *>(rp.p[q])[k]);
+    reinterpret_cast<int *>(out)[k] = m;
+  }
+}
+void launch_sum_ranks(const RankPtrs &rp, int nranks, int n, bool is_double, double *out, cudaStream_t st) {
+  k_sum_ranks<<<1, 32, 0, st>>>(rp, nranks, n, is_double ? 1 : 0, out);
+}
+
 // ---- measured FP64 peak: 8 independent DFMA chains per thread, 16 warps per SM x 4 CTAs: the pipe's own rate
 //      ("to be measured by the builder with a DFMA loop")
 __global__ void __launch_bounds__(512) k_fp64_peak(double *out, int n, double a, double b) {

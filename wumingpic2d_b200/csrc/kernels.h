@@ -155,6 +155,9 @@ struct CgpArgs {
 bool cgp_plan(int nx, int nyl, int nsm, size_t smem_max, int *cbx, int *cby, int *rl, size_t *smem);
 cudaError_t cgp_prepare(size_t smem);
 cudaError_t launch_cg_persist(const DevParams &P, const CgpArgs &a, size_t smem, cudaStream_t st);
+struct RankPtrs { void *p[CGP_MAXR]; };
+// out[k] = sum (doubles) or min (ints) over the ranks' p[q][k], in rank order (loopback all-reduce)
+void launch_sum_ranks(const RankPtrs &rp, int nranks, int n, bool is_double, double *out, cudaStream_t st);
 void launch_fp64_peak(double *out, int nblocks, int n, cudaStream_t st);  // 8 x n DFMA per thread, 512 threads per block
 size_t cgctl_bytes();
 size_t cgctl_active_offset();       // int active[3]; int ite[3]; int stop  (contiguous)
