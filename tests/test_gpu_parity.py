@@ -230,6 +230,25 @@ def test_host_step_dropin():
     c.close()
 
 
+def test_host_steps_sync_interval():
+    """wm_host_steps(n): one upload, n steps, one download -- what the shim does with WM_SYNC_INTERVAL = n (host arrays valid
+    every n-th step).  Here the CG warm start survives between the steps, as in a resident run, so it equals n oracle steps."""
+    prm, w = make_world(32, 16, 8)
+    s = oracle_state(w)
+    c = ctx_for(prm)
+    up, uf, np2, cum = s["up"].copy(), s["uf"].copy(), s["np2"].copy(), s["cumcnt"].copy()
+    w.step(5)
+    c.host_steps(up, uf, np2, cum, 5)
+    assert c.cg_iters() == w.cg_iters()
+    assert np.array_equal(cum, w.array(0, O.CUMCNT)) and np.array_equal(np2, w.array(0, O.NP2))
+    assert rel_to_max(uf, w.array(0, O.UF)).max() <= 1e-10
+    a, b = flatten_by_id(up, np2), flatten_by_id(w.array(0, O.UP), w.array(0, O.NP2))
+    assert np.array_equal(a[0], b[0])
+    ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+    assert ex <= 1e-10 and eu <= 1e-10
+    c.close()
+
+
 def test_moments_match_oracle(warm):
     prm, w0 = warm
     s = oracle_state(w0)
