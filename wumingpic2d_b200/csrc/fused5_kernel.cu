@@ -362,6 +362,14 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
           asm volatile("prefetch.global.L1 [%0];" ::"l"(b + 8));
           asm volatile("prefetch.global.L1 [%0];" ::"l"(b + 16));
         }
+        if (PFD >= 10) {
+          // two-level prefetch: the WHOLE list this lane's group works on next goes to L2 now, a pass (8-9 iterations) ahead,
+          // so that the L1 hints and the loads of that pass find their lines in L2 instead of DRAM.  A list of n slots is
+          // ceil(n / 8) blocks of three 128-byte lines; the 8 lanes of the group take every 8th line.
+          const double2 *b0 = reinterpret_cast<const double2 *>(px) + pslot_w((last ? (size_t)0 : (size_t)P.cap) + pb);
+          const int nln = ((pn + 7) >> 3) * 3;
+          for (int ln = l8; ln < nln; ln += 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + ln * 8));
+        }
       }
       int k = k0;
       for (; k < nmax; k += 8) {
@@ -371,10 +379,10 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
         double hx, hy, dxn, dyn, qvz;
         double sxm, sx0, sxp, sym, sy0, syp;
         double idc;  // the id moves with the record (bit pattern)
-        if (p + 8 * PFD < end) {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 * PFD));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 * PFD + 8));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 * PFD + 16));
+        if (p + 8 * (PFD % 10) < end) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 * (PFD % 10)));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 * (PFD % 10) + 8));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 24 * (PFD % 10) + 16));
         }
         if (active) {
           const double2 r0 = pl[0], r1 = pl[8], r2 = pl[16];
@@ -827,6 +835,8 @@ void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaSt
     k_fused_sm<3, true, 0, 2, false><<<grid, FT, 0, st>>>(P, a);  // every cell changer left to k_place
   else if (variant == 10)
     k_fused_sm<3, true, 0, 3, true><<<grid, FT, 0, st>>>(P, a);   // hints three iterations ahead
+  else if (variant == 11)
+    k_fused_sm<3, true, 0, 12, true><<<grid, FT, 0, st>>>(P, a);  // + the next list as a whole into L2 a pass ahead (measured: slower)
   else
     k_fused_sm<3, true, 0, 2, true><<<grid, FT, 0, st>>>(P, a);
 }
