@@ -123,6 +123,29 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank to the CPUs next to its GPU before the pinned host buffers of the e2e leg are allocated (first touch
+    decides the NUMA node): with 8 ranks each moving 26 GB per step through host memory, buffers on the far socket halve the
+    PCIe rate.  Returns the CPU list, or None if the topology cannot be read."""
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                                      text=True, stderr=subprocess.DEVNULL).strip().lower()
+        dom, rest = bus.split(":", 1)
+        with open("/sys/bus/pci/devices/%s:%s/local_cpulist" % (dom[-4:], rest)) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return txt
+    except Exception:
+        pass
+    return None
+
+
 def cpu_reference_rate(steps, warmup, rows=32, nx=NX, ppc=PPC):
     """The CPU oracle (timing build, all host threads) on a bounded sample of the workload:
     same nx, ppc, physics and IC recipe, `rows` rows instead of 512 per GPU."""
@@ -185,6 +208,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-interval", type=int, default=50, help="also time wm_host_steps over this many steps per upload/download")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-affinity", action="store_true", help="N > 1: do not pin the ranks to the CPUs next to their GPUs")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exact", action="store_true", help="bit-exact push arithmetic (WM_FLAG_EXACT_PUSH)")
     args = ap.parse_args()
@@ -210,6 +234,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local) if (world > 1 and not args.no_affinity) else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -342,6 +367,7 @@ def main():
             e2e = {"value": n_total * args.e2e_steps / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                    "api": "wm_host_step(up, uf, np2, cumcnt): pinned host arrays in the reference's Fortran layout",
+                   "cpu_affinity_rank0": numa,
                    "note": "every step moves the whole state over PCIe: %.1f GB up, then the step, then %.1f GB down; the two "
                            "transfers of one call cannot overlap (the step lies between them), so ~2 x 13 GB / 55 GB/s bounds "
                            "it" % (h2d / 1e9, d2h / 1e9)}

@@ -28,3 +28,5 @@ run racecheck_recon racecheck -- reconnection 2
 run memcheck_shock memcheck -- shock 3
 run racecheck_shock racecheck -- shock 2
 run initcheck_weibel initcheck -- weibel 2
+run memcheck_cg0 memcheck WM_CG=0 -- weibel 2
+run racecheck_recon_cg racecheck -- reconnection 3
