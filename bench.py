@@ -354,7 +354,13 @@ def main():
             uf_t = torch.empty(int(np.prod(ctx.shape_uf())), dtype=torch.float64, pin_memory=True)
             up = up_t.numpy().reshape(shape_up)
             uf = uf_t.numpy().reshape(ctx.shape_uf())
-            _, np2, cum = ctx.download_particles(up)
+            _, np2_d, cum_d = ctx.download_particles(up)
+            # the index arrays are pinned as well: a copy from or to pageable memory blocks the host thread that feeds the pipeline
+            np2_t = torch.empty(np2_d.size, dtype=torch.int32, pin_memory=True)
+            cum_t = torch.empty(cum_d.size, dtype=torch.int32, pin_memory=True)
+            np2, cum = np2_t.numpy().reshape(np2_d.shape), cum_t.numpy().reshape(cum_d.shape)
+            np2[...], cum[...] = np2_d, cum_d
+            del np2_d, cum_d
             uf[...] = ctx.download_field()
             h2d = d2h = int(np2.sum()) * 48 + uf.nbytes + np2.nbytes + cum.nbytes
             ctx.host_step(up, uf, np2, cum)  # warm-up
@@ -368,9 +374,11 @@ def main():
                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                    "api": "wm_host_step(up, uf, np2, cumcnt): pinned host arrays in the reference's Fortran layout",
                    "cpu_affinity_rank0": numa,
-                   "note": "every step moves the whole state over PCIe: %.1f GB up, then the step, then %.1f GB down; the two "
-                           "transfers of one call cannot overlap (the step lies between them), so ~2 x 13 GB / 55 GB/s bounds "
-                           "it" % (h2d / 1e9, d2h / 1e9)}
+                   "host_pipe_chunks": ctx.host_pipe_chunks(),
+                   "note": "every step moves the whole state over PCIe, %.1f GB up and %.1f GB down; the rows travel in chunks of "
+                           "WM_HOSTPIPE_ROWS (default 16) rows, upload of the next chunks / particle pass / download of the finished "
+                           "rows side by side: bounded by ~13 GB / 45 GB/s of full-duplex PCIe Gen5 (measured, "
+                           "scripts/micro/pcie_duplex.py) instead of 2 x 13 GB / 55 GB/s" % (h2d / 1e9, d2h / 1e9)}
             # how the shim is meant to be used: host arrays refreshed every intvl_mom = 50 steps (WM_SYNC_INTERVAL=50)
             if args.e2e_interval > 1:
                 barrier()

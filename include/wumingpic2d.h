@@ -150,6 +150,11 @@ int wm_host_step(wm_ctx *ctx, double *up, double *uf, int32_t *np2, int32_t *cum
  * WM_SYNC_INTERVAL = n (host arrays refreshed every n-th sort__bucket; the sample config's intvl_mom is 50, i.e. the driver
  * looks at up/uf every 50 steps, proj/weibel/config_sample.json, proj/weibel/app.f90:109-126). */
 int wm_host_steps(wm_ctx *ctx, double *up, double *uf, int32_t *np2, int32_t *cumcnt, int32_t nsteps);
+/* wm_host_step moves the rows in chunks (WM_HOSTPIPE_ROWS rows, default 16): the upload of the next chunks, the particle pass
+ * over the chunk that has arrived and the download of the rows that are final run side by side (PCIe is full duplex), the
+ * field solve beside the last downloads.  Same kernels and results as upload + wm_step + download; WM_HOSTPIPE=0 selects that
+ * sequence.  Returns the number of chunks of the last wm_host_step (0 = it ran unpipelined). */
+int wm_host_pipe_chunks(const wm_ctx *ctx);
 /* particle__solv(gp,up,uf,cumcnt,nxs,nxe)   common/particle.f90:48 */
 int wm_host_particle__solv(wm_ctx *ctx, double *gp, const double *up, const double *uf,
                            const int32_t *cumcnt, const int32_t *np2);

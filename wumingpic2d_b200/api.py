@@ -50,7 +50,7 @@ EXPORTS = [
     "wm_particle_counts", "wm_particle__solv", "wm_field__ele_cur", "wm_boundary__curre",
     "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_boundary__injection",
     "wm_set_u_inject", "wm_set_xrange", "wm_append_particles", "wm_sort__bucket",
-    "wm_step", "wm_host_step", "wm_host_steps", "wm_loopback_create", "wm_loopback_destroy", "wm_comm_init_loopback", "wm_cg_path", "wm_cg_plan", "wm_fp64_peak", "wm_ic_harris", "wm_ic_shock", "wm_shock_inject", "wm_shock_relocate", "wm_xrange", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
+    "wm_step", "wm_host_step", "wm_host_steps", "wm_host_pipe_chunks", "wm_loopback_create", "wm_loopback_destroy", "wm_comm_init_loopback", "wm_cg_path", "wm_cg_plan", "wm_fp64_peak", "wm_ic_harris", "wm_ic_shock", "wm_shock_inject", "wm_shock_relocate", "wm_xrange", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
     "wm_energy", "wm_gauss_residual", "wm_moments", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_ic_weibel", "wm_timing", "wm_synchronize", "wm_layout_rebuilds",
 ]
 
@@ -118,6 +118,7 @@ def load_library():
     lib.wm_append_particles.argtypes = [P, C.c_int32, C.c_int64, D]
     lib.wm_host_step.argtypes = [P, D, D, I32, I32]
     lib.wm_host_steps.argtypes = [P, D, D, I32, I32, C.c_int32]
+    lib.wm_host_pipe_chunks.argtypes = [P]
     lib.wm_host_particle__solv.argtypes = [P, D, D, D, I32, I32]
     lib.wm_host_sort__bucket.argtypes = [P, D, D, I32, I32]
     lib.wm_cg_iters.argtypes = [P, I32]
@@ -305,6 +306,10 @@ class Context:
     # ---- host-array (drop-in) calls
     def host_step(self, up, uf, np2, cumcnt):
         self._ck(self.lib.wm_host_step(self.h, _d(up), _d(uf), _i(np2), _i(cumcnt)))
+
+    def host_pipe_chunks(self):
+        """chunks of the last host_step (0 = upload, step, download one after the other)"""
+        return int(self.lib.wm_host_pipe_chunks(self.h))
 
     def host_steps(self, up, uf, np2, cumcnt, nsteps):
         self._ck(self.lib.wm_host_steps(self.h, _d(up), _d(uf), _i(np2), _i(cumcnt), nsteps))

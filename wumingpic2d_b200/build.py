@@ -14,7 +14,7 @@ OUT = os.path.join(HERE, "libwumingpic2d.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # field kernels keep the reference's unfused operation order; particle kernels use FMA
-UNITS = [("fused_kernel.cu", []), ("fused5_kernel.cu", []), ("fused6_kernel.cu", []), ("particle_kernels.cu", []), ("gen_kernels.cu", []), ("field_kernels.cu", ["-fmad=false"]), ("cg_persist_kernel.cu", ["-fmad=false"]), ("wm_api.cu", [])]
+UNITS = [("fused_kernel.cu", []), ("fused5_kernel.cu", []), ("fused6_kernel.cu", []), ("particle_kernels.cu", []), ("gen_kernels.cu", []), ("hostpipe_kernels.cu", []), ("field_kernels.cu", ["-fmad=false"]), ("cg_persist_kernel.cu", ["-fmad=false"]), ("wm_api.cu", [])]
 
 
 def source_hash():

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
   __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x;
-  const int tile = blockIdx.x;
+  const int tile = blockIdx.x + a.tile0;
   const int li0 = (tile % P.ntx) * TX, lj0 = (tile / P.ntx) * TY;
   const int tw = min(TX, P.nx - li0), th = min(TY, P.nyl - lj0);
 
@@ -821,8 +821,8 @@ __global__ void __launch_bounds__(FT, MINB) k_fused_sm(const DevParams P, const 
 
 bool fused_sm_has_tail(int variant) { return variant != 3; }
 
-void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaStream_t st) {
-  const int grid = P.ntx * P.nty;
+void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaStream_t st, int ntiles) {
+  const int grid = ntiles > 0 ? ntiles : P.ntx * P.nty;  // (a.tile0 = the first one)
   if (P.bc == WM_BC_SHOCK)
     k_fused_sm<3, true, 2, 2, true><<<grid, FT, 0, st>>>(P, a);
   else if (P.bc == WM_BC_RECONNECTION)

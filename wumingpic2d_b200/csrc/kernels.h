@@ -40,17 +40,25 @@ void launch_check_counts(const int *cnt, int n, const int lim[4], unsigned *err,
 // rim_only: k_fused_sm<TAIL> served the tile's own cells, only the window rim is left (k_place_rim)
 void launch_place(const DevParams &P, const double *stage, const uint32_t *tag, const PartSoA &dst, const int *cstart,
                   int *cnt_new, const int *tilebase, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
-                  bool rim_only, cudaStream_t st);
+                  bool rim_only, cudaStream_t st, int tile0 = 0, int ntiles = 0);
 // does launch_fused_sm(variant) place the in-tile cell changers itself?
 bool fused_sm_has_tail(int variant);
 void launch_clamp_counts(const DevParams &P, const int *cstart, int *cnt, cudaStream_t st, const int *cntb = nullptr);
+// pipelined host step (hostpipe_kernels.cu): the reference's cumcnt on the device, layout changes by row range
+void launch_cum_to_counts(const DevParams &P, const int *cum, const int *np2, int *cnt, unsigned *err, cudaStream_t st);
+void launch_rows_from_aos(const DevParams &P, const double *rec, int n, int isp, int ra, int rb, const int *rowoff, int base, const int *cum,
+                          const int *cstart, const PartSoA &dst, unsigned *err, cudaStream_t st);
+void launch_mark_gaps_rows(const DevParams &P, PView<double> x, const int *cstart, const int *cnt, int ra, int rb, cudaStream_t st);
+void launch_rows_cumcnt(const DevParams &P, const int *cnt, int ra, int rb, int *cum, int *rowoff, cudaStream_t st);
+void launch_rows_to_aos(const DevParams &P, const PartSoA &src, int ra, int rb, const int *cstart, const int *cnt, const int *cum,
+                        const int *rowoff, double *rec, int reccap, unsigned *err, cudaStream_t st);
 void launch_mark_gaps(const DevParams &P, PView<double> x, const int *cstart, const int *cnt, cudaStream_t st);
 void launch_nbr_max(const DevParams &P, const int *in, int *out, int r, cudaStream_t st);
 void launch_mark_dead(const DevParams &P, PView<double> x, const int *cstart, const int *cnt_old, int *cnt_new, cudaStream_t st);
 // fused push + deposit + boundaries that moves cell changers itself (no tags, no scatter pass)
 void launch_fused_inplace(const DevParams &P, const Pass1Args &a, cudaStream_t st);
 // k_fused<INPLACE> with the deposit split into stayers (21 sums, in the loop) and movers (queued, drained per cell) (fused5_kernel.cu)
-void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaStream_t st);
+void launch_fused_sm(const DevParams &P, const Pass1Args &a, int variant, cudaStream_t st, int ntiles = 0);
 // push + deposit + boundaries + sort with direct placement of the cell changers: reads a.src, writes a.dst (fused6_kernel.cu)
 void launch_fused_dp(const DevParams &P, const Pass1Args &a, cudaStream_t st);
 void launch_place_rim2(const DevParams &P, const uint32_t *tag, const PartSoA &dst, const int *cstart, int *cnt_new, const int *cntb_new,

@@ -1101,12 +1101,12 @@ __global__ void __launch_bounds__(PR_THREADS) k_place_rim(const DevParams P, con
                                                           const uint32_t *__restrict__ tag, const PartSoA dst,
                                                           const int *__restrict__ cstart, int *cnt_new,
                                                           const int *__restrict__ tilebase, double *ovf, int *ovfsp, int *ovfcnt,
-                                                          int ovfcap, unsigned *err) {
+                                                          int ovfcap, unsigned *err, int tile0) {
   __shared__ int s_base[WM_NSP_MAX * WIN], s_end[WM_NSP_MAX * WIN];
   __shared__ int s_roff[WM_NSP_MAX * PL_NQ], s_rcnt[WM_NSP_MAX * PL_NQ];
   __shared__ int2 s_list[(PR_THREADS / 32) * 2 * PR_RB * 32];
   static_assert(PL_NQ % PR_RB == 0, "regions in flight never straddle the species");
-  const int tid = threadIdx.x, tile = blockIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, tile = blockIdx.x + tile0, wid = tid >> 5, lane = tid & 31;
   const int li0 = (tile % P.ntx) * TX, lj0 = (tile / P.ntx) * TY;
   const int tw = min(TX, P.nx - li0), th = min(TY, P.nyl - lj0);
   const int *tb = tilebase + (size_t)tile * P.nsp * (2 * WIN);
@@ -1346,10 +1346,10 @@ void launch_check_counts(const int *cnt, int n, const int lim[4], unsigned *err,
 }
 void launch_place(const DevParams &P, const double *stage, const uint32_t *tag, const PartSoA &dst, const int *cstart,
                   int *cnt_new, const int *tilebase, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
-                  bool rim_only, cudaStream_t st) {
+                  bool rim_only, cudaStream_t st, int tile0, int ntiles) {
   if (rim_only) {
-    k_place_rim<<<P.ntx * P.nty, PR_THREADS, 0, st>>>(P, reinterpret_cast<const double2 *>(stage), tag, dst, cstart, cnt_new,
-                                                      tilebase, ovf, ovfsp, ovfcnt, ovfcap, err);
+    k_place_rim<<<ntiles > 0 ? ntiles : P.ntx * P.nty, PR_THREADS, 0, st>>>(P, reinterpret_cast<const double2 *>(stage), tag, dst, cstart, cnt_new,
+                                                      tilebase, ovf, ovfsp, ovfcnt, ovfcap, err, tile0);
     return;
   }
   k_place<<<P.ntx * P.nty, PL_THREADS, 0, st>>>(P, reinterpret_cast<const double2 *>(stage), tag, dst, cstart, cnt_new, tilebase,

@@ -115,6 +115,7 @@ struct Pass1Args {
   int sendcap;
   unsigned *err;
   double delt_push;         // delt (push) or delt/2 (mom_calc__accl)
+  int tile0;                // k_fused_sm: first tile of this launch (row-range launches of the pipelined host step; 0 = whole slab)
 };
 
 #ifdef __CUDACC__
