@@ -65,6 +65,12 @@ module wm_cabi
        character(kind=c_char), intent(in) :: id128(128)
        integer(c_int) :: ierr
      end function wm_comm_init
+     function wm_host_register(ptr, bytes) bind(C, name='wm_host_register') result(ierr)
+       import :: c_int, c_ptr, c_size_t
+       type(c_ptr), value :: ptr
+       integer(c_size_t), value :: bytes
+       integer(c_int) :: ierr
+     end function wm_host_register
      function wm_upload_particles_sorted(ctx, up, np2, cumcnt) bind(C, name='wm_upload_particles_sorted') result(ierr)
        import :: c_int, c_ptr, c_double, c_int32_t
        type(c_ptr), value :: ctx
@@ -266,6 +272,17 @@ contains
   subroutine wm_shim__mark_host_dirty()
     host_dirty = .true.
   end subroutine wm_shim__mark_host_dirty
+
+  !> optional, once after the allocation of the particle arrays (proj/weibel/app.f90:74-82): page-lock them, so that the copies
+  !! of the sync steps run asynchronously at the full PCIe rate (wm_host_register; pageable memory is staged at about half of it)
+  subroutine wm_shim__pin_host(up, gp)
+    real(c_double), intent(in), target :: up(*), gp(*)
+    integer(c_size_t) :: bytes
+    bytes = 8_c_size_t * int(cfg%ndim, c_size_t) * int(cfg%np, c_size_t) &
+          * int(cfg%nye - cfg%nys + 1, c_size_t) * int(cfg%nsp, c_size_t)
+    call wm_check(wm_host_register(c_loc(up), bytes), 'wm_host_register(up)')
+    call wm_check(wm_host_register(c_loc(gp), bytes), 'wm_host_register(gp)')
+  end subroutine wm_shim__pin_host
 
   !> host -> device, if needed.  np2(j,isp) = cumcnt(nxge+1,j,isp) by construction (common/sort.f90:64-69)
   subroutine wm_shim__upload_if_dirty(up, uf, cumcnt)

@@ -28,6 +28,7 @@
 #ifndef WUMINGPIC2D_H
 #define WUMINGPIC2D_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -155,6 +156,12 @@ int wm_host_steps(wm_ctx *ctx, double *up, double *uf, int32_t *np2, int32_t *cu
  * field solve beside the last downloads.  Same kernels and results as upload + wm_step + download; WM_HOSTPIPE=0 selects that
  * sequence.  Returns the number of chunks of the last wm_host_step (0 = it ran unpipelined). */
 int wm_host_pipe_chunks(const wm_ctx *ctx);
+/* Page-lock a host array the calls above copy from / to (cudaHostRegister), so that the copies run at the full PCIe rate and
+ * asynchronously: the reference's allocatables up, gp, uf, cumcnt (proj/weibel/app.f90:74-82) are pageable.  Once per array
+ * after its allocation; registering an array twice is not an error.  Without it everything still works, the copies are
+ * staged by the driver (about half the rate, and the pipelined wm_host_step cannot overlap them). */
+int wm_host_register(void *ptr, size_t bytes);
+int wm_host_unregister(void *ptr);
 /* particle__solv(gp,up,uf,cumcnt,nxs,nxe)   common/particle.f90:48 */
 int wm_host_particle__solv(wm_ctx *ctx, double *gp, const double *up, const double *uf,
                            const int32_t *cumcnt, const int32_t *np2);

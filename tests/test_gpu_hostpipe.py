@@ -174,3 +174,24 @@ def test_pipelined_host_step_ring_loopback(monkeypatch):
             raise AssertionError("rank %d: %r" % (r, e)) from e
     assert all(not t.is_alive() for t in th)
     w.close()
+
+
+def test_host_register_pageable_arrays(monkeypatch):
+    """wm_host_register page-locks the caller's (numpy = pageable) arrays: same results, registering twice is not an error"""
+    import wumingpic2d_b200 as wm
+    from wumingpic2d_b200.api import host_register, host_unregister
+    monkeypatch.setenv("WM_HOSTPIPE_ROWS", "8")
+    prm, w = make_world(40, 24, 8)
+    s = oracle_state(w)
+    c = wm.Context.from_params(prm)
+    up, uf, np2, cum = s["up"].copy(), s["uf"].copy(), s["np2"].copy(), s["cumcnt"].copy()
+    for a in (up, uf, np2, cum, up):
+        host_register(a)
+    for it in range(2):
+        w.step(1)
+        c.host_step(up, uf, np2, cum)
+        _check_against(w, prm, up, uf, np2, cum, tol=1e-12 if it == 0 else 1e-10)
+    for a in (up, uf, np2, cum):
+        host_unregister(a)
+    c.close()
+    w.close()
