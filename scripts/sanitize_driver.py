@@ -29,8 +29,24 @@ def main():
         prm, w = make_wall_world(40, 19, 8)
     elif kind == "shock":
         prm, w = make_shock_world(40, 19, 8, u0=-0.3)
+    elif kind == "hostpipe":
+        # the pipelined wm_host_step: six chunks of one tile row (the last one ragged), row-range kernels, four streams
+        os.environ["WM_HOSTPIPE_ROWS"] = "8"
+        prm, w = make_world(48 + 8, 44, 10)
+        c = wm.Context.from_params(prm, device=0)
+        up, uf = w.array(0, O.UP).copy(), w.array(0, O.UF).copy()
+        np2, cum = w.array(0, O.NP2).copy(), w.array(0, O.CUMCNT).copy()
+        for _ in range(nsteps):
+            w.step(1)
+            c.host_step(up, uf, np2, cum)
+            assert c.host_pipe_chunks() == 6
+            assert np.array_equal(cum, w.array(0, O.CUMCNT)) and np.array_equal(np2, w.array(0, O.NP2)), "per-cell counts differ from the oracle"
+        print("sanitize_driver hostpipe: %d steps ok" % nsteps)
+        c.close()
+        w.close()
+        return
     else:
-        raise SystemExit("kind: weibel | reconnection | shock")
+        raise SystemExit("kind: weibel | reconnection | shock | hostpipe")
     c = wm.Context.from_params(prm, device=0)
     if kind == "shock":
         c.set_u_inject(-0.3)

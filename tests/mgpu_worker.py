@@ -64,6 +64,35 @@ def main():
     assert np.allclose(e.cpu().numpy(), w.energy(), rtol=1e-10, atol=0)
     ctx.close()
     w.close()
+    # ---- the pipelined host step (wm_host_step: rows in chunks, upload / pass / download side by side) on the ring: the leavers
+    #      of the edge rows cross to the neighbour GPUs at the end of the pass, the CG exchanges inside k_cg_persist
+    if os.environ.get("WM_INPLACE") != "0":
+        os.environ["WM_HOSTPIPE_ROWS"] = "8"
+        prm = O.weibel_params(40, 24 * world + 3, 10, nranks=world)
+        w = O.World(prm)
+        w.ic_weibel(20260117)
+        nys, nye = w.bounds(rank)
+        ctx = wm.Context.from_params(prm, nys=nys, nye=nye, nrank=rank, nsize=world, device=local)
+        ids = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0])
+        up, uf = w.array(rank, O.UP).copy(), w.array(rank, O.UF).copy()
+        np2, cum = w.array(rank, O.NP2).copy(), w.array(rank, O.CUMCNT).copy()
+        for it in range(4):
+            w.step(1)
+            ctx.host_step(up, uf, np2, cum)
+            assert ctx.host_pipe_chunks() >= 3, ctx.host_pipe_chunks()
+            assert ctx.cg_iters() == w.cg_iters(), (ctx.cg_iters(), w.cg_iters())
+            assert np.array_equal(np2, w.array(rank, O.NP2)) and np.array_equal(cum, w.array(rank, O.CUMCNT)), \
+                "host step: counts differ on rank %d step %d" % (rank, it)
+            a, b = flatten_by_id(up, np2), flatten_by_id(w.array(rank, O.UP), w.array(rank, O.NP2))
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+            ex, eu = particle_err(a[2], b[2], prm["nx"], prm["vte"])
+            tol = 1e-12 if it == 0 else 1e-10
+            assert ex <= tol and eu <= tol, ("host step", it, ex, eu)
+            assert rel_to_max(uf, w.array(rank, O.UF)).max() <= tol
+        ctx.close()
+        w.close()
     # ---- the wall boundary modules on the ring: reconnection (reflecting / conducting walls) and shock (injection wall,
     #      bc__injection before the deposit), both periodic in y over the ranks
     from helpers import make_shock_world, make_wall_world

@@ -195,3 +195,23 @@ def test_host_register_pageable_arrays(monkeypatch):
         host_unregister(a)
     c.close()
     w.close()
+
+
+def test_pipelined_host_step_with_overflowing_segments(monkeypatch):
+    """hardly any segment slack: segments overflow inside a pipelined step, the parked records are not in the rows that have
+    already gone back -> the layout is rebuilt and everything is fetched again (correct, slow)"""
+    import wumingpic2d_b200 as wm
+    monkeypatch.setenv("WM_HOSTPIPE_ROWS", "8")
+    monkeypatch.setenv("WM_SLACK", "0.01")
+    prm, w = make_world(40, 40, 17)
+    s = oracle_state(w)
+    c = wm.Context.from_params(prm)
+    up, uf, np2, cum = s["up"].copy(), s["uf"].copy(), s["np2"].copy(), s["cumcnt"].copy()
+    for it in range(6):
+        w.step(1)
+        c.host_step(up, uf, np2, cum)
+        assert c.host_pipe_chunks() == 5
+        _check_against(w, prm, up, uf, np2, cum, tol=1e-12 if it == 0 else 1e-9)
+    assert c.rebuilds() > 0, "the overflow branch was not exercised"
+    c.close()
+    w.close()
