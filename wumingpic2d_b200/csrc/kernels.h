@@ -30,8 +30,8 @@ void launch_relayout_from_aos(const DevParams &P, const double *rec, long long n
                               const PartSoA &dst, size_t so, unsigned *err, cudaStream_t st);
 void launch_relayout_to_aos(const DevParams &P, const PartSoA &key, const PartSoA &val, size_t so, const int *cstart_src,
                             const int *tight, double *rec, cudaStream_t st);
-void launch_relayout_soa(const DevParams &P, const PartSoA &src, const int *cstart_src, const PartSoA &dst,
-                         const int *cstart_dst, size_t so, unsigned *err, cudaStream_t st);
+void launch_relayout_soa(const DevParams &P, const PartSoA &src, const int *cstart_src, const int *cnt_src, const PartSoA &dst,
+                         const int *cstart_dst, unsigned *err, cudaStream_t st);
 void launch_incoming_append(const DevParams &P, const double *rec, int n, int isp, const int *cstart, int *cnt_tail,
                             const PartSoA &dst, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
                             cudaStream_t st, const int *n_dev = nullptr, const int *cntb = nullptr);

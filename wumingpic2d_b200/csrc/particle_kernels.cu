@@ -906,26 +906,31 @@ __global__ void k_relayout_to_aos(const DevParams P, const PartSoA key, const Pa
   }
 }
 
-// segments -> segments with different offsets (layout rebuild); dst.x must be dead-filled
-__global__ void k_relayout_soa(const DevParams P, const PartSoA src, const int *__restrict__ cstart_src, const PartSoA dst,
-                               const int *__restrict__ cstart_dst, size_t so, unsigned *err) {
-  const int span = cstart_src[P.ncell];
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < span; p += gridDim.x * blockDim.x) {
-    const double x = src.x[so + p];
-    if (!slot_live(x)) continue;
-    const double y = src.y[so + p];
-    const int cell = cell_of(P, x, y);
-    if ((long long)cstart_dst[cell] + (p - cstart_src[cell]) >= P.cap) {
-      atomicOr(err, ERR_CAPACITY);
+// segments -> segments with different offsets (layout rebuild), all species in one launch.  Count-driven: a warp copies the
+// cnt live records at the front of a segment (the in-place sort keeps them compact), so the cost follows the particle
+// number, not the span of the store (the shock run holds 35 M particles per species in 537 M slots).
+__global__ void k_relayout_soa(const DevParams P, const PartSoA src, const int *__restrict__ cstart_src, const int *__restrict__ cnt_src,
+                               const PartSoA dst, const int *__restrict__ cstart_dst, unsigned *err) {
+  const long long n = (long long)P.nsp * P.ncell;
+  const int lane = threadIdx.x & 31;
+  for (long long wk = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wk < n; wk += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int isp = (int)(wk / P.ncell), cell = (int)(wk - (long long)isp * P.ncell);
+    const int m = cnt_src[wk];
+    if (m <= 0) continue;
+    const size_t so = (size_t)isp * P.cap;
+    const int s0 = cstart_src[(size_t)isp * (P.ncell + 1) + cell];
+    const int d0 = cstart_dst[(size_t)isp * (P.ncell + 1) + cell], d1 = cstart_dst[(size_t)isp * (P.ncell + 1) + cell + 1];
+    if ((long long)d0 + m > P.cap || d0 + m > d1) {
+      if (lane == 0) atomicOr(err, ERR_CAPACITY);
       continue;
     }
-    const size_t o = so + (size_t)cstart_dst[cell] + (p - cstart_src[cell]);
-    dst.x[o] = x;
-    dst.y[o] = y;
-    dst.ux[o] = src.ux[so + p];
-    dst.uy[o] = src.uy[so + p];
-    dst.uz[o] = src.uz[so + p];
-    dst.id[o] = src.id[so + p];
+    for (int k = lane; k < m; k += 32) {
+      const double2 *w = src.word(so + (size_t)s0 + k);
+      double2 *o = dst.word(so + (size_t)d0 + k);
+      o[0] = w[0];
+      o[8] = w[8];
+      o[16] = w[16];
+    }
   }
 }
 
@@ -1326,9 +1331,9 @@ void launch_relayout_to_aos(const DevParams &P, const PartSoA &key, const PartSo
                             const int *tight, double *rec, cudaStream_t st) {
   k_relayout_to_aos<<<148 * 16, 256, 0, st>>>(P, key, val, so, cstart_src, tight, rec);
 }
-void launch_relayout_soa(const DevParams &P, const PartSoA &src, const int *cstart_src, const PartSoA &dst,
-                         const int *cstart_dst, size_t so, unsigned *err, cudaStream_t st) {
-  k_relayout_soa<<<148 * 16, 256, 0, st>>>(P, src, cstart_src, dst, cstart_dst, so, err);
+void launch_relayout_soa(const DevParams &P, const PartSoA &src, const int *cstart_src, const int *cnt_src, const PartSoA &dst,
+                         const int *cstart_dst, unsigned *err, cudaStream_t st) {
+  k_relayout_soa<<<148 * 16, 256, 0, st>>>(P, src, cstart_src, cnt_src, dst, cstart_dst, err);
 }
 void launch_incoming_append(const DevParams &P, const double *rec, int n, int isp, const int *cstart, int *cnt_tail,
                             const PartSoA &dst, double *ovf, int *ovfsp, int *ovfcnt, int ovfcap, unsigned *err,
