@@ -57,15 +57,45 @@ def weibel_params(nx, ny, n_ppc, cap_factor=1.25):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons of this rank's GPU DURING the timed region (B200_PROFILING.md): NVML polled every 5 ms by a
+    thread of this process (nvidia-smi needs longer to start on an 8-GPU box than 20 steps take); `nvidia-smi -lms` as the
+    fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.index, self.lines, self.p = index, [], None
+        self.index, self.lines, self.p, self.h, self.nv = index, [], None, None, None
+        self.sm, self.mask, self.mx, self.stop_flag = [], 0, None, False
+        try:  # the handle is opened before the timed region; by UUID, so that CUDA_VISIBLE_DEVICES does not matter
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(index).uuid))
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self.h is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "100"],
@@ -80,6 +110,12 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.h is not None:
+            self.stop_flag = True
+            self.t.join(timeout=2)
+            sm = sorted(self.sm)
+            return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": self.mx, "samples": len(sm),
+                    "reasons": [n for b, n in self.REASONS if self.mask & b], "source": "nvml, every 5 ms inside the timed region"}
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -104,7 +140,7 @@ class ClockSampler:
         # under load = upper half of the samples (the region is short; idle samples bracket it)
         load = sm[len(sm) // 2:] if sm else []
         return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": mx,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 def workload_config(nx, rows, ppc, world):
