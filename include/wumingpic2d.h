@@ -156,6 +156,10 @@ int wm_host_steps(wm_ctx *ctx, double *up, double *uf, int32_t *np2, int32_t *cu
  * field solve beside the last downloads.  Same kernels and results as upload + wm_step + download; WM_HOSTPIPE=0 selects that
  * sequence.  Returns the number of chunks of the last wm_host_step (0 = it ran unpipelined). */
 int wm_host_pipe_chunks(const wm_ctx *ctx);
+/* The order of work of the pipelined call over a slab of nyl rows in chunks of `rows` rows, as triples (kind, a, b): 0 = push
+ * tile rows [a,b) (tile row = 8 rows), 1 = place the rim arrivals of tile rows [a,b), 2 = rows [a,b) are final and go back,
+ * 3 = the ring exchange.  Returns the number of triples (or -needed if max_ops is too small).  No device needed. */
+int wm_host_pipe_plan(int32_t nyl, int32_t rows, int32_t *ops, int32_t max_ops);
 /* Page-lock a host array the calls above copy from / to (cudaHostRegister), so that the copies run at the full PCIe rate and
  * asynchronously: the reference's allocatables up, gp, uf, cumcnt (proj/weibel/app.f90:74-82) are pageable.  Once per array
  * after its allocation; registering an array twice is not an error.  Without it everything still works, the copies are

@@ -50,7 +50,7 @@ EXPORTS = [
     "wm_particle_counts", "wm_particle__solv", "wm_field__ele_cur", "wm_boundary__curre",
     "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y", "wm_boundary__injection",
     "wm_set_u_inject", "wm_set_xrange", "wm_append_particles", "wm_sort__bucket",
-    "wm_step", "wm_host_step", "wm_host_steps", "wm_host_pipe_chunks", "wm_host_register", "wm_host_unregister", "wm_loopback_create", "wm_loopback_destroy", "wm_comm_init_loopback", "wm_cg_path", "wm_cg_plan", "wm_fp64_peak", "wm_ic_harris", "wm_ic_shock", "wm_shock_inject", "wm_shock_relocate", "wm_xrange", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
+    "wm_step", "wm_host_step", "wm_host_steps", "wm_host_pipe_chunks", "wm_host_pipe_plan", "wm_host_register", "wm_host_unregister", "wm_loopback_create", "wm_loopback_destroy", "wm_comm_init_loopback", "wm_cg_path", "wm_cg_plan", "wm_fp64_peak", "wm_ic_harris", "wm_ic_shock", "wm_shock_inject", "wm_shock_relocate", "wm_xrange", "wm_host_particle__solv", "wm_host_sort__bucket", "wm_cg_iters",
     "wm_energy", "wm_gauss_residual", "wm_moments", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_ic_weibel", "wm_timing", "wm_synchronize", "wm_layout_rebuilds",
 ]
 
@@ -119,6 +119,7 @@ def load_library():
     lib.wm_host_step.argtypes = [P, D, D, I32, I32]
     lib.wm_host_steps.argtypes = [P, D, D, I32, I32, C.c_int32]
     lib.wm_host_pipe_chunks.argtypes = [P]
+    lib.wm_host_pipe_plan.argtypes = [C.c_int32, C.c_int32, I32, C.c_int32]
     lib.wm_host_register.argtypes = [C.c_void_p, C.c_size_t]
     lib.wm_host_unregister.argtypes = [C.c_void_p]
     lib.wm_host_particle__solv.argtypes = [P, D, D, D, I32, I32]
@@ -153,6 +154,17 @@ def cg_plan(nx, nyl, nsm=148, smem_max=227 * 1024 - 2048):
     if lib.wm_cg_plan(nx, nyl, nsm, smem_max, out):
         raise WmError(lib.wm_last_error().decode())
     return tuple(out)
+
+
+def host_pipe_plan(nyl, rows=16):
+    """the schedule of a pipelined host step: list of (kind, a, b) -- 'push' / 'place' tile rows [a,b), 'down' rows [a,b), 'ring'"""
+    lib = load_library()
+    buf = np.zeros(3 * (4 * (nyl // 8 + 4) + 8), dtype=np.int32)
+    n = lib.wm_host_pipe_plan(nyl, rows, buf.ctypes.data_as(C.POINTER(C.c_int32)), buf.size // 3)
+    if n < 0:
+        raise WmError("wm_host_pipe_plan(%d, %d) = %d" % (nyl, rows, n))
+    names = ("push", "place", "down", "ring")
+    return [(names[buf[3 * i]], int(buf[3 * i + 1]), int(buf[3 * i + 2])) for i in range(n)]
 
 
 def host_register(a):
