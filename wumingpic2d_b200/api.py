@@ -38,7 +38,8 @@ class WmConfig(C.Structure):
 
 
 def library_path():
-    return os.path.join(HERE, "libwumingpic2d.so")
+    """the in-tree library; WM_LIB selects another build of the same sources (compiler-flag experiments, scripts/build_variants.sh)"""
+    return os.environ.get("WM_LIB") or os.path.join(HERE, "libwumingpic2d.so")
 
 
 _lib = None
