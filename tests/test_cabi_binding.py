@@ -1,0 +1,66 @@
+"""fortran/wm_cabi.f90's interface block against the prototypes of include/wumingpic2d.h (scripts/check_cabi_binding.py): an
+interface block is an unchecked promise about a C function -- a missing VALUE or a wrong integer kind links fine and corrupts
+memory at run time, and no Fortran compiler (absent here anyway) would notice.  Parsed with numpy.f2py's
+crackfortran, so the shim has at least met A Fortran parser.  CPU only."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+
+
+def test_every_bound_function_matches_its_prototype():
+    import check_cabi_binding as B
+    protos, binds = B.c_prototypes(), B.fortran_bindings()
+    bound = [n for n in binds if n.startswith("wm_")]
+    assert len(bound) >= 26 and len(protos) >= 58
+    # the procedures the shim modules call must all be bound
+    for need in ("wm_create", "wm_particle__solv", "wm_field__fdtd_i", "wm_boundary__particle_x", "wm_boundary__particle_y",
+                 "wm_sort__bucket", "wm_mom_calc__accl", "wm_mom_calc__nvt", "wm_boundary__mom", "wm_upload_particles_sorted",
+                 "wm_download_particles", "wm_set_xrange", "wm_boundary__injection", "wm_host_register"):
+        assert need in binds, need
+    assert B.compare(protos, binds) == []
+
+
+def test_the_checker_sees_the_classic_mistakes():
+    import check_cabi_binding as B
+    protos = B.c_prototypes()
+    src = open(B.CABI).read()
+    # (1) a scalar passed by reference instead of by value
+    bad = src.replace("integer(c_int32_t), value :: nsteps", "integer(c_int32_t) :: nsteps", 1)
+    assert bad != src
+    assert any(p.startswith("wm_step:") for p in B.compare(protos, B.fortran_bindings(text=bad)))
+    # (2) the wrong integer kind
+    bad = src.replace("integer(c_int64_t), value :: n", "integer(c_int32_t), value :: n", 1)
+    assert bad != src
+    assert any(p.startswith("wm_append_particles:") for p in B.compare(protos, B.fortran_bindings(text=bad)))
+    # (3) an output array declared intent(in)
+    bad = src.replace("real(c_double), intent(inout)  :: gp(*)", "real(c_double), intent(in)  :: gp(*)", 1)
+    if bad != src:
+        assert any(p.startswith("wm_download_gp:") for p in B.compare(protos, B.fortran_bindings(text=bad)))
+
+
+def test_shim_files_parse():
+    """module and procedure structure of both shim files as a Fortran parser sees it"""
+    import contextlib
+    import io
+    import numpy.f2py.crackfortran as cf
+    cf.verbose = 0
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(buf):
+        blocks = cf.crackfortran([os.path.join(ROOT, "fortran", "wm_shim_modules.f90")])
+    mods = {b["name"]: [x["name"] for x in b["body"] if x.get("block") in ("subroutine", "function")] for b in blocks if b.get("block") == "module"}
+    assert set(mods) == {"particle", "field", "sort", "boundary_periodic", "mom_calc", "boundary_reconnection", "boundary_shock"}
+    assert mods["particle"] == ["particle__init", "particle__solv"]
+    assert mods["sort"] == ["sort__init", "sort__bucket"]
+    assert len(mods["boundary_periodic"]) == 7 and len(mods["boundary_shock"]) == 8
+    assert sum(len(v) for v in mods.values()) == 31
+
+
+def test_call_sites_pass_the_right_number_of_arguments():
+    import check_cabi_binding as B
+    binds = B.fortran_bindings()
+    sites = [s for s in B.call_sites() if s[2] in binds]
+    assert len(sites) >= 30
+    assert B.check_calls(binds, sites) == []
+    assert B.check_calls(binds, [("x.f90", 1, "wm_step", 1)]) != []
