@@ -5,6 +5,10 @@ crackfortran, so the shim has at least met A Fortran parser.  CPU only."""
 import os
 import sys
 
+import pytest
+
+pytestmark = pytest.mark.filterwarnings("ignore")   # (the parser warns about cfg%nye in dimension expressions)
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
 
