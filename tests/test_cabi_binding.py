@@ -68,3 +68,26 @@ def test_call_sites_pass_the_right_number_of_arguments():
     assert len(sites) >= 30
     assert B.check_calls(binds, sites) == []
     assert B.check_calls(binds, [("x.f90", 1, "wm_step", 1)]) != []
+
+
+def test_shim_uses_only_declared_names():
+    """scripts/lint_shim.py: every identifier in the executable part of the shim's 38 procedures is a dummy, a declared local, a
+    module variable / procedure / bound function, an intrinsic or an MPI name"""
+    import lint_shim as L
+    assert L.lint() == []
+
+
+def test_lint_sees_typos():
+    import lint_shim as L
+    texts = {f: open(f).read() for f in L.FILES}
+    cabi, mods = L.FILES
+    bad = dict(texts)
+    bad[cabi] = texts[cabi].replace("    nstep_since_sync = 0\n  end subroutine wm_shim__download", "    nstep_since_sink = 0\n  end subroutine wm_shim__download")
+    assert bad[cabi] != texts[cabi] and any("nstep_since_sink" in p for p in L.lint(texts=bad))
+    bad = dict(texts)
+    bad[mods] = texts[mods].replace("call wm_check(wm_sort__bucket(ctx), 'sort__bucket')", "call wm_check(wm_sort__buckets(ctx), 'sort__bucket')")
+    assert bad[mods] != texts[mods] and any("wm_sort__buckets" in p for p in L.lint(texts=bad))
+    bad = dict(texts)   # a local that lost its declaration (and must not be mistaken for the component cfg%nrank)
+    bad[mods] = texts[mods].replace("    integer :: nerr, nrank, nsize\n    call MPI_COMM_RANK(ncomw_in, nrank, nerr)",
+                                    "    integer :: nerr, nsize\n    call MPI_COMM_RANK(ncomw_in, nrank, nerr)", 1)
+    assert bad[mods] != texts[mods] and any("nrank" in p for p in L.lint(texts=bad))
