@@ -15,7 +15,8 @@ Fortran parser (crackfortran) and the header with a small prototype parser and c
     C  `double` / `int32_t` / `int64_t` / `size_t`        <->  real(c_double) / integer(c_int32_t / c_int64_t / c_size_t), value
     C  return `int`                                       <->  integer(c_int) result
 
-and every call of a bound function in the shim sources passes as many actual arguments as its interface has dummies.
+and every call of a bound function in the shim sources passes as many actual arguments as its interface has dummies; and
+`type, bind(C) :: wm_config` mirrors `struct wm_config` member by member (names, order, kinds, array lengths).
 
     python scripts/check_cabi_binding.py        exit code 0 = every bound function matches its prototype
 """
@@ -201,9 +202,58 @@ def check_calls(binds, sites=None):
     return problems
 
 
+def c_struct_members(text=None, name="wm_config"):
+    """[(C type, member, array length or None)] of `struct name` in the header, in declaration order"""
+    text = text if text is not None else open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    m = re.search(r"typedef\s+struct\s+%s\s*\{(.*?)\}\s*%s\s*;" % (name, name), text, flags=re.S)
+    out = []
+    for st in m.group(1).split(";"):
+        st = " ".join(st.split())
+        if not st:
+            continue
+        typ, rest = st.split(" ", 1)
+        for mem in rest.split(","):
+            mm = re.match(r"\s*(\w+)\s*(?:\[\s*(\w+)\s*\])?", mem)
+            out.append((typ, mm.group(1), mm.group(2)))
+    return out
+
+
+def fortran_type_components(text=None, name="wm_config"):
+    """[(typespec, kind, component, array length or None)] of `type, bind(C) :: name` in wm_cabi.f90, in declaration order"""
+    text = text if text is not None else open(CABI).read()
+    m = re.search(r"^\s*type\s*,\s*bind\s*\(\s*C\s*\)\s*::\s*%s\s*$(.*?)^\s*end\s+type" % name, text, flags=re.S | re.M | re.I)
+    out = []
+    for ln in m.group(1).split("\n"):
+        ln = ln.split("!")[0].strip()
+        if not ln:
+            continue
+        dm = re.match(r"(integer|real)\s*\(\s*(\w+)\s*\)\s*::\s*(.*)$", ln, flags=re.I)
+        for comp in re.findall(r"(\w+)\s*(?:\(\s*(\w+)\s*\))?\s*(?:,|$)", dm.group(3)):
+            out.append((dm.group(1).lower(), dm.group(2).lower(), comp[0], comp[1] or None))
+    return out
+
+
+def compare_struct(cm=None, fm=None):
+    """member by member: the same names in the same order, interoperable kinds, the same array lengths"""
+    cm = cm if cm is not None else c_struct_members()
+    fm = fm if fm is not None else fortran_type_components()
+    problems = []
+    if len(cm) != len(fm):
+        problems.append("wm_config: %d C members, %d Fortran components" % (len(cm), len(fm)))
+    for (ct, cn, cl), (ft, fk, fn, fl) in zip(cm, fm):
+        if cn.lower() != fn.lower():
+            problems.append("wm_config: member %s of the C struct is component %s in Fortran (order matters: bind(C))" % (cn, fn))
+        elif SCALARS.get(ct) != (ft, fk):
+            problems.append("wm_config%%%s: C %s, Fortran %s(%s)" % (fn, ct, ft, fk))
+        elif (cl or "").lower() != (fl or "").lower():
+            problems.append("wm_config%%%s: array length %s in C, %s in Fortran" % (fn, cl, fl))
+    return problems
+
+
 def main():
     protos, binds = c_prototypes(), fortran_bindings()
-    probs = compare(protos, binds) + check_calls(binds)
+    probs = compare(protos, binds) + check_calls(binds) + compare_struct()
     print("%d functions bound in fortran/wm_cabi.f90, %d declared in include/wumingpic2d.h, %d problems"
           % (len([n for n in binds if n.startswith("wm_")]), len(protos), len(probs)))
     for p in probs:

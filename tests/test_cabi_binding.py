@@ -91,3 +91,28 @@ def test_lint_sees_typos():
     bad[mods] = texts[mods].replace("    integer :: nerr, nrank, nsize\n    call MPI_COMM_RANK(ncomw_in, nrank, nerr)",
                                     "    integer :: nerr, nsize\n    call MPI_COMM_RANK(ncomw_in, nrank, nerr)", 1)
     assert bad[mods] != texts[mods] and any("nrank" in p for p in L.lint(texts=bad))
+
+
+def test_wm_config_is_mirrored_member_by_member():
+    """struct wm_config (include/wumingpic2d.h) == type, bind(C) :: wm_config (fortran/wm_cabi.f90) == api.WmConfig (ctypes):
+    names, order, kinds, array lengths -- a mismatch would shift every member behind it"""
+    import ctypes as C
+    import re
+    import check_cabi_binding as B
+    cm, fm = B.c_struct_members(), B.fortran_type_components()
+    assert len(cm) == 21 and B.compare_struct(cm, fm) == []
+    swapped = list(fm)
+    swapped[7], swapped[8] = swapped[8], swapped[7]
+    assert B.compare_struct(cm, swapped) != []
+    assert B.compare_struct(cm, [(t, "c_int64_t" if n == "flags" else k, n, ln) for t, k, n, ln in fm]) != []
+    from wumingpic2d_b200.api import WM_NSP_MAX, WmConfig
+    ctype = {"int32_t": C.c_int32, "double": C.c_double, "int64_t": C.c_int64}
+    want = [(n, ctype[t] * WM_NSP_MAX if ln else ctype[t]) for t, n, ln in cm]
+    assert [(n, t) for n, t in WmConfig._fields_] == want
+    # the enumerators and flags carry the same values on all three sides
+    hdr, f90 = open(B.HEADER).read(), open(B.CABI).read()
+    import wumingpic2d_b200.api as api
+    for name in ("WM_BC_PERIODIC", "WM_BC_RECONNECTION", "WM_BC_SHOCK", "WM_FLAG_EXACT_PUSH", "WM_NSP_MAX"):
+        c_val = int(re.search(r"\b%s\b\s*=?\s*(\d+)" % name, hdr).group(1))
+        f_val = int(re.search(r"\b%s\s*=\s*(\d+)" % name, f90).group(1))
+        assert c_val == f_val == getattr(api, name), name
