@@ -351,8 +351,9 @@ def main():
     # dram__bytes_read.sum + dram__bytes_write.sum and the FP64 pipe utilisation of the same kernel, from the committed
     # `ncu --set full` capture of this workload (profiles/pass1_traffic.json names the report it was read from)
     traffic, fp64_pipe = None, None
-    # FP64 vector peak of this device, measured in this run with a DFMA loop; the kernel executes 209
-    # FP64 instructions per particle (SASS count of the loop, profiles/r01u_tail.md), so its FP64 instruction rate is known live
+    # FP64 vector peak of this device, measured in this run with a DFMA loop; the kernel executes 285
+    # FP64 instructions per particle over the whole launch (DFMA 180 + DMUL 61 + DADD 31 + DSETP 13: executed-instruction
+    # counts of the ncu capture, profiles/r02_fused_sm.md; 209 in the particle loop alone), so its FP64 instruction rate is known live
     try:
         fp64_peak = ctx.fp64_peak()
     except Exception:
@@ -369,7 +370,8 @@ def main():
                 "peak_source": peak_kind, "alg_bytes_per_particle": ALG_BYTES_PASS1, "ms_per_launch": ms_pass1,
                 "fp64_pipe_pct_of_peak_ncu": fp64_pipe,
                 "fp64_peak_tflops_measured": fp64_peak,
-                "fp64_instr_rate_frac_of_measured_peak": (209.0 * n_local / (ms_pass1 * 1e-3) * 2 / 1e12 / fp64_peak) if fp64_peak else None,
+                "fp64_instr_per_particle": 285.0,
+                "fp64_instr_rate_frac_of_measured_peak": (285.0 * n_local / (ms_pass1 * 1e-3) * 2 / 1e12 / fp64_peak) if fp64_peak else None,
                 "note": ("alg_bytes_per_particle = 48 B read + 48 B written per particle (SURVEY 8d); the kernel also does the sort "
                          "of 98 % of the particles (stayers compacted in place, in-tile cell changers staged and appended by the "
                          "CTA's tail: about 13 B/particle more traffic, not counted), which SURVEY 8d books as another 96 B: "
